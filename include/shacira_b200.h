@@ -1,0 +1,162 @@
+/*
+ * shacira_b200.h -- C ABI of the B200-native latent hash-grid hot path.
+ *
+ * One shared library (shacira_b200/libshacira_b200.so, built by shacira_b200/build.py with
+ * nvcc for sm_100a) exports exactly these symbols. There are no torch types in any
+ * signature: plain device pointers, sizes and a CUDA stream handle. The Python host side
+ * (shacira_b200/_lib.py) binds them with ctypes; INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Every entry point
+ *   - returns 0 on success or a negative SHACIRA_ERR_* code (never throws, never aborts);
+ *     shacira_last_error() returns the message of the last failure on the calling thread;
+ *   - launches asynchronously on `stream` (NULL = legacy default stream) on the CURRENT
+ *     device, like the reference (`at::cuda::getCurrentCUDAStream()`,
+ *     wisp/csrc/ops/hashgrid_interpolate2d_cuda.cu:116-118), and is re-entrant;
+ *   - takes `coords` as float32 [n, dim] row-major in [-1, 1], `resolutions` and
+ *     `first_idx` as HOST int32[num_lods] (the reference passes first_idx as a device
+ *     tensor and dereferences it in-kernel; the torch shim caches the host copy);
+ *   - computes in fp32 (the graded path; kodak.yaml disables AMP).
+ *
+ * Level l of the table holds min(2^bitwidth, res_l^dim) rows starting at row first_idx[l]
+ * (wisp/models/grids/latent_grid.py:100-112). Corner index, weights and summation follow
+ * wisp/csrc/ops/hashgrid_interpolate{,2d}_cuda.cu; see DESIGN.md for the exact arithmetic.
+ */
+#ifndef SHACIRA_B200_H_
+#define SHACIRA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHACIRA_ABI_VERSION 1
+#define SHACIRA_MAX_LEVELS 32
+
+#define SHACIRA_OK 0
+#define SHACIRA_ERR_INVALID_ARGUMENT (-1) /* null pointer, bad dim/size/bitwidth ...            */
+#define SHACIRA_ERR_UNSUPPORTED (-2)      /* channel combination without a compiled kernel      */
+#define SHACIRA_ERR_CUDA (-3)             /* a CUDA runtime call or launch failed               */
+#define SHACIRA_ERR_Q2_WINDOW (-4)        /* level where the reference's int32 dense predicate  */
+                                          /* overflows (res^3 wraps): behaviour undefined there */
+#define SHACIRA_ERR_NO_DEVICE (-5)        /* no CUDA device visible                             */
+
+typedef void* shacira_stream_t; /* cudaStream_t */
+
+/* ---- library info ------------------------------------------------------------------- */
+int shacira_abi_version(void);
+const char* shacira_last_error(void);
+/* Number of kernels launched by this library since load (process-wide, all threads). */
+int64_t shacira_launch_count(void);
+/* sm count / L2 bytes / max persisting L2 bytes of the current device. */
+int shacira_device_info(int32_t* sm_count, int64_t* l2_bytes, int64_t* l2_persist_max);
+/* Pin [base, base+bytes) in L2 for kernels subsequently launched on `stream`
+ * (cudaStreamAttributeAccessPolicyWindow, hitRatio clipped to the persisting carve-out).
+ * bytes == 0 clears the window. */
+int shacira_l2_pin(const void* base, int64_t bytes, shacira_stream_t stream);
+
+/* ---- plain hash grid: replaces wisp._C.ops.hashgrid_interpolate{,2d}_cuda ------------- */
+/* hashgrid_interpolate.h:18-23 (3D) and :35-40 (2D); host loops hashgrid_interpolate.cpp:44-66,
+ * 130-152. ALL levels in one launch. feats[n, num_lods*feature_dim], element
+ * [i, lod*feature_dim + j]. feature_dim in {1,2,4,8}. */
+int shacira_hashgrid_forward(int32_t dim, const float* coords, int64_t n, const float* codebook,
+                             const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                             int32_t codebook_bitwidth, int32_t feature_dim, float* feats, shacira_stream_t stream);
+
+/* hashgrid_interpolate.h:25-33, :42-50; host loops hashgrid_interpolate.cpp:68-100,154-186.
+ * grad_codebook[table_rows, feature_dim] is zero-filled by this call when zero_first != 0
+ * (the reference allocates zeros_like, .cpp:81,167) and accumulated into otherwise.
+ * The reference's grad_coords output is computed with wrong indices and discarded
+ * (SURVEY Q6); it is not provided. */
+int shacira_hashgrid_backward(int32_t dim, const float* coords, int64_t n, const float* grad_output,
+                              const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                              int32_t codebook_bitwidth, int32_t feature_dim, int64_t table_rows, int32_t zero_first,
+                              float* grad_codebook, shacira_stream_t stream);
+
+/* Level-local corner indices idx[n, num_lods, 2^dim] (int32) and weights w[n, num_lods, 2^dim]
+ * exactly as the forward/backward kernels use them (bit-exactness tests, debugging). */
+int shacira_hashgrid_corners(int32_t dim, const float* coords, int64_t n, const int32_t* resolutions,
+                             int32_t num_lods, int32_t codebook_bitwidth, int32_t* idx, float* w,
+                             shacira_stream_t stream);
+
+/* ---- fused latent grid: replaces latent_dec(codebook) + hashgrid*() ------------------ */
+/* LatentGrid.interpolate (wisp/models/grids/latent_grid.py:340-382) with an affine latent
+ * decoder (LatentDecoder / HierarchicalLatentDecoder with num_layers_dec = 0,
+ * wisp/models/latent_decoders/basic_latent_decoder.py:85-95,182-198):
+ *   q      = round_flag ? rint(latents) : latents           (StraightThrough, :28-36)
+ *   z[i,l] = sum_k w_k * q[first_idx[l] + idx_k]             (latent_dim channels)
+ *   feats[i, l*F + f] = sum_c z[i,l,c] * A[la,c,f] + shift[la,f]
+ * with A = scale / div[:,None] prepared by the caller ([1|L, C, F] row-major; la = l when
+ * per_level != 0 else 0) and shift [1|L, F] or NULL. Interpolating before the affine map
+ * equals the reference's decode-then-interpolate because the weights sum to 1.
+ * zsave (nullable) receives z[n, L*C] for the backward pass.
+ * latent_dim C in {1,2,4}, feature_dim F in {1,2,4,8}. */
+int shacira_latent_forward(int32_t dim, const float* coords, int64_t n, const float* latents,
+                           const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                           int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim, int32_t round_flag,
+                           const float* A, const float* shift, int32_t per_level, float* feats, float* zsave,
+                           shacira_stream_t stream);
+
+/* Backward of the above. grad_latents[table_rows, C] += w_k * sum_f g[i,l,f] * A[la,c,f]
+ * (straight-through: the rounding passes gradients unchanged); grad_A[L, C, F] and
+ * grad_shift[L, F] (always per level; the caller sums over levels for a single decoder)
+ * are ACCUMULATED into (caller zero-fills); either may be NULL. zsave is the forward's
+ * z[n, L*C] (required when grad_A != NULL). */
+int shacira_latent_backward(int32_t dim, const float* coords, int64_t n, const float* grad_output,
+                            const float* zsave, const int32_t* first_idx, const int32_t* resolutions,
+                            int32_t num_lods, int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim,
+                            const float* A, int32_t per_level, int64_t table_rows, int32_t zero_first,
+                            float* grad_latents, float* grad_A, float* grad_shift, shacira_stream_t stream);
+
+/* ---- factorized-density bit-rate estimate -------------------------------------------- */
+/* LatentGrid.ent_loss (latent_grid.py:122-136) + BitEstimator/Bitparm
+ * (wisp/models/prob_models/bit_estimator.py:9-65), forward and backward in one pass:
+ *   x = latents + noise (noise != NULL)  or  rint(latents) (noise == NULL, the is_val branch)
+ *   p = CDF(x + .5) - CDF(x - .5);  bits = clamp(-log(p + 1e-10) / ln 2, 0, 50)
+ * num_layers in 1..4 selects f1..f(num_layers-1) then f4 (bit_estimator.py:58-65).
+ * params: float32 [4, 3, C] = {f1,f2,f3,f4} x {h,b,a} x channel (f4.a unused).
+ * Outputs (all nullable except bits): bits[1 + num_lods] double = total, then per level;
+ * grad_latents[T, C] = d total / d latents (written, not accumulated; zero when noise==NULL);
+ * grad_params[4, 3, C] float32 = d total / d params (ACCUMULATED; caller zero-fills).
+ * first_idx (host, nullable with num_lods = 0) gives the per-level reduction. */
+int shacira_entropy_bits(const float* latents, const float* noise, int64_t table_rows, int32_t latent_dim,
+                         const float* params, int32_t num_layers, const int32_t* first_idx, int32_t num_lods,
+                         double* bits, float* grad_latents, float* grad_params, shacira_stream_t stream);
+
+/* ---- symbols / histogram for LatentGrid.size() --------------------------------------- */
+/* latent_grid.py:138-153: per channel q = rint(latents[:,c]); symbols[T, C] (int16,
+ * nullable) = q, minmax[2*C] (int32) = {min_c, max_c}. Values must fit int16
+ * (the reference casts to int16 for torchac, latent_grid.py:170). */
+int shacira_quantize_symbols(const float* latents, int64_t table_rows, int32_t latent_dim, int16_t* symbols,
+                             int32_t* minmax, shacira_stream_t stream);
+/* counts[C, num_bins] (int64, ACCUMULATED) of rint(latents[:,c]) - lo[c]; lo is HOST int32[C]. */
+int shacira_symbol_histogram(const float* latents, int64_t table_rows, int32_t latent_dim, const int32_t* lo,
+                             int32_t num_bins, int64_t* counts, shacira_stream_t stream);
+
+/* ---- latent bitstream (host side) ---------------------------------------------------- */
+/* Static arithmetic coder over dense symbol ranks 0..num_symbols-1 with 16-bit cumulative
+ * frequencies cdf[num_symbols+1] (cdf[0] = 0, strictly increasing, cdf[num_symbols] = 65536).
+ * Stands in for torchac.encode_float_cdf (latent_grid.py:170), whose length is all the
+ * reference uses; byte parity with torchac is unpinned (package absent), round trip is exact.
+ * encode returns the number of bytes written or a negative error; both run on the host. */
+int64_t shacira_ac_encode(const int16_t* symbols, int64_t n, const uint32_t* cdf, int32_t num_symbols,
+                          uint8_t* out, int64_t out_capacity);
+int shacira_ac_decode(const uint8_t* in, int64_t nbytes, const uint32_t* cdf, int32_t num_symbols,
+                      int16_t* symbols, int64_t n);
+
+/* ---- host-buffer entry (end-to-end measurement, non-torch hosts) --------------------- */
+/* One fused latent fwd+bwd step with every buffer in HOST memory (pinned or pageable):
+ * copies coords, latents, grad_output, A, shift to the device, runs shacira_latent_forward
+ * + shacira_latent_backward, copies feats and grad_latents back, synchronises. Device
+ * scratch is cached per thread between calls. */
+int shacira_latent_step_host(int32_t dim, const float* coords, int64_t n, const float* latents, int64_t table_rows,
+                             const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                             int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim, int32_t round_flag,
+                             const float* A, const float* shift, int32_t per_level, const float* grad_output,
+                             float* feats, float* grad_latents);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHACIRA_B200_H_ */

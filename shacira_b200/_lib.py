@@ -1,0 +1,329 @@
+"""ctypes binding of the C-ABI library (include/shacira_b200.h) + thin torch-tensor wrappers.
+
+PyTorch is plumbing here: it owns device memory and the current stream; every compute call
+goes through `libshacira_b200.so`. There is NO fallback: if the library is missing or a call
+fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libshacira_b200.so")
+
+OK = 0
+ERR_INVALID_ARGUMENT = -1
+ERR_UNSUPPORTED = -2
+ERR_CUDA = -3
+ERR_Q2_WINDOW = -4
+ERR_NO_DEVICE = -5
+MAX_LEVELS = 32
+
+_c_int32_p = ctypes.POINTER(ctypes.c_int32)
+_vp = ctypes.c_void_p
+_i32 = ctypes.c_int32
+_i64 = ctypes.c_int64
+
+# name -> (restype, argtypes); mirrors include/shacira_b200.h one to one.
+SIGNATURES = {
+    "shacira_abi_version": (ctypes.c_int, []),
+    "shacira_last_error": (ctypes.c_char_p, []),
+    "shacira_launch_count": (_i64, []),
+    "shacira_device_info": (ctypes.c_int, [_c_int32_p, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "shacira_l2_pin": (ctypes.c_int, [_vp, _i64, _vp]),
+    "shacira_hashgrid_forward": (ctypes.c_int, [_i32, _vp, _i64, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _vp, _vp]),
+    "shacira_hashgrid_backward": (ctypes.c_int, [_i32, _vp, _i64, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i64, _i32, _vp, _vp]),
+    "shacira_hashgrid_corners": (ctypes.c_int, [_i32, _vp, _i64, _c_int32_p, _i32, _i32, _vp, _vp, _vp]),
+    "shacira_latent_forward": (ctypes.c_int, [_i32, _vp, _i64, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "shacira_latent_backward": (ctypes.c_int, [_i32, _vp, _i64, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "shacira_entropy_bits": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _c_int32_p, _i32, _vp, _vp, _vp, _vp]),
+    "shacira_quantize_symbols": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "shacira_symbol_histogram": (ctypes.c_int, [_vp, _i64, _i32, _c_int32_p, _i32, _vp, _vp]),
+    "shacira_ac_encode": (_i64, [_vp, _i64, _vp, _i32, _vp, _i64]),
+    "shacira_ac_decode": (ctypes.c_int, [_vp, _i64, _vp, _i32, _vp, _i64]),
+    "shacira_latent_step_host": (ctypes.c_int, [_i32, _vp, _i64, _vp, _i64, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class ShaciraError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("shacira_b200 [%d]: %s" % (code, msg))
+        self.code = code
+
+
+def load():
+    """Load the C-ABI library. Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "shacira_b200: %s is missing -- build it with `python -m shacira_b200.build` "
+                "(or __graft_entry__.build()). There is no CPU / PyTorch fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the ABI drifted
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise ShaciraError(rc, load().shacira_last_error().decode("utf-8", "replace"))
+
+
+_arr_cache = {}
+
+
+def _i32_array(values):
+    key = tuple(int(v) for v in values)
+    arr = _arr_cache.get(key)
+    if arr is None:
+        arr = (ctypes.c_int32 * len(key))(*key)
+        if len(_arr_cache) > 4096:
+            _arr_cache.clear()
+        _arr_cache[key] = arr
+    return arr, len(key)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, name):
+    if not t.is_cuda:
+        raise ShaciraError(ERR_INVALID_ARGUMENT, "%s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        raise ShaciraError(ERR_UNSUPPORTED, "%s must be float32 (fp32 is the supported path), got %s" % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def launch_count():
+    return int(load().shacira_launch_count())
+
+
+def device_info():
+    sm, l2, pers = ctypes.c_int32(0), ctypes.c_int64(0), ctypes.c_int64(0)
+    _check(load().shacira_device_info(ctypes.byref(sm), ctypes.byref(l2), ctypes.byref(pers)))
+    return {"sm_count": sm.value, "l2_bytes": l2.value, "l2_persist_max": pers.value}
+
+
+def l2_pin(tensor):
+    """Pin `tensor` in L2 for kernels launched on the current stream (None clears the window)."""
+    if tensor is None:
+        _check(load().shacira_l2_pin(None, 0, _stream()))
+    else:
+        _check(load().shacira_l2_pin(_ptr(tensor), tensor.numel() * tensor.element_size(), _stream()))
+
+
+def _dim_of(coords):
+    if coords.dim() != 2 or coords.shape[1] not in (2, 3):
+        raise ShaciraError(ERR_INVALID_ARGUMENT, "coords must be [N, 2] or [N, 3], got %s" % (tuple(coords.shape),))
+    return coords.shape[1]
+
+
+def hashgrid_forward(coords, codebook, first_idx, resolutions, bitwidth):
+    """feats[N, L*F]; first_idx / resolutions are host int sequences."""
+    lib = load()
+    coords = _f32c(coords, "coords")
+    codebook = _f32c(codebook, "codebook")
+    dim = _dim_of(coords)
+    fi, L = _i32_array(first_idx)
+    rs, L2 = _i32_array(resolutions)
+    if L != L2:
+        raise ShaciraError(ERR_INVALID_ARGUMENT, "first_idx and resolutions differ in length")
+    n, F = coords.shape[0], codebook.shape[1]
+    feats = torch.empty((n, L * F), dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        _check(lib.shacira_hashgrid_forward(dim, _ptr(coords), n, _ptr(codebook), fi, rs, L, bitwidth, F,
+                                            _ptr(feats), _stream()))
+    return feats
+
+
+def hashgrid_backward(coords, grad_output, first_idx, resolutions, bitwidth, feature_dim, table_rows, out=None):
+    lib = load()
+    coords = _f32c(coords, "coords")
+    grad_output = _f32c(grad_output, "grad_output")
+    dim = _dim_of(coords)
+    fi, L = _i32_array(first_idx)
+    rs, _ = _i32_array(resolutions)
+    n = coords.shape[0]
+    zero_first = 1
+    if out is None:
+        out = torch.empty((table_rows, feature_dim), dtype=torch.float32, device=coords.device)
+    else:
+        zero_first = 0
+    with torch.cuda.device(coords.device):
+        _check(lib.shacira_hashgrid_backward(dim, _ptr(coords), n, _ptr(grad_output), fi, rs, L, bitwidth,
+                                             feature_dim, table_rows, zero_first, _ptr(out), _stream()))
+    return out
+
+
+def hashgrid_corners(coords, resolutions, bitwidth):
+    lib = load()
+    coords = _f32c(coords, "coords")
+    dim = _dim_of(coords)
+    rs, L = _i32_array(resolutions)
+    n = coords.shape[0]
+    idx = torch.empty((n, L, 1 << dim), dtype=torch.int32, device=coords.device)
+    w = torch.empty((n, L, 1 << dim), dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        _check(lib.shacira_hashgrid_corners(dim, _ptr(coords), n, rs, L, bitwidth, _ptr(idx), _ptr(w), _stream()))
+    return idx, w
+
+
+def latent_forward(coords, latents, first_idx, resolutions, bitwidth, A, shift, feature_dim, round_flag, save_z):
+    """A: [1|L, C, F]; shift: [1|L, F] or None. Returns (feats[N, L*F], z[N, L*C] or None)."""
+    lib = load()
+    coords = _f32c(coords, "coords")
+    latents = _f32c(latents, "latents")
+    A = _f32c(A, "A")
+    shift = _f32c(shift, "shift") if shift is not None else None
+    dim = _dim_of(coords)
+    fi, L = _i32_array(first_idx)
+    rs, _ = _i32_array(resolutions)
+    n, C = coords.shape[0], latents.shape[1]
+    per_level = 1 if A.shape[0] == L and L > 1 else 0
+    if A.shape[0] not in (1, L) or tuple(A.shape[1:]) != (C, feature_dim):
+        raise ShaciraError(ERR_INVALID_ARGUMENT, "A must be [1|L, C, F], got %s" % (tuple(A.shape),))
+    feats = torch.empty((n, L * feature_dim), dtype=torch.float32, device=coords.device)
+    z = torch.empty((n, L * C), dtype=torch.float32, device=coords.device) if save_z else None
+    with torch.cuda.device(coords.device):
+        _check(lib.shacira_latent_forward(dim, _ptr(coords), n, _ptr(latents), fi, rs, L, bitwidth, C, feature_dim,
+                                          1 if round_flag else 0, _ptr(A), _ptr(shift), per_level, _ptr(feats),
+                                          _ptr(z), _stream()))
+    return feats, z
+
+
+def latent_backward(coords, grad_output, z, first_idx, resolutions, bitwidth, A, latent_dim, feature_dim,
+                    table_rows, want_decoder_grads):
+    """Returns (grad_latents[T, C], grad_A[L, C, F] or None, grad_shift[L, F] or None)."""
+    lib = load()
+    coords = _f32c(coords, "coords")
+    grad_output = _f32c(grad_output, "grad_output")
+    A = _f32c(A, "A")
+    dim = _dim_of(coords)
+    fi, L = _i32_array(first_idx)
+    rs, _ = _i32_array(resolutions)
+    n = coords.shape[0]
+    per_level = 1 if A.shape[0] == L and L > 1 else 0
+    dev = coords.device
+    gl = torch.empty((table_rows, latent_dim), dtype=torch.float32, device=dev)
+    gA = gS = None
+    if want_decoder_grads:
+        gA = torch.zeros((L, latent_dim, feature_dim), dtype=torch.float32, device=dev)
+        gS = torch.zeros((L, feature_dim), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.shacira_latent_backward(dim, _ptr(coords), n, _ptr(grad_output), _ptr(z), fi, rs, L, bitwidth,
+                                           latent_dim, feature_dim, _ptr(A), per_level, table_rows, 1, _ptr(gl),
+                                           _ptr(gA), _ptr(gS), _stream()))
+    return gl, gA, gS
+
+
+def entropy_bits(latents, noise, params, num_layers, first_idx=None, want_grads=True):
+    """params [4, 3, C]. Returns (bits[1+L] float64, grad_latents[T, C] | None, grad_params[4,3,C] | None)."""
+    lib = load()
+    latents = _f32c(latents, "latents")
+    noise = _f32c(noise, "noise") if noise is not None else None
+    params = _f32c(params, "params")
+    T, C = latents.shape
+    if first_idx is not None:
+        fi, L = _i32_array(first_idx)
+    else:
+        fi, L = None, 0
+    dev = latents.device
+    bits = torch.empty((1 + L,), dtype=torch.float64, device=dev)
+    gl = torch.empty_like(latents) if want_grads else None
+    gp = torch.empty((4, 3, C), dtype=torch.float32, device=dev) if want_grads else None
+    with torch.cuda.device(dev):
+        _check(lib.shacira_entropy_bits(_ptr(latents), _ptr(noise), T, C, _ptr(params), num_layers, fi, L,
+                                        _ptr(bits), _ptr(gl), _ptr(gp), _stream()))
+    return bits, gl, gp
+
+
+def quantize_symbols(latents, want_symbols=True):
+    """Returns (symbols[T, C] int16 | None, minmax[C, 2] int32)."""
+    lib = load()
+    latents = _f32c(latents, "latents")
+    T, C = latents.shape
+    dev = latents.device
+    sym = torch.empty((T, C), dtype=torch.int16, device=dev) if want_symbols else None
+    mm = torch.empty((C, 2), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.shacira_quantize_symbols(_ptr(latents), T, C, _ptr(sym), _ptr(mm), _stream()))
+    return sym, mm
+
+
+def symbol_histogram(latents, lo, num_bins):
+    """counts[C, num_bins] int64 of rint(latents[:, c]) - lo[c]."""
+    lib = load()
+    latents = _f32c(latents, "latents")
+    T, C = latents.shape
+    lo_arr, nlo = _i32_array(lo)
+    if nlo != C:
+        raise ShaciraError(ERR_INVALID_ARGUMENT, "lo must have one entry per channel")
+    counts = torch.zeros((C, num_bins), dtype=torch.int64, device=latents.device)
+    with torch.cuda.device(latents.device):
+        _check(lib.shacira_symbol_histogram(_ptr(latents), T, C, lo_arr, num_bins, _ptr(counts), _stream()))
+    return counts
+
+
+def latent_step_host(coords, latents, first_idx, resolutions, bitwidth, A, shift, grad_output, round_flag=True,
+                     feats_out=None, grad_latents_out=None):
+    """Host-buffer fwd+bwd (end-to-end entry): every tensor lives in (ideally pinned) host memory."""
+    lib = load()
+    for name, t in (("coords", coords), ("latents", latents), ("A", A), ("grad_output", grad_output)):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ShaciraError(ERR_INVALID_ARGUMENT, "%s must be a contiguous float32 HOST tensor" % name)
+    dim = _dim_of(coords)
+    fi, L = _i32_array(first_idx)
+    rs, _ = _i32_array(resolutions)
+    n, (T, C) = coords.shape[0], latents.shape
+    F = A.shape[2]
+    per_level = 1 if A.shape[0] == L and L > 1 else 0
+    if feats_out is None:
+        feats_out = torch.empty((n, L * F), dtype=torch.float32).pin_memory()
+    if grad_latents_out is None:
+        grad_latents_out = torch.empty((T, C), dtype=torch.float32).pin_memory()
+    _check(lib.shacira_latent_step_host(dim, _ptr(coords), n, _ptr(latents), T, fi, rs, L, bitwidth, C, F,
+                                        1 if round_flag else 0, _ptr(A), _ptr(shift), per_level, _ptr(grad_output),
+                                        _ptr(feats_out), _ptr(grad_latents_out)))
+    return feats_out, grad_latents_out
+
+
+def ac_encode(symbols, cdf):
+    """symbols: int16 numpy/torch CPU array of dense ranks; cdf: uint32 array [K+1]. Returns bytes."""
+    import numpy as np
+    lib = load()
+    sym = np.ascontiguousarray(symbols, dtype=np.int16)
+    cdf = np.ascontiguousarray(cdf, dtype=np.uint32)
+    cap = int(sym.size * 2 + 64)
+    out = np.empty(cap, dtype=np.uint8)
+    r = lib.shacira_ac_encode(sym.ctypes.data, sym.size, cdf.ctypes.data, cdf.size - 1, out.ctypes.data, cap)
+    if r < 0:
+        raise ShaciraError(int(r), lib.shacira_last_error().decode("utf-8", "replace"))
+    return out[:r].tobytes()
+
+
+def ac_decode(stream, cdf, n):
+    import numpy as np
+    lib = load()
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    cdf = np.ascontiguousarray(cdf, dtype=np.uint32)
+    out = np.empty(n, dtype=np.int16)
+    _check(lib.shacira_ac_decode(buf.ctypes.data, buf.size, cdf.ctypes.data, cdf.size - 1, out.ctypes.data, n))
+    return out

@@ -1,0 +1,46 @@
+"""Build shacira_b200/libshacira_b200.so (the C-ABI library) with nvcc for sm_100a.
+
+In-tree, no torch dependency, no JIT cache: the .so is git-ignored but travels to the GPU
+box with the gpurun snapshot. `python -m shacira_b200.build [-v] [--force]`.
+"""
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libshacira_b200.so")
+SOURCES = ["capi.cu"]
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--shared",
+]
+
+
+def _deps():
+    d = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".inl", ".h"))]
+    d.append(os.path.join(os.path.dirname(PKG), "include", "shacira_b200.h"))
+    d.append(os.path.abspath(__file__))
+    return d
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in _deps())
+
+
+def build(force=False, verbose=False, extra=()):
+    if not force and not is_stale():
+        return LIB
+    cmd = ["nvcc"] + NVCC_FLAGS + list(extra) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    extra = ["-Xptxas", "-v"] if "--ptxas" in sys.argv else []
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra=extra))

@@ -1,0 +1,472 @@
+// capi.cu -- the extern "C" surface declared in include/shacira_b200.h: argument validation,
+// level metadata, template dispatch and launches. No torch, no exceptions across the ABI.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "arith_coder.inl"
+#include "entropy_kernels.cuh"
+#include "hashgrid_kernels.cuh"
+
+using namespace shacira;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_OK(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver         \
+                            ? SHACIRA_ERR_NO_DEVICE : SHACIRA_ERR_CUDA,                        \
+                        "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCHED()                    \
+    do {                              \
+        g_launches.fetch_add(1);      \
+        CUDA_OK(cudaGetLastError());  \
+    } while (0)
+
+// Level metadata + the checks the reference does not make (SURVEY 8b "error convention").
+int build_levels(int32_t dim, const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                 int32_t bitwidth, LevelParams& lp) {
+    if (dim != 2 && dim != 3) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "dim must be 2 or 3, got %d", dim);
+    if (!resolutions) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "resolutions is NULL");
+    if (num_lods < 1 || num_lods > SHACIRA_MAX_LEVELS)
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "num_lods must be in [1, %d], got %d", SHACIRA_MAX_LEVELS, num_lods);
+    if (bitwidth < 1 || bitwidth > 30)
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "codebook_bitwidth must be in [1, 30], got %d", bitwidth);
+    memset(&lp, 0, sizeof(lp));
+    const int64_t T = (int64_t)1 << bitwidth;
+    lp.num_lods = num_lods;
+    lp.hash_mask = (uint32_t)(T - 1);
+    int64_t running = 0;
+    for (int l = 0; l < num_lods; ++l) {
+        const int64_t r = resolutions[l];
+        if (r < 2 || r > (1 << 24))
+            return fail(SHACIRA_ERR_INVALID_ARGUMENT, "resolution[%d] = %lld out of range [2, 2^24]", l, (long long)r);
+        // the reference's predicate, with its int32 wrap-around (hashgrid_interpolate_cuda.cu:27-29)
+        const int32_t r32 = (int32_t)r;
+        const int32_t rr32 = (int32_t)((uint32_t)r32 * (uint32_t)r32);
+        const int32_t rrr32 = (int32_t)((uint32_t)rr32 * (uint32_t)r32);
+        const bool ref_dense = r32 < T && rr32 < T && (dim == 2 || rrr32 < T);
+        // the same predicate in 64-bit
+        const int64_t pts = (dim == 2) ? r * r : r * r * r;
+        const bool dense = r < T && r * r < T && pts < T;
+        if (ref_dense != dense)
+            return fail(SHACIRA_ERR_Q2_WINDOW,
+                        "level %d (res %lld, 2^%d rows): the reference's int32 dense predicate overflows here and "
+                        "indexes outside the table; parity is undefined (SURVEY Q2)", l, (long long)r, bitwidth);
+        if (dense) lp.dense_mask |= (1u << l);
+        lp.res[l] = r32;
+        lp.rows[l] = (int32_t)(pts < T ? pts : T);
+        lp.hi[l] = (float)((double)(r32 - 1) - 1e-5);
+        lp.first[l] = first_idx ? first_idx[l] : (int32_t)running;
+        if (lp.first[l] < 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "first_idx[%d] is negative", l);
+        running += lp.rows[l];
+    }
+    return SHACIRA_OK;
+}
+
+inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+template <int D, int F>
+int launch_plain_fwd(const float* coords, int64_t n, const float* table, const LevelParams& lp, float* feats,
+                     cudaStream_t s) {
+    hashgrid_fwd_kernel<D, F><<<grid_for(n, kBlock), kBlock, 0, s>>>(coords, n, table, lp, feats);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+template <int D, int F>
+int launch_plain_bwd(const float* coords, int64_t n, const float* g, const LevelParams& lp, float* gt,
+                     cudaStream_t s) {
+    hashgrid_bwd_kernel<D, F><<<grid_for(n, kBlock), kBlock, 0, s>>>(coords, n, g, lp, gt);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+template <int D, int C, int F>
+int launch_latent_fwd(const float* coords, int64_t n, const float* lat, const LevelParams& lp, const float* A,
+                      const float* shift, int per_level, int round_flag, float* feats, float* zsave,
+                      cudaStream_t s) {
+    const int nA = per_level ? lp.num_lods : 1;
+    const size_t smem = sizeof(float) * (size_t)(nA * C * F + nA * F);
+    latent_fwd_kernel<D, C, F><<<grid_for(n, kBlock), kBlock, smem, s>>>(coords, n, lat, lp, A, shift, per_level,
+                                                                          round_flag, feats, zsave);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+template <int D, int C, int F>
+int launch_latent_bwd(const float* coords, int64_t n, const float* g, const float* zsave, const LevelParams& lp,
+                      const float* A, int per_level, float* gl, float* gA, float* gS, cudaStream_t s) {
+    const int nA = per_level ? lp.num_lods : 1;
+    const size_t smem = sizeof(float) * (size_t)(nA * C * F + lp.num_lods * C * F + lp.num_lods * F);
+    latent_bwd_kernel<D, C, F><<<grid_for(n, kBlock), kBlock, smem, s>>>(coords, n, g, zsave, lp, A, per_level, gl,
+                                                                          gA, gS);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
+#define DISPATCH_F(D_, F_, CALL)                                                                   \
+    switch (F_) {                                                                                  \
+        case 1: { constexpr int kF = 1; return CALL; }                                             \
+        case 2: { constexpr int kF = 2; return CALL; }                                             \
+        case 4: { constexpr int kF = 4; return CALL; }                                             \
+        case 8: { constexpr int kF = 8; return CALL; }                                             \
+        default: return fail(SHACIRA_ERR_UNSUPPORTED, "feature_dim %d not in {1,2,4,8}", (int)F_); \
+    }
+
+#define DISPATCH_CF(C_, F_, CALL)                                                                        \
+    switch (C_) {                                                                                        \
+        case 1: { constexpr int kC = 1; DISPATCH_F(0, F_, CALL) }                                        \
+        case 2: { constexpr int kC = 2; DISPATCH_F(0, F_, CALL) }                                        \
+        case 4: { constexpr int kC = 4; DISPATCH_F(0, F_, CALL) }                                        \
+        default: return fail(SHACIRA_ERR_UNSUPPORTED, "latent_dim %d not in {1,2,4}", (int)C_);          \
+    }
+
+int check_points(const float* coords, int64_t n) {
+    if (n < 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "n is negative");
+    if (n > 0 && !coords) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "coords is NULL");
+    if (n > ((int64_t)1 << 31) * (int64_t)kBlock / 2) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "n too large");
+    return SHACIRA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int shacira_abi_version(void) { return SHACIRA_ABI_VERSION; }
+const char* shacira_last_error(void) { return g_err; }
+int64_t shacira_launch_count(void) { return g_launches.load(); }
+
+int shacira_device_info(int32_t* sm_count, int64_t* l2_bytes, int64_t* l2_persist_max) {
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    CUDA_OK(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = p.l2CacheSize;
+    if (l2_persist_max) *l2_persist_max = p.persistingL2CacheMaxSize;
+    return SHACIRA_OK;
+}
+
+int shacira_l2_pin(const void* base, int64_t bytes, shacira_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    CUDA_OK(cudaGetDeviceProperties(&p, dev));
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (bytes > 0 && base) {
+        size_t carve = (size_t)p.persistingL2CacheMaxSize;
+        if ((size_t)bytes < carve) carve = (size_t)bytes;
+        CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+        size_t win = (size_t)bytes;
+        if (win > (size_t)p.accessPolicyMaxWindowSize) win = (size_t)p.accessPolicyMaxWindowSize;
+        attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+        attr.accessPolicyWindow.num_bytes = win;
+        attr.accessPolicyWindow.hitRatio = win <= carve ? 1.0f : (float)carve / (float)win;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } else {
+        attr.accessPolicyWindow.num_bytes = 0;
+    }
+    CUDA_OK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return SHACIRA_OK;
+}
+
+int shacira_hashgrid_forward(int32_t dim, const float* coords, int64_t n, const float* codebook,
+                             const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                             int32_t codebook_bitwidth, int32_t feature_dim, float* feats, shacira_stream_t stream) {
+    LevelParams lp;
+    int rc = build_levels(dim, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
+    if (rc) return rc;
+    if ((rc = check_points(coords, n))) return rc;
+    if (n == 0) return SHACIRA_OK;
+    if (!codebook || !feats) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "codebook/feats is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dim == 2) { DISPATCH_F(2, feature_dim, (launch_plain_fwd<2, kF>(coords, n, codebook, lp, feats, s))) }
+    DISPATCH_F(3, feature_dim, (launch_plain_fwd<3, kF>(coords, n, codebook, lp, feats, s)))
+}
+
+int shacira_hashgrid_backward(int32_t dim, const float* coords, int64_t n, const float* grad_output,
+                              const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                              int32_t codebook_bitwidth, int32_t feature_dim, int64_t table_rows, int32_t zero_first,
+                              float* grad_codebook, shacira_stream_t stream) {
+    LevelParams lp;
+    int rc = build_levels(dim, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
+    if (rc) return rc;
+    if ((rc = check_points(coords, n))) return rc;
+    if (!grad_codebook) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "grad_codebook is NULL");
+    if (feature_dim != 1 && feature_dim != 2 && feature_dim != 4 && feature_dim != 8)
+        return fail(SHACIRA_ERR_UNSUPPORTED, "feature_dim %d not in {1,2,4,8}", feature_dim);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (zero_first) CUDA_OK(cudaMemsetAsync(grad_codebook, 0, sizeof(float) * (size_t)table_rows * feature_dim, s));
+    if (n == 0) return SHACIRA_OK;
+    if (!grad_output) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "grad_output is NULL");
+    if (dim == 2) { DISPATCH_F(2, feature_dim, (launch_plain_bwd<2, kF>(coords, n, grad_output, lp, grad_codebook, s))) }
+    DISPATCH_F(3, feature_dim, (launch_plain_bwd<3, kF>(coords, n, grad_output, lp, grad_codebook, s)))
+}
+
+int shacira_hashgrid_corners(int32_t dim, const float* coords, int64_t n, const int32_t* resolutions,
+                             int32_t num_lods, int32_t codebook_bitwidth, int32_t* idx, float* w,
+                             shacira_stream_t stream) {
+    LevelParams lp;
+    int rc = build_levels(dim, nullptr, resolutions, num_lods, codebook_bitwidth, lp);
+    if (rc) return rc;
+    if ((rc = check_points(coords, n))) return rc;
+    if (n == 0) return SHACIRA_OK;
+    if (!idx || !w) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "idx/w is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dim == 2) corners_kernel<2><<<grid_for(n, kBlock), kBlock, 0, s>>>(coords, n, lp, idx, w);
+    else corners_kernel<3><<<grid_for(n, kBlock), kBlock, 0, s>>>(coords, n, lp, idx, w);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
+int shacira_latent_forward(int32_t dim, const float* coords, int64_t n, const float* latents,
+                           const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                           int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim, int32_t round_flag,
+                           const float* A, const float* shift, int32_t per_level, float* feats, float* zsave,
+                           shacira_stream_t stream) {
+    LevelParams lp;
+    int rc = build_levels(dim, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
+    if (rc) return rc;
+    if ((rc = check_points(coords, n))) return rc;
+    if (n == 0) return SHACIRA_OK;
+    if (!latents || !feats || !A) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "latents/feats/A is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dim == 2) {
+        DISPATCH_CF(latent_dim, feature_dim,
+                    (launch_latent_fwd<2, kC, kF>(coords, n, latents, lp, A, shift, per_level, round_flag, feats,
+                                                  zsave, s)))
+    }
+    DISPATCH_CF(latent_dim, feature_dim,
+                (launch_latent_fwd<3, kC, kF>(coords, n, latents, lp, A, shift, per_level, round_flag, feats, zsave,
+                                              s)))
+}
+
+int shacira_latent_backward(int32_t dim, const float* coords, int64_t n, const float* grad_output,
+                            const float* zsave, const int32_t* first_idx, const int32_t* resolutions,
+                            int32_t num_lods, int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim,
+                            const float* A, int32_t per_level, int64_t table_rows, int32_t zero_first,
+                            float* grad_latents, float* grad_A, float* grad_shift, shacira_stream_t stream) {
+    LevelParams lp;
+    int rc = build_levels(dim, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
+    if (rc) return rc;
+    if ((rc = check_points(coords, n))) return rc;
+    if (!grad_latents || !A) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "grad_latents/A is NULL");
+    if (grad_A && !zsave) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "grad_A requested without zsave");
+    if (latent_dim != 1 && latent_dim != 2 && latent_dim != 4)
+        return fail(SHACIRA_ERR_UNSUPPORTED, "latent_dim %d not in {1,2,4}", latent_dim);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (zero_first) CUDA_OK(cudaMemsetAsync(grad_latents, 0, sizeof(float) * (size_t)table_rows * latent_dim, s));
+    if (n == 0) return SHACIRA_OK;
+    if (!grad_output) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "grad_output is NULL");
+    if (dim == 2) {
+        DISPATCH_CF(latent_dim, feature_dim,
+                    (launch_latent_bwd<2, kC, kF>(coords, n, grad_output, zsave, lp, A, per_level, grad_latents,
+                                                  grad_A, grad_shift, s)))
+    }
+    DISPATCH_CF(latent_dim, feature_dim,
+                (launch_latent_bwd<3, kC, kF>(coords, n, grad_output, zsave, lp, A, per_level, grad_latents, grad_A,
+                                              grad_shift, s)))
+}
+
+int shacira_entropy_bits(const float* latents, const float* noise, int64_t table_rows, int32_t latent_dim,
+                         const float* params, int32_t num_layers, const int32_t* first_idx, int32_t num_lods,
+                         double* bits, float* grad_latents, float* grad_params, shacira_stream_t stream) {
+    if (!latents || !params || !bits) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "latents/params/bits is NULL");
+    if (table_rows < 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "table_rows is negative");
+    if (latent_dim < 1 || latent_dim > kMaxEntC || (latent_dim & (latent_dim - 1)))
+        return fail(SHACIRA_ERR_UNSUPPORTED, "latent_dim %d must be a power of two <= %d", latent_dim, kMaxEntC);
+    if (num_layers < 1) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "num_layers must be >= 1");
+    if (num_lods < 0 || num_lods > SHACIRA_MAX_LEVELS || (num_lods > 0 && !first_idx))
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "bad num_lods/first_idx");
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_OK(cudaMemsetAsync(bits, 0, sizeof(double) * (size_t)(1 + num_lods), s));
+    if (grad_params) CUDA_OK(cudaMemsetAsync(grad_params, 0, sizeof(float) * 12 * (size_t)latent_dim, s));
+    const int64_t total = table_rows * latent_dim;
+    if (total == 0) return SHACIRA_OK;
+    LevelBounds lb;
+    memset(&lb, 0, sizeof(lb));
+    lb.num_lods = num_lods;
+    for (int l = 0; l < num_lods; ++l) lb.first[l] = first_idx[l];
+    lb.first[num_lods] = (int32_t)table_rows;
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t blocks = (total + kEntBlock - 1) / kEntBlock;
+    const int64_t cap = (int64_t)sms * 8;  // persistent-ish: a few resident blocks per SM
+    if (blocks > cap) blocks = cap;
+    entropy_kernel<<<(int)blocks, kEntBlock, 0, s>>>(latents, noise, total, latent_dim, params, num_layers, lb, bits,
+                                                     grad_latents, grad_params);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
+int shacira_quantize_symbols(const float* latents, int64_t table_rows, int32_t latent_dim, int16_t* symbols,
+                             int32_t* minmax, shacira_stream_t stream) {
+    if (!latents || !minmax) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "latents/minmax is NULL");
+    if (latent_dim < 1 || latent_dim > kMaxEntC || (latent_dim & (latent_dim - 1)))
+        return fail(SHACIRA_ERR_UNSUPPORTED, "latent_dim %d must be a power of two <= %d", latent_dim, kMaxEntC);
+    cudaStream_t s = (cudaStream_t)stream;
+    init_minmax_kernel<<<1, 32, 0, s>>>(minmax, latent_dim);
+    LAUNCHED();
+    const int64_t total = table_rows * latent_dim;
+    if (total <= 0) return SHACIRA_OK;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    quantize_symbols_kernel<<<(int)blocks, 256, 0, s>>>(latents, total, latent_dim, symbols, minmax);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
+int shacira_symbol_histogram(const float* latents, int64_t table_rows, int32_t latent_dim, const int32_t* lo,
+                             int32_t num_bins, int64_t* counts, shacira_stream_t stream) {
+    if (!latents || !lo || !counts) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "latents/lo/counts is NULL");
+    if (latent_dim < 1 || latent_dim > kMaxEntC || (latent_dim & (latent_dim - 1)))
+        return fail(SHACIRA_ERR_UNSUPPORTED, "latent_dim %d must be a power of two <= %d", latent_dim, kMaxEntC);
+    if (num_bins < 1) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "num_bins must be >= 1");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t total = table_rows * latent_dim;
+    if (total <= 0) return SHACIRA_OK;
+    // lo travels as a kernel-visible device copy: tiny, staged through a stream-ordered allocation
+    int32_t* d_lo = nullptr;
+    CUDA_OK(cudaMallocAsync((void**)&d_lo, sizeof(int32_t) * latent_dim, s));
+    CUDA_OK(cudaMemcpyAsync(d_lo, lo, sizeof(int32_t) * latent_dim, cudaMemcpyHostToDevice, s));
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    symbol_histogram_kernel<<<(int)blocks, 256, 0, s>>>(latents, total, latent_dim, d_lo, num_bins,
+                                                        (unsigned long long*)counts);
+    g_launches.fetch_add(1);
+    cudaError_t le = cudaGetLastError();
+    cudaFreeAsync(d_lo, s);
+    if (le != cudaSuccess) return fail(SHACIRA_ERR_CUDA, "histogram launch: %s", cudaGetErrorString(le));
+    return SHACIRA_OK;
+}
+
+// ---- latent bitstream (host) ---------------------------------------------------------------
+int64_t shacira_ac_encode(const int16_t* symbols, int64_t n, const uint32_t* cdf, int32_t num_symbols, uint8_t* out,
+                          int64_t out_capacity) {
+    if (!symbols || !cdf || !out || n < 0 || num_symbols < 1) {
+        fail(SHACIRA_ERR_INVALID_ARGUMENT, "ac_encode: bad argument");
+        return SHACIRA_ERR_INVALID_ARGUMENT;
+    }
+    if (cdf[0] != 0 || cdf[num_symbols] != (1u << 16)) {
+        fail(SHACIRA_ERR_INVALID_ARGUMENT, "ac_encode: cdf must run from 0 to 65536");
+        return SHACIRA_ERR_INVALID_ARGUMENT;
+    }
+    for (int32_t k = 0; k < num_symbols; ++k)
+        if (cdf[k + 1] <= cdf[k]) {
+            fail(SHACIRA_ERR_INVALID_ARGUMENT, "ac_encode: cdf must be strictly increasing");
+            return SHACIRA_ERR_INVALID_ARGUMENT;
+        }
+    const int64_t r = shacira_ac::encode(symbols, n, cdf, num_symbols, out, out_capacity);
+    if (r == -1) {
+        fail(SHACIRA_ERR_INVALID_ARGUMENT, "ac_encode: symbol out of range");
+        return SHACIRA_ERR_INVALID_ARGUMENT;
+    }
+    if (r < -1) {
+        fail(SHACIRA_ERR_INVALID_ARGUMENT, "ac_encode: output buffer too small (%lld bytes needed)", (long long)(-2 - r));
+        return SHACIRA_ERR_INVALID_ARGUMENT;
+    }
+    return r;
+}
+
+int shacira_ac_decode(const uint8_t* in, int64_t nbytes, const uint32_t* cdf, int32_t num_symbols, int16_t* symbols,
+                      int64_t n) {
+    if (!in || !cdf || !symbols || n < 0 || num_symbols < 1)
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "ac_decode: bad argument");
+    return shacira_ac::decode(in, nbytes, cdf, num_symbols, symbols, n);
+}
+
+// ---- host-buffer step ------------------------------------------------------------------
+namespace {
+struct HostStepScratch {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t up_done = nullptr;
+    int dev = -1;
+};
+thread_local HostStepScratch g_scratch;
+}  // namespace
+
+int shacira_latent_step_host(int32_t dim, const float* coords, int64_t n, const float* latents, int64_t table_rows,
+                             const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                             int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim, int32_t round_flag,
+                             const float* A, const float* shift, int32_t per_level, const float* grad_output,
+                             float* feats, float* grad_latents) {
+    if (n <= 0 || table_rows <= 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "n and table_rows must be positive");
+    if (!coords || !latents || !A || !grad_output || !feats || !grad_latents)
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "NULL host buffer");
+    if (dim != 2 && dim != 3) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "dim must be 2 or 3");
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    HostStepScratch& sc = g_scratch;
+    const int nA = per_level ? num_lods : 1;
+    const size_t LF = (size_t)num_lods * feature_dim;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_coords = al(sizeof(float) * n * dim), b_lat = al(sizeof(float) * table_rows * latent_dim);
+    const size_t b_rows = al(sizeof(float) * n * LF), b_A = al(sizeof(float) * nA * latent_dim * feature_dim);
+    const size_t b_shift = al(sizeof(float) * nA * feature_dim);
+    const size_t need = b_coords + 2 * b_lat + 2 * b_rows + b_A + b_shift;
+    if (sc.dev != dev || sc.bytes < need) {
+        if (sc.ptr) cudaFree(sc.ptr);
+        sc.ptr = nullptr;
+        CUDA_OK(cudaMalloc(&sc.ptr, need));
+        sc.bytes = need;
+        if (sc.dev != dev) {
+            for (int k = 0; k < 2; ++k) CUDA_OK(cudaStreamCreateWithFlags(&sc.stream[k], cudaStreamNonBlocking));
+            CUDA_OK(cudaEventCreateWithFlags(&sc.up_done, cudaEventDisableTiming));
+        }
+        sc.dev = dev;
+    }
+    char* p = (char*)sc.ptr;
+    float* d_coords = (float*)p; p += b_coords;
+    float* d_lat = (float*)p; p += b_lat;
+    float* d_glat = (float*)p; p += b_lat;
+    float* d_feats = (float*)p; p += b_rows;
+    float* d_gout = (float*)p; p += b_rows;
+    float* d_A = (float*)p; p += b_A;
+    float* d_shift = (float*)p;
+    cudaStream_t s0 = sc.stream[0], s1 = sc.stream[1];
+    // stream 0: table + coords up, forward, features down. stream 1: grad_output up (overlaps
+    // the forward), then the backward once the forward's inputs are resident, gradient down.
+    CUDA_OK(cudaMemcpyAsync(d_lat, latents, sizeof(float) * table_rows * latent_dim, cudaMemcpyHostToDevice, s0));
+    CUDA_OK(cudaMemcpyAsync(d_A, A, sizeof(float) * nA * latent_dim * feature_dim, cudaMemcpyHostToDevice, s0));
+    if (shift) CUDA_OK(cudaMemcpyAsync(d_shift, shift, sizeof(float) * nA * feature_dim, cudaMemcpyHostToDevice, s0));
+    CUDA_OK(cudaMemcpyAsync(d_coords, coords, sizeof(float) * n * dim, cudaMemcpyHostToDevice, s0));
+    CUDA_OK(cudaEventRecord(sc.up_done, s0));
+    CUDA_OK(cudaMemcpyAsync(d_gout, grad_output, sizeof(float) * n * LF, cudaMemcpyHostToDevice, s1));
+    int rc = shacira_latent_forward(dim, d_coords, n, d_lat, first_idx, resolutions, num_lods, codebook_bitwidth,
+                                    latent_dim, feature_dim, round_flag, d_A, shift ? d_shift : nullptr, per_level,
+                                    d_feats, nullptr, s0);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(feats, d_feats, sizeof(float) * n * LF, cudaMemcpyDeviceToHost, s0));
+    CUDA_OK(cudaStreamWaitEvent(s1, sc.up_done, 0));
+    rc = shacira_latent_backward(dim, d_coords, n, d_gout, nullptr, first_idx, resolutions, num_lods,
+                                 codebook_bitwidth, latent_dim, feature_dim, d_A, per_level, table_rows, 1, d_glat,
+                                 nullptr, nullptr, s1);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(grad_latents, d_glat, sizeof(float) * table_rows * latent_dim, cudaMemcpyDeviceToHost, s1));
+    CUDA_OK(cudaStreamSynchronize(s0));
+    CUDA_OK(cudaStreamSynchronize(s1));
+    return SHACIRA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,243 @@
+// entropy_kernels.cuh -- fused factorized-density bit-rate estimate (forward + backward in one
+// pass) and the symbol/histogram kernels behind LatentGrid.size().
+//
+// Reference: LatentGrid.ent_loss  wisp/models/grids/latent_grid.py:122-136
+//            Bitparm/BitEstimator  wisp/models/prob_models/bit_estimator.py:9-65
+//            LatentGrid.size       wisp/models/grids/latent_grid.py:138-153
+#pragma once
+#include "common.cuh"
+
+namespace shacira {
+
+constexpr int kEntBlock = 256;
+constexpr int kMaxEntC = 16;
+
+struct LevelBounds {
+    int32_t first[SHACIRA_MAX_LEVELS + 1];  // first row of each level, then total rows
+    int32_t num_lods;
+};
+
+// One evaluation of the CDF chain at x, keeping what the reverse sweep needs.
+struct CdfTrace {
+    float xin[3];  // input of non-final layer k
+    float th[3];   // tanh(u_k)
+    float xf;      // input of the final layer
+    float F;       // sigmoid output
+};
+
+__device__ __forceinline__ float cdf_forward(float x, int m, const float* sp, const float* b, const float* ta,
+                                             int C, int ch, CdfTrace& tr) {
+    // non-final layers f1..fm: u = x*softplus(h) + b ; x = u + tanh(u)*tanh(a)   (bit_estimator.py:43-44)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (k < m) {
+            tr.xin[k] = x;
+            const float u = fmaf(x, sp[k * C + ch], b[k * C + ch]);
+            const float th = tanhf(u);
+            tr.th[k] = th;
+            x = fmaf(th, ta[k * C + ch], u);
+        }
+    }
+    // final layer f4: sigmoid(x*softplus(h) + b)                                  (bit_estimator.py:41)
+    tr.xf = x;
+    const float v = fmaf(x, sp[3 * C + ch], b[3 * C + ch]);
+    tr.F = 1.0f / (1.0f + expf(-v));
+    return tr.F;
+}
+
+// Reverse sweep: given G = d(loss)/dF, accumulate d/d{softplus(h), b, tanh(a)} per layer and
+// return d(loss)/dx.
+__device__ __forceinline__ float cdf_backward(float G, int m, const float* sp, const float* ta, int C, int ch,
+                                              const CdfTrace& tr, float (&d_sp)[4], float (&d_b)[4],
+                                              float (&d_ta)[4]) {
+    float gv = G * tr.F * (1.0f - tr.F);
+    d_sp[3] += gv * tr.xf;
+    d_b[3] += gv;
+    float gx = gv * sp[3 * C + ch];
+#pragma unroll
+    for (int k = 2; k >= 0; --k) {
+        if (k < m) {
+            const float th = tr.th[k];
+            d_ta[k] += gx * th;
+            const float gu = gx * fmaf(1.0f - th * th, ta[k * C + ch], 1.0f);
+            d_sp[k] += gu * tr.xin[k];
+            d_b[k] += gu;
+            gx = gu * sp[k * C + ch];
+        }
+    }
+    return gx;
+}
+
+// params [4][3][C] = {f1,f2,f3,f4} x {h,b,a}. total = rows*C elements, element e -> (row e/C, ch e%C).
+__global__ void __launch_bounds__(kEntBlock)
+entropy_kernel(const float* __restrict__ latents, const float* __restrict__ noise, int64_t total, int C,
+               const float* __restrict__ params, int num_layers, const __grid_constant__ LevelBounds lb,
+               double* __restrict__ bits, float* __restrict__ grad_latents, float* __restrict__ grad_params) {
+    __shared__ float s_sp[4 * kMaxEntC], s_b[4 * kMaxEntC], s_ta[4 * kMaxEntC];
+    __shared__ float s_dsp[4 * kMaxEntC], s_dta[4 * kMaxEntC];  // chain-rule factors
+    __shared__ float s_lvl[SHACIRA_MAX_LEVELS];
+    __shared__ float s_acc[3 * 4 * kMaxEntC];
+    __shared__ double s_total;
+    const int tid = threadIdx.x;
+    if (tid < 4 * C) {
+        const int k = tid / C, ch = tid % C;
+        const float h = params[(k * 3 + 0) * C + ch];
+        const float a = params[(k * 3 + 2) * C + ch];
+        // F.softplus(h): beta 1, threshold 20
+        s_sp[tid] = (h > 20.0f) ? h : log1pf(expf(h));
+        s_dsp[tid] = 1.0f / (1.0f + expf(-h));  // d softplus / dh
+        s_b[tid] = params[(k * 3 + 1) * C + ch];
+        const float t = (k < 3) ? tanhf(a) : 0.0f;
+        s_ta[tid] = t;
+        s_dta[tid] = 1.0f - t * t;
+    }
+    if (tid < SHACIRA_MAX_LEVELS) s_lvl[tid] = 0.0f;
+    for (int e = tid; e < 3 * 4 * kMaxEntC; e += kEntBlock) s_acc[e] = 0.0f;
+    if (tid == 0) s_total = 0.0;
+    __syncthreads();
+
+    const int m = min(num_layers, 4) - 1;  // non-final layers in use (bit_estimator.py:58-64)
+    const int lane = tid & 31;
+    const float inv_ln2 = 1.0f / 0.6931471805599453f;
+    float d_sp[4] = {0, 0, 0, 0}, d_b[4] = {0, 0, 0, 0}, d_ta[4] = {0, 0, 0, 0};
+    float my_bits = 0.0f;
+    const int64_t stride = (int64_t)gridDim.x * kEntBlock;  // multiple of C (C divides 256)
+    const int ch = (int)(((int64_t)blockIdx.x * kEntBlock + tid) % C);
+    const int64_t rounds = (total + stride - 1) / stride;
+    for (int64_t r = 0; r < rounds; ++r) {
+        const int64_t e = r * stride + (int64_t)blockIdx.x * kEntBlock + tid;
+        const bool live = e < total;
+        float bval = 0.0f;
+        int lvl = 0;
+        if (live) {
+            const float w = __ldg(latents + e);
+            const float x = noise ? (w + __ldg(noise + e)) : rintf(w);  // latent_grid.py:132
+            CdfTrace up, lo;
+            const float Fu = cdf_forward(x + 0.5f, m, s_sp, s_b, s_ta, C, ch, up);
+            const float Fl = cdf_forward(x - 0.5f, m, s_sp, s_b, s_ta, C, ch, lo);
+            const float p = Fu - Fl;
+            const float raw = -logf(p + 1e-10f) * inv_ln2;  // latent_grid.py:135
+            bval = fminf(fmaxf(raw, 0.0f), 50.0f);
+            // d clamp: pass-through inside [0, 50] (inclusive, as torch.clamp)
+            const float g_raw = (raw >= 0.0f && raw <= 50.0f) ? 1.0f : 0.0f;
+            const float g_p = -g_raw * inv_ln2 / (p + 1e-10f);
+            const float gx_u = cdf_backward(g_p, m, s_sp, s_ta, C, ch, up, d_sp, d_b, d_ta);
+            const float gx_l = cdf_backward(-g_p, m, s_sp, s_ta, C, ch, lo, d_sp, d_b, d_ta);
+            if (grad_latents) grad_latents[e] = noise ? (gx_u + gx_l) : 0.0f;  // round() has zero gradient
+            if (lb.num_lods > 0) {
+                const int32_t row = (int32_t)(e / C);
+                int a = 0, bnd = lb.num_lods;  // last level whose first row <= row
+                while (bnd - a > 1) {
+                    const int mid = (a + bnd) >> 1;
+                    if (lb.first[mid] <= row) a = mid; else bnd = mid;
+                }
+                lvl = a;
+            }
+        }
+        my_bits += bval;
+        if (lb.num_lods > 0) {
+            const int l0 = __shfl_sync(0xffffffffu, lvl, 0);
+            const float s = warp_sum((live && lvl == l0) ? bval : 0.0f);
+            if (lane == 0) atomicAdd(&s_lvl[l0], s);
+            if (live && lvl != l0) atomicAdd(&s_lvl[lvl], bval);
+        }
+    }
+    // block reduction: total bits (double) and parameter gradients per channel
+    const float wsum = warp_sum(my_bits);
+    if (lane == 0) atomicAdd(&s_total, (double)wsum);
+    if (grad_params) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v0 = d_sp[k], v1 = d_b[k], v2 = d_ta[k];
+            // lanes l and l^o share a channel when o is a multiple of C
+            for (int o = 16; o >= C; o >>= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+            }
+            if (lane < C) {
+                const int c2 = (C <= 32) ? ((tid & ~31) + lane) % C : 0;
+                atomicAdd(&s_acc[(k * 3 + 0) * kMaxEntC + c2], v0);
+                atomicAdd(&s_acc[(k * 3 + 1) * kMaxEntC + c2], v1);
+                atomicAdd(&s_acc[(k * 3 + 2) * kMaxEntC + c2], v2);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) atomicAdd(bits, s_total);
+    if (tid < lb.num_lods && s_lvl[tid] != 0.0f) atomicAdd(bits + 1 + tid, (double)s_lvl[tid]);
+    if (grad_params && tid < 4 * C) {
+        const int k = tid / C, c2 = tid % C;
+        // chain to the raw parameters: h through softplus, a through tanh
+        red_add(grad_params + (k * 3 + 0) * C + c2, s_acc[(k * 3 + 0) * kMaxEntC + c2] * s_dsp[tid]);
+        red_add(grad_params + (k * 3 + 1) * C + c2, s_acc[(k * 3 + 1) * kMaxEntC + c2]);
+        if (k < 3) red_add(grad_params + (k * 3 + 2) * C + c2, s_acc[(k * 3 + 2) * kMaxEntC + c2] * s_dta[tid]);
+    }
+}
+
+// ---- symbols and histogram ---------------------------------------------------------------
+__global__ void init_minmax_kernel(int32_t* minmax, int C) {
+    const int c = threadIdx.x;
+    if (c < C) {
+        minmax[2 * c + 0] = INT32_MAX;
+        minmax[2 * c + 1] = INT32_MIN;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+quantize_symbols_kernel(const float* __restrict__ latents, int64_t total, int C, int16_t* __restrict__ symbols,
+                        int32_t* __restrict__ minmax) {
+    __shared__ int32_t s_min[kMaxEntC], s_max[kMaxEntC];
+    if (threadIdx.x < C) {
+        s_min[threadIdx.x] = INT32_MAX;
+        s_max[threadIdx.x] = INT32_MIN;
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    const int ch = (int)(((int64_t)blockIdx.x * 256 + threadIdx.x) % C);
+    int32_t lo = INT32_MAX, hi = INT32_MIN;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += stride) {
+        const int32_t q = __float2int_rn(__ldg(latents + e));  // torch.round: half to even
+        if (symbols) symbols[e] = (int16_t)q;
+        lo = min(lo, q);
+        hi = max(hi, q);
+    }
+    if (lo <= hi) {
+        atomicMin(&s_min[ch], lo);
+        atomicMax(&s_max[ch], hi);
+    }
+    __syncthreads();
+    if (threadIdx.x < C && s_min[threadIdx.x] <= s_max[threadIdx.x]) {
+        atomicMin(&minmax[2 * threadIdx.x + 0], s_min[threadIdx.x]);
+        atomicMax(&minmax[2 * threadIdx.x + 1], s_max[threadIdx.x]);
+    }
+}
+
+constexpr int kHistSmemBins = 8192;
+
+__global__ void __launch_bounds__(256)
+symbol_histogram_kernel(const float* __restrict__ latents, int64_t total, int C, const int32_t* __restrict__ lo,
+                        int num_bins, unsigned long long* __restrict__ counts) {
+    __shared__ uint32_t s_hist[kHistSmemBins];
+    const bool use_smem = (int64_t)C * num_bins <= kHistSmemBins;
+    if (use_smem) {
+        for (int e = threadIdx.x; e < C * num_bins; e += 256) s_hist[e] = 0u;
+        __syncthreads();
+    }
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    const int ch = (int)(((int64_t)blockIdx.x * 256 + threadIdx.x) % C);
+    const int32_t off = lo[ch];
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += stride) {
+        const int32_t bin = __float2int_rn(__ldg(latents + e)) - off;
+        if (bin < 0 || bin >= num_bins) continue;  // caller sizes the bins from the min/max pass
+        if (use_smem) atomicAdd(&s_hist[ch * num_bins + bin], 1u);
+        else atomicAdd(&counts[(int64_t)ch * num_bins + bin], 1ull);
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < C * num_bins; e += 256)
+            if (s_hist[e]) atomicAdd(&counts[e], (unsigned long long)s_hist[e]);
+    }
+}
+
+}  // namespace shacira

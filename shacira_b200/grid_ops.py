@@ -1,0 +1,147 @@
+"""Host-side mirror of the reference's `wisp/ops/grid.py` (autograd Functions + wrappers).
+
+`hashgrid` / `hashgrid2d` keep the reference signatures (wisp/ops/grid.py:113-131,178-196),
+including the arguments the reference accepts and ignores (`lod_idx`, `codebook_sizes`,
+SURVEY Q9) and the exception for odd feature dims (:75,:140, Q10). `latent_hashgrid` is the
+fused quantize -> gather -> lerp -> decode op that `LatentGrid.interpolate` uses instead of
+`latent_dec(codebook)` followed by `hashgrid*()`.
+"""
+import torch
+
+from . import _lib
+from ._C import ops as _ops
+from ._C.ops import _host_ints
+
+_amp_fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_amp_bwd = torch.amp.custom_bwd(device_type="cuda")
+
+
+class HashGridInterpolate(torch.autograd.Function):
+    """wisp/ops/grid.py:69-111. fp32 compute also under autocast (the reference casts to half)."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, coords, resolutions, codebook_bitwidth, lod_idx, codebook, codebook_sizes, codebook_first_idx):
+        if codebook[0].shape[-1] % 2 == 1:
+            raise Exception("The codebook feature dimension needs to be a multiple of 2.")
+        feats_out = _ops.hashgrid_interpolate_cuda(coords.float().contiguous(), codebook, codebook_first_idx,
+                                                   resolutions, codebook_bitwidth)
+        ctx.save_for_backward(coords, codebook_first_idx)
+        ctx.resolutions = resolutions
+        ctx.codebook_bitwidth = codebook_bitwidth
+        ctx.table_shape = tuple(codebook.shape)
+        return feats_out
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, grad_output):
+        coords, first_idx = ctx.saved_tensors
+        rows, feature_dim = ctx.table_shape
+        grad_codebook = _lib.hashgrid_backward(coords.float().contiguous(), grad_output.contiguous(),
+                                               _host_ints(first_idx), list(ctx.resolutions), ctx.codebook_bitwidth,
+                                               feature_dim, rows)
+        return (None, None, None, None, grad_codebook, None, None)
+
+
+class HashGridInterpolate2D(HashGridInterpolate):
+    """wisp/ops/grid.py:135-176 (one kernel family serves both dimensions here)."""
+
+
+def hashgrid(coords, resolutions, codebook_bitwidth, lod_idx, codebook, codebook_sizes, codebook_first_idx):
+    """3D hash-grid query + trilinear interpolation. coords [batch, 3] -> [batch, F * num_lods]."""
+    batch, dim = coords.shape
+    feats = HashGridInterpolate.apply(coords.contiguous(), resolutions, codebook_bitwidth, lod_idx, codebook,
+                                      codebook_sizes, codebook_first_idx)
+    return feats.reshape(batch, codebook.shape[1] * len(resolutions))
+
+
+def hashgrid2d(coords, resolutions, codebook_bitwidth, lod_idx, codebook, codebook_sizes, codebook_first_idx):
+    """2D hash-grid query + bilinear interpolation. coords [batch, 2] -> [batch, F * num_lods]."""
+    batch, dim = coords.shape
+    feats = HashGridInterpolate2D.apply(coords.contiguous(), resolutions, codebook_bitwidth, lod_idx, codebook,
+                                        codebook_sizes, codebook_first_idx)
+    return feats.reshape(batch, codebook.shape[1] * len(resolutions))
+
+
+class _HashGridAnyF(torch.autograd.Function):
+    """Plain interpolate without the even-F restriction (the kernels handle F = 1 natively)."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, coords, codebook, first_idx, resolutions, bitwidth):
+        ctx.save_for_backward(coords)
+        ctx.meta = (first_idx, tuple(resolutions), bitwidth, tuple(codebook.shape))
+        return _lib.hashgrid_forward(coords, codebook, first_idx, resolutions, bitwidth)
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, grad_output):
+        (coords,) = ctx.saved_tensors
+        first_idx, resolutions, bitwidth, (rows, F) = ctx.meta
+        g = _lib.hashgrid_backward(coords, grad_output.contiguous(), first_idx, resolutions, bitwidth, F, rows)
+        return (None, g, None, None, None)
+
+
+def hashgrid_any(coords, codebook, first_idx, resolutions, bitwidth):
+    return _HashGridAnyF.apply(coords.float().contiguous(), codebook, _host_ints(first_idx), list(resolutions),
+                               int(bitwidth))
+
+
+class LatentHashGrid(torch.autograd.Function):
+    """Fused LatentGrid.interpolate for affine latent decoders (latent_grid.py:359-368 +
+    basic_latent_decoder.py:85-95,192-194): feats = lerp(round?(latents)) @ A + shift."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, coords, latents, A, shift, first_idx, resolutions, bitwidth, round_flag):
+        F = A.shape[2]
+        need_dec = bool(ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
+        feats, z = _lib.latent_forward(coords, latents, first_idx, resolutions, bitwidth, A, shift, F, round_flag,
+                                       save_z=need_dec)
+        ctx.save_for_backward(coords, A.detach(), z if z is not None else coords.new_empty(0))
+        ctx.meta = (first_idx, tuple(resolutions), bitwidth, tuple(latents.shape), F, need_dec, shift is not None,
+                    A.shape[0])
+        return feats
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, grad_output):
+        coords, A, z = ctx.saved_tensors
+        first_idx, resolutions, bitwidth, (rows, C), F, need_dec, has_shift, nA = ctx.meta
+        gl, gA, gS = _lib.latent_backward(coords, grad_output.contiguous(), z if need_dec else None, first_idx,
+                                          resolutions, bitwidth, A, C, F, rows, need_dec)
+        if need_dec and nA == 1:
+            gA = gA.sum(0, keepdim=True)
+            gS = gS.sum(0, keepdim=True)
+        if not ctx.needs_input_grad[1]:
+            gl = None
+        return (None, gl, gA if need_dec else None, gS if (need_dec and has_shift) else None, None, None, None, None)
+
+
+def latent_hashgrid(coords, latents, A, shift, first_idx, resolutions, bitwidth, round_flag=True):
+    """coords [N, 2|3]; latents [T, C]; A [1|L, C, F]; shift [1|L, F] | None -> feats [N, L*F]."""
+    return LatentHashGrid.apply(coords.float().contiguous(), latents, A, shift, _host_ints(first_idx),
+                                list(resolutions), int(bitwidth), bool(round_flag))
+
+
+class EntropyBits(torch.autograd.Function):
+    """Fused LatentGrid.ent_loss body (latent_grid.py:132-135): total bits of the factorized density.
+    The kernel produces value and gradients in one pass; backward only scales them."""
+
+    @staticmethod
+    def forward(ctx, latents, noise, params, num_layers, first_idx):
+        bits, gl, gp = _lib.entropy_bits(latents, noise, params, num_layers, first_idx, want_grads=True)
+        ctx.save_for_backward(gl, gp)
+        ctx.per_level = bits[1:].to(torch.float32)
+        return bits[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_total):
+        gl, gp = ctx.saved_tensors
+        return (gl * grad_total if ctx.needs_input_grad[0] else None, None,
+                gp * grad_total if ctx.needs_input_grad[2] else None, None, None)
+
+
+def entropy_bits(latents, noise, params, num_layers, first_idx=None):
+    fi = _host_ints(first_idx) if first_idx is not None else None
+    return EntropyBits.apply(latents, noise, params, int(num_layers), fi)
