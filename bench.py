@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- latent hash-grid fwd+bwd throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this package (CUDA, C-ABI)
+    python bench.py --impl reference --steps K --warmup W    # the reference's path on the host cores
+    python bench.py --impl reference-gpu                     # the reference's own CUDA kernels (oracle/_ref)
+
+Workload (BASELINE.json configs[1]): the Kodak-shape image INR grid -- 768x512
+pixel-centre coordinates in reference (y, x) order shuffled by randperm, 2D LatentGrid, 16 levels
+16->512, 2^16-row tables (374 612 rows), latent_dim = feature_dim = 1, affine per-table decoder
+with shift, straight-through rounding. One STEP = one forward + one backward of the latent grid
+over the full 393 216-point batch: quantise + decode + interpolate, then the scatter-add to the
+latents plus the decoder's scale/shift gradients. Synthetic, seeded data; random-init parameters
+(latents scaled so that rounding is non-trivial).
+
+Multi-GPU (N > 1, torchrun): every rank fits its own independent image (different shuffle,
+different latents) -- the path shards by independent units, there is no data-path collective,
+scaling is weak. Timing is on the device (CUDA events), barrier + synchronize on both sides, max
+over ranks.
+
+The JSON line also carries: `roofline` (dominant kernel, algorithmic bytes / measured launch time
+against the measured HBM copy peak), `kernels` (every kernel of the step), `entropy` (the fused
+bit-rate kernel, reported beside the step), `cpu_baseline` (the oracle port on this box's host
+cores), `e2e` (the same fwd+bwd through the host-buffer C-ABI entry, PCIe copies inside the timed region),
+`clocks`, `gpu_launches`.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 512, 768
+NUM_LODS, BITWIDTH, MIN_RES, MAX_RES = 16, 16, 16, 512
+LATENT_DIM, FEATURE_DIM, DIM = 1, 1, 2
+ROTATE = 4  # independent input/output buffer sets cycled through so that no step finds its streams in L2
+
+
+def algorithmic_bytes_per_point(D, L, C, F):
+    """fwd [4D + 2^D*L*C*4 + 4*L*F] + bwd [4D + 4*L*F + 2^D*L*C*4]."""
+    one = 4 * D + (2 ** D) * L * C * 4 + 4 * L * F
+    return one, one
+
+
+def make_workload(seed):
+    b = np.exp((np.log(MAX_RES) - np.log(MIN_RES)) / (NUM_LODS - 1))  # latent_grid.py:280-281
+    res = [int(1 + np.floor(MIN_RES * (b ** l))) for l in range(NUM_LODS)]
+    sizes, first, T = oracle_layout(res)
+    rng = np.random.default_rng(seed)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    coords = np.stack([(ys.reshape(-1) / H - 0.5) * 2, (xs.reshape(-1) / W - 0.5) * 2], 1).astype(np.float32)
+    sets = []
+    for r in range(ROTATE):
+        perm = rng.permutation(coords.shape[0])
+        sets.append(dict(coords=np.ascontiguousarray(coords[perm]),
+                         grad_out=rng.standard_normal((coords.shape[0], NUM_LODS * FEATURE_DIM)).astype(np.float32)))
+    latents = ((rng.random((T, LATENT_DIM), dtype=np.float32) - 0.5) * 16).astype(np.float32)  # U(-8, 8)
+    scale = (rng.standard_normal((1, LATENT_DIM, FEATURE_DIM)) * 0.1).astype(np.float32)
+    shift = (rng.standard_normal((1, FEATURE_DIM)) * 0.05).astype(np.float32)
+    noise = (rng.random((T, LATENT_DIM), dtype=np.float32) - 0.5).astype(np.float32)
+    prob = (rng.standard_normal((4, 3, LATENT_DIM)) * 0.3).astype(np.float32)
+    return dict(res=res, first=first, T=T, sets=sets, latents=latents, A=scale, shift=shift, noise=noise, prob=prob)
+
+
+def oracle_layout(res):
+    sizes = [min(2 ** BITWIDTH, r ** DIM) for r in res]
+    first = [0]
+    for s in sizes[:-1]:
+        first.append(first[-1] + s)
+    return sizes, first, sum(sizes)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
+class ClockSampler:
+    """Polls NVML during the timed region: SM clock and clock-event (throttle) reasons."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step(wl, s, want_entropy=False):
+    """One step of the reference's path restated on the CPU: table-side round + decode (torch), then the
+    reference's interpolation forward and backward (oracle/hashgrid_oracle.c, OpenMP). F == 1 is padded to
+    2 and strided back exactly like LatentGrid.interpolate (latent_grid.py:361-363,370)."""
+    import torch
+    import oracle
+    from oracle import latent_oracle as lo
+    cb = torch.from_numpy(wl["latents"])
+    table = lo.decode_single(lo.ste_round(cb), torch.ones(LATENT_DIM), torch.from_numpy(wl["A"][0]),
+                             torch.from_numpy(wl["shift"]))
+    table2 = table.repeat(1, 2).numpy()
+    feats = oracle.forward(s["coords"], table2, wl["first"], wl["res"], BITWIDTH)[:, ::2]
+    g2 = np.zeros((s["coords"].shape[0], NUM_LODS * 2), dtype=np.float32)
+    g2[:, ::2] = s["grad_out"]
+    gtab = oracle.backward(s["coords"], g2, wl["T"], wl["first"], wl["res"], BITWIDTH, 2)
+    glat = gtab.sum(1, keepdims=True) * wl["A"][0, 0, 0]  # straight-through + d decode / d latent
+    ent = None
+    if want_entropy:
+        p = wl["prob"]
+        params = {"f%d" % (i + 1): (torch.from_numpy(p[i, 0:1]), torch.from_numpy(p[i, 1:2]),
+                                    torch.from_numpy(p[i, 2:3]) if i < 3 else None) for i in range(4)}
+        ent = lo.ent_loss(cb, torch.from_numpy(wl["noise"]), params, 2)[1].item()
+    return feats, glat, ent
+
+
+def run_cpu(wl, steps, warmup):
+    import oracle
+    n = wl["sets"][0]["coords"].shape[0]
+    for i in range(warmup):
+        cpu_step(wl, wl["sets"][i % ROTATE])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        cpu_step(wl, wl["sets"][i % ROTATE])
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    cpu_step(wl, wl["sets"][0], want_entropy=True)
+    t_with_ent = time.perf_counter() - t1
+    return {"mpts": n * steps / dt / 1e6, "ms_per_step": dt / steps * 1e3, "threads": oracle.num_threads(),
+            "entropy_ms": max(0.0, t_with_ent * 1e3 - dt / steps * 1e3)}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = make_workload(0)
+    n = wl["sets"][0]["coords"].shape[0]
+    steps, warmup = args.steps, args.warmup
+    r = run_cpu(wl, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "latent hash-grid fwd+bwd Mpoints/s per GPU", "value": r["mpts"],
+        "unit": "Mpoints/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": r["mpts"], "unit": "Mpoints/s", "cores": r["threads"], "kind": "port",
+                         "sample": "%d steps x full %d-point batch (fwd+bwd incl. table decode), OpenMP oracle port; "
+                                   "the reference has no CPU implementation of this path" % (steps, n)},
+        "e2e": {"value": r["mpts"], "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "entropy": {"ms": r["entropy_ms"], "impl": "torch CPU restatement of ent_loss forward (no backward)"},
+        "host_cpus": os.cpu_count(),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config():
+    return {"workload": "BASELINE cfg2: Kodak-shape 768x512 image INR grid, 2D LatentGrid, 16 levels 16->512, "
+                        "2^16-row tables (374612 rows), C=F=1, affine decoder, STE rounding; 393216 points/step",
+            "points_per_step": H * W, "levels": NUM_LODS, "bitwidth": BITWIDTH, "latent_dim": LATENT_DIM,
+            "feature_dim": FEATURE_DIM, "step": "latent grid forward + backward (latents + decoder grads)",
+            "l2": "inputs larger than L2: %d rotating input/output sets (~%d MB) cycled between steps" % (
+                ROTATE, ROTATE * (H * W * (8 + 3 * 64)) // (1 << 20)),
+            "parallelism": "independent images, one per GPU, no collective"}
+
+
+# ------------------------------------------------------------------------------------------------
+# this package
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    if args.impl == "reference-gpu":
+        return reference_gpu_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from shacira_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
+                         "(use --impl reference for the host-core baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    wl = make_workload(rank)  # every rank: its own image (independent unit)
+    n, T, L = H * W, wl["T"], NUM_LODS
+    d = lambda a: torch.from_numpy(a).to(dev)
+    sets = [dict(coords=d(s["coords"]), grad_out=d(s["grad_out"])) for s in wl["sets"]]
+    latents, A, shift = d(wl["latents"]), d(wl["A"]), d(wl["shift"])
+    noise, prob = d(wl["noise"]), d(wl["prob"])
+    first, res = wl["first"], wl["res"]
+
+    def step(i, ev=None):
+        s = sets[i % ROTATE]
+        if ev is not None:
+            ev[0].record()
+        feats, z = _lib.latent_forward(s["coords"], latents, first, res, BITWIDTH, A, shift, FEATURE_DIM, True, True)
+        if ev is not None:
+            ev[1].record()
+        gl, gA, gS = _lib.latent_backward(s["coords"], s["grad_out"], z, first, res, BITWIDTH, A, LATENT_DIM,
+                                          FEATURE_DIM, T, True)
+        if ev is not None:
+            ev[2].record()
+        return feats, gl
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count()
+    sampler.start()
+    start.record()
+    for i in range(steps):
+        step(i, evs[i])
+    stop.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    if world > 1:
+        dist.barrier()
+    total_ms = start.elapsed_time(stop)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+
+    # the fused bit-rate kernel, reported beside the step (table-side: once per step, not per point)
+    for _ in range(3):
+        _lib.entropy_bits(latents, noise, prob, 2, first)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        _lib.entropy_bits(latents, noise, prob, 2, first)
+    e1.record()
+    torch.cuda.synchronize()
+    ent_ms = e0.elapsed_time(e1) / 20
+
+    # end to end: the host-buffer C-ABI entry, pinned host memory, copies inside the timed region
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    h_sets = [dict(coords=pin(s["coords"]), grad_out=pin(s["grad_out"])) for s in wl["sets"][:2]]
+    h_lat, h_A, h_shift = pin(wl["latents"]), pin(wl["A"]), pin(wl["shift"])
+    h_feats = torch.empty((n, L * FEATURE_DIM), dtype=torch.float32).pin_memory()
+    h_gl = torch.empty((T, LATENT_DIM), dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(steps, 50))
+    for i in range(3):
+        _lib.latent_step_host(h_sets[i % 2]["coords"], h_lat, first, res, BITWIDTH, h_A, h_shift,
+                              h_sets[i % 2]["grad_out"], True, h_feats, h_gl)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        _lib.latent_step_host(h_sets[i % 2]["coords"], h_lat, first, res, BITWIDTH, h_A, h_shift,
+                              h_sets[i % 2]["grad_out"], True, h_feats, h_gl)
+    e2e_s = time.perf_counter() - t0  # the call synchronises before returning
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    h2d = 4 * (n * DIM + T * LATENT_DIM + n * L * FEATURE_DIM + A.numel() + shift.numel())
+    d2h = 4 * (n * L * FEATURE_DIM + T * LATENT_DIM)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peaks()
+    bf, bb = algorithmic_bytes_per_point(DIM, L, LATENT_DIM, FEATURE_DIM)
+    kernels = {
+        "latent_fwd": {"ms": fwd_ms, "algorithmic_GBs": bf * n / fwd_ms / 1e6, "bytes_per_point": bf},
+        "latent_bwd": {"ms": bwd_ms, "algorithmic_GBs": bb * n / bwd_ms / 1e6, "bytes_per_point": bb},
+    }
+    dom = "latent_bwd" if bwd_ms >= fwd_ms else "latent_fwd"
+    traffic = recorded_traffic()
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["algorithmic_GBs"], "peak": peak,
+                "unit": "GB/s", "frac": kernels[dom]["algorithmic_GBs"] / peak,
+                "traffic": traffic.get(dom), "peak_source": peak_src,
+                "step_achieved": (bf + bb) * n * steps / total_ms / 1e6,
+                "step_frac": (bf + bb) * n * steps / total_ms / 1e6 / peak}
+    value = n * world * steps / (total_ms * 1e-3) / 1e6
+    line = {
+        "metric": "latent hash-grid fwd+bwd Mpoints/s per GPU", "value": value, "unit": "Mpoints/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
+        "per_gpu": value / world, "roofline": roofline, "kernels": kernels,
+        "entropy": {"ms": ent_ms, "rows": T, "GBs": 12.0 * T * LATENT_DIM / ent_ms / 1e6,
+                    "note": "fused bit-rate fwd+bwd kernel, 12 B/entry algorithmic"},
+        "e2e": {"value": n * world * e2e_steps / e2e_s / 1e6, "unit": "Mpoints/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                "api": "shacira_latent_step_host (C-ABI, pinned host buffers in and out)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        r = run_cpu(make_workload(0), 3, 1)
+        line["cpu_baseline"] = {"value": r["mpts"], "unit": "Mpoints/s", "cores": r["threads"], "kind": "port",
+                                "sample": "3 steps x full %d-point batch (fwd+bwd incl. table decode) after 1 warm-up; "
+                                          "OpenMP oracle port of the reference kernels" % n,
+                                "host_cpus": os.cpu_count()}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def reference_gpu_arm(args):
+    """`--impl reference-gpu`: the reference's own CUDA kernels on this GPU (REF-GPU in BASELINE.md), a
+    separate invocation so that the default run never touches oracle/."""
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    dev = torch.device("cuda", 0)
+    wl = make_workload(0)
+    d = lambda a: torch.from_numpy(a).to(dev)
+    sets = [dict(coords=d(s["coords"]), grad_out=d(s["grad_out"])) for s in wl["sets"]]
+    r = time_reference_kernels(wl, dev, sets, d(wl["latents"]), d(wl["A"]), d(wl["shift"]), args.steps, args.warmup)
+    r.update({"impl": "reference-gpu", "metric": "latent hash-grid fwd+bwd Mpoints/s per GPU", "n_gpus": 1,
+              "config": workload_config()})
+    print(json.dumps(r), flush=True)
+    return 0
+
+
+def time_reference_kernels(wl, dev, sets, latents, A, shift, steps=20, warmup=5):
+    """The reference's own path on this GPU: table-side decode with torch ops, repeat(1,2), then its
+    CUDA kernels (oracle/_ref, one launch per level), backward through the same kernels. Baseline only."""
+    try:
+        import torch
+        from oracle import build_ref
+        ref = build_ref.load()
+        if ref is None:
+            return {"unavailable": "oracle/_ref/wisp_ref_ops.so not built"}
+        first_dev = torch.tensor(wl["first"], dtype=torch.int32, device=dev)
+        n = H * W
+
+        def ref_step(i):
+            s = sets[i % ROTATE]
+            table = (torch.round(latents) / 1.0) @ A[0] + shift
+            table2 = table.repeat(1, 2)
+            feats = ref.hashgrid_interpolate2d_cuda(s["coords"], table2, first_dev, wl["res"], BITWIDTH)[:, ::2]
+            g2 = torch.zeros((n, NUM_LODS * 2), device=dev)
+            g2[:, ::2] = s["grad_out"]
+            gt = ref.hashgrid_interpolate2d_backward_cuda(s["coords"], g2, table2, first_dev, wl["res"], BITWIDTH, 2, False)
+            return feats, gt.sum(1, keepdim=True) * A[0, 0, 0]
+
+        for i in range(max(warmup, 3)):
+            ref_step(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k = steps
+        e0.record()
+        for i in range(k):
+            ref_step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / k
+        return {"value": n / ms / 1e3, "unit": "Mpoints/s", "ms_per_step": ms,
+                "what": "reference CUDA kernels compiled for sm_100a + torch table decode, same workload, same GPU"}
+    except Exception as e:  # baseline only: never fail the bench over it
+        return {"unavailable": repr(e)[:200]}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

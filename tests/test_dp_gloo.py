@@ -1,0 +1,48 @@
+"""N>1 host logic on CPU: two processes, gloo backend, 127.0.0.1 rendezvous."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from shacira_b200 import dp
+    torch.manual_seed(0)
+    table = torch.nn.Parameter(torch.zeros(1 << 17, 1))        # "latents": reduced in place
+    small = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(7))]
+    frozen = torch.nn.Parameter(torch.zeros(5))                 # no grad: skipped
+    table.grad = torch.full_like(table, float(rank + 1))
+    for i, p in enumerate(small):
+        p.grad = torch.full_like(p, float(10 * (i + 1) + rank))
+    n = dp.allreduce_grads([table, frozen] + small)
+    ok = n == 2 and bool((table.grad == 3.0).all())             # 1 + 2
+    ok &= bool((small[0].grad == 21.0).all()) and bool((small[1].grad == 41.0).all())
+    b, e = dp.split_rays(4096, rank, world)
+    ok &= (e - b) == 2048
+    res = dp.gather_results({"rank": rank, "units": dp.shard_units(5)})
+    ok &= [r["units"] for r in res] == [[0, 2, 4], [1, 3]]
+    table.grad = torch.full_like(table, float(rank + 1))
+    dp.allreduce_grads([table], average=True)
+    ok &= bool((table.grad == 1.5).all())
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_allreduce_grads_world2_gloo():
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    assert dict(out) == {0: True, 1: True}
