@@ -109,6 +109,39 @@ int shacira_latent_backward(int32_t dim, const float* coords, int64_t n, const f
                             const float* A, int32_t per_level, int64_t table_rows, int32_t zero_first,
                             float* grad_latents, float* grad_A, float* grad_shift, shacira_stream_t stream);
 
+/* ---- tiled fast path: spatial plan + planned fused forward / backward ----------------- */
+/* A plan bins the points of ONE coordinate set into power-of-two spatial tiles (about
+ * tile_points per tile; 0 = default) and keeps the permutation and a sorted copy of the
+ * coordinates on the device. It depends only on the coordinates, not on the levels, and is
+ * reusable for every forward/backward over those coordinates (an image fit uses the same
+ * coordinates for tens of thousands of steps). Creation is asynchronous on `stream`.
+ * The planned kernels give one CTA per tile, stage the grid nodes the tile touches in shared
+ * memory (forward) or accumulate into them in fixed point (backward); DESIGN.md "tiled path".
+ * Results follow the same arithmetic as the unplanned entry points; outputs are in the
+ * ORIGINAL point order. */
+typedef struct shacira_plan shacira_plan_t;
+int shacira_plan_create(int32_t dim, const float* coords, int64_t n, int32_t tile_points, shacira_stream_t stream,
+                        shacira_plan_t** plan);
+int shacira_plan_destroy(shacira_plan_t* plan);
+int shacira_plan_info(const shacira_plan_t* plan, int64_t* n, int32_t* dim, int32_t* tiles_per_axis,
+                      int32_t* ntiles);
+/* Device pointers of the plan's arrays (perm[n], coords_sorted[n,dim], tile_off[ntiles+1]) for tests. */
+int shacira_plan_debug(const shacira_plan_t* plan, const int32_t** perm, const float** coords_sorted,
+                       const int32_t** tile_off);
+/* Same contract as shacira_latent_forward (no zsave: the backward recomputes the interpolation). */
+int shacira_latent_forward_planned(const shacira_plan_t* plan, const float* latents, const int32_t* first_idx,
+                                   const int32_t* resolutions, int32_t num_lods, int32_t codebook_bitwidth,
+                                   int32_t latent_dim, int32_t feature_dim, int32_t round_flag, const float* A,
+                                   const float* shift, int32_t per_level, float* feats, shacira_stream_t stream);
+/* Same contract as shacira_latent_backward; `latents` (+ round_flag) replace zsave and are needed
+ * only when grad_A / grad_shift are requested. */
+int shacira_latent_backward_planned(const shacira_plan_t* plan, const float* grad_output, const float* latents,
+                                    const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                                    int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim,
+                                    int32_t round_flag, const float* A, int32_t per_level, int64_t table_rows,
+                                    int32_t zero_first, float* grad_latents, float* grad_A, float* grad_shift,
+                                    shacira_stream_t stream);
+
 /* ---- factorized-density bit-rate estimate -------------------------------------------- */
 /* LatentGrid.ent_loss (latent_grid.py:122-136) + BitEstimator/Bitparm
  * (wisp/models/prob_models/bit_estimator.py:9-65), forward and backward in one pass:

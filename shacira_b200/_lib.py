@@ -38,6 +38,12 @@ SIGNATURES = {
     "shacira_hashgrid_corners": (ctypes.c_int, [_i32, _vp, _i64, _c_int32_p, _i32, _i32, _vp, _vp, _vp]),
     "shacira_latent_forward": (ctypes.c_int, [_i32, _vp, _i64, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "shacira_latent_backward": (ctypes.c_int, [_i32, _vp, _i64, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "shacira_plan_create": (ctypes.c_int, [_i32, _vp, _i64, _i32, _vp, ctypes.POINTER(_vp)]),
+    "shacira_plan_destroy": (ctypes.c_int, [_vp]),
+    "shacira_plan_info": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), _c_int32_p, _c_int32_p, _c_int32_p]),
+    "shacira_plan_debug": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    "shacira_latent_forward_planned": (ctypes.c_int, [_vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "shacira_latent_backward_planned": (ctypes.c_int, [_vp, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "shacira_entropy_bits": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _c_int32_p, _i32, _vp, _vp, _vp, _vp]),
     "shacira_quantize_symbols": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "shacira_symbol_histogram": (ctypes.c_int, [_vp, _i64, _i32, _c_int32_p, _i32, _vp, _vp]),
@@ -231,6 +237,105 @@ def latent_backward(coords, grad_output, z, first_idx, resolutions, bitwidth, A,
         _check(lib.shacira_latent_backward(dim, _ptr(coords), n, _ptr(grad_output), _ptr(z), fi, rs, L, bitwidth,
                                            latent_dim, feature_dim, _ptr(A), per_level, table_rows, 1, _ptr(gl),
                                            _ptr(gA), _ptr(gS), _stream()))
+    return gl, gA, gS
+
+
+class Plan:
+    """Spatial tile plan of one coordinate set (shacira_plan_create). Holds a reference to the
+    coordinates it was built from so that their storage cannot be recycled while the plan lives."""
+
+    def __init__(self, coords, tile_points=0):
+        lib = load()
+        coords = _f32c(coords, "coords")
+        self.dim = _dim_of(coords)
+        self.n = coords.shape[0]
+        self.device = coords.device
+        self.coords = coords
+        handle = ctypes.c_void_p(0)
+        with torch.cuda.device(coords.device):
+            _check(lib.shacira_plan_create(self.dim, _ptr(coords), self.n, int(tile_points), _stream(),
+                                           ctypes.byref(handle)))
+        self.handle = handle
+
+    def info(self):
+        n, d, g, t = ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+        _check(load().shacira_plan_info(self.handle, ctypes.byref(n), ctypes.byref(d), ctypes.byref(g), ctypes.byref(t)))
+        return {"n": n.value, "dim": d.value, "tiles_per_axis": g.value, "ntiles": t.value}
+
+    def arrays(self):
+        """(perm[n] int32, coords_sorted[n, dim] float32, tile_off[ntiles+1] int32) copied to the host (tests)."""
+        import numpy as np
+        perm, cs, off = ctypes.c_void_p(0), ctypes.c_void_p(0), ctypes.c_void_p(0)
+        _check(load().shacira_plan_debug(self.handle, ctypes.byref(perm), ctypes.byref(cs), ctypes.byref(off)))
+        nt = self.info()["ntiles"]
+        torch.cuda.synchronize(self.device)
+
+        class _Dev:  # alias raw device memory through the CUDA array interface
+            def __init__(self, ptr, count, typestr):
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, True),
+                                                 "version": 2}
+
+        def grab(ptr, count, dtype):
+            typestr = "<i4" if dtype == torch.int32 else "<f4"
+            with torch.cuda.device(self.device):
+                return torch.as_tensor(_Dev(ptr.value, count, typestr), device=self.device).clone().cpu().numpy()
+
+        return (grab(perm, self.n, torch.int32), grab(cs, self.n * self.dim, torch.float32).reshape(self.n, self.dim),
+                grab(off, nt + 1, torch.int32))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            try:
+                load().shacira_plan_destroy(self.handle)
+            finally:
+                self.handle = ctypes.c_void_p(0)
+                self.coords = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def latent_forward_planned(plan, latents, first_idx, resolutions, bitwidth, A, shift, feature_dim, round_flag):
+    lib = load()
+    latents = _f32c(latents, "latents")
+    A = _f32c(A, "A")
+    shift = _f32c(shift, "shift") if shift is not None else None
+    fi, L = _i32_array(first_idx)
+    rs, _ = _i32_array(resolutions)
+    C = latents.shape[1]
+    per_level = 1 if A.shape[0] == L and L > 1 else 0
+    if A.shape[0] not in (1, L) or tuple(A.shape[1:]) != (C, feature_dim):
+        raise ShaciraError(ERR_INVALID_ARGUMENT, "A must be [1|L, C, F], got %s" % (tuple(A.shape),))
+    feats = torch.empty((plan.n, L * feature_dim), dtype=torch.float32, device=plan.device)
+    with torch.cuda.device(plan.device):
+        _check(lib.shacira_latent_forward_planned(plan.handle, _ptr(latents), fi, rs, L, bitwidth, C, feature_dim,
+                                                  1 if round_flag else 0, _ptr(A), _ptr(shift), per_level,
+                                                  _ptr(feats), _stream()))
+    return feats
+
+
+def latent_backward_planned(plan, grad_output, latents, first_idx, resolutions, bitwidth, A, latent_dim, feature_dim,
+                            table_rows, round_flag, want_decoder_grads):
+    lib = load()
+    grad_output = _f32c(grad_output, "grad_output")
+    A = _f32c(A, "A")
+    latents = _f32c(latents, "latents") if latents is not None else None
+    fi, L = _i32_array(first_idx)
+    rs, _ = _i32_array(resolutions)
+    per_level = 1 if A.shape[0] == L and L > 1 else 0
+    dev = plan.device
+    gl = torch.empty((table_rows, latent_dim), dtype=torch.float32, device=dev)
+    gA = gS = None
+    if want_decoder_grads:
+        gA = torch.zeros((L, latent_dim, feature_dim), dtype=torch.float32, device=dev)
+        gS = torch.zeros((L, feature_dim), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.shacira_latent_backward_planned(plan.handle, _ptr(grad_output), _ptr(latents), fi, rs, L, bitwidth,
+                                                   latent_dim, feature_dim, 1 if round_flag else 0, _ptr(A), per_level,
+                                                   table_rows, 1, _ptr(gl), _ptr(gA), _ptr(gS), _stream()))
     return gl, gA, gS
 
 

@@ -10,10 +10,10 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libshacira_b200.so")
-SOURCES = ["capi.cu"]
+SOURCES = ["capi.cu", "tiled_capi.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
 ]
 
 
@@ -34,10 +34,25 @@ def is_stale():
 def build(force=False, verbose=False, extra=()):
     if not force and not is_stale():
         return LIB
-    cmd = ["nvcc"] + NVCC_FLAGS + list(extra) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    # one object per translation unit, compiled in parallel, then one link
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src + ".o")
+        cmd = ["nvcc", "-c"] + NVCC_FLAGS + list(extra) + [os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    link = ["nvcc", "--shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB]
     if verbose:
-        print(" ".join(cmd), flush=True)
-    subprocess.check_call(cmd)
+        print(" ".join(link), flush=True)
+    subprocess.check_call(link)
     return LIB
 
 

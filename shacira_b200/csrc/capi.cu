@@ -1,46 +1,23 @@
 // capi.cu -- the extern "C" surface declared in include/shacira_b200.h: argument validation,
 // level metadata, template dispatch and launches. No torch, no exceptions across the ABI.
-#include <atomic>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-
 #include "arith_coder.inl"
+#include "capi_internal.h"
 #include "entropy_kernels.cuh"
 #include "hashgrid_kernels.cuh"
 
 using namespace shacira;
 
-namespace {
+namespace shacira {
 
-thread_local char g_err[512] = "";
-std::atomic<int64_t> g_launches{0};
-
-int fail(int code, const char* fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-    return code;
+char* last_error_buffer() {
+    thread_local char buf[512] = "";
+    return buf;
+}
+std::atomic<int64_t>& launch_counter() {
+    static std::atomic<int64_t> c{0};
+    return c;
 }
 
-#define CUDA_OK(expr)                                                                          \
-    do {                                                                                       \
-        cudaError_t e__ = (expr);                                                              \
-        if (e__ != cudaSuccess)                                                                \
-            return fail(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver         \
-                            ? SHACIRA_ERR_NO_DEVICE : SHACIRA_ERR_CUDA,                        \
-                        "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
-    } while (0)
-
-#define LAUNCHED()                    \
-    do {                              \
-        g_launches.fetch_add(1);      \
-        CUDA_OK(cudaGetLastError());  \
-    } while (0)
-
-// Level metadata + the checks the reference does not make (SURVEY 8b "error convention").
 int build_levels(int32_t dim, const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
                  int32_t bitwidth, LevelParams& lp) {
     if (dim != 2 && dim != 3) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "dim must be 2 or 3, got %d", dim);
@@ -80,6 +57,17 @@ int build_levels(int32_t dim, const int32_t* first_idx, const int32_t* resolutio
     }
     return SHACIRA_OK;
 }
+
+int check_points(const float* coords, int64_t n) {
+    if (n < 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "n is negative");
+    if (n > 0 && !coords) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "coords is NULL");
+    if (n > ((int64_t)1 << 31) * (int64_t)kBlock / 2) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "n too large");
+    return SHACIRA_OK;
+}
+
+}  // namespace shacira
+
+namespace {
 
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
@@ -136,20 +124,13 @@ int launch_latent_bwd(const float* coords, int64_t n, const float* g, const floa
         default: return fail(SHACIRA_ERR_UNSUPPORTED, "latent_dim %d not in {1,2,4}", (int)C_);          \
     }
 
-int check_points(const float* coords, int64_t n) {
-    if (n < 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "n is negative");
-    if (n > 0 && !coords) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "coords is NULL");
-    if (n > ((int64_t)1 << 31) * (int64_t)kBlock / 2) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "n too large");
-    return SHACIRA_OK;
-}
-
 }  // namespace
 
 extern "C" {
 
 int shacira_abi_version(void) { return SHACIRA_ABI_VERSION; }
-const char* shacira_last_error(void) { return g_err; }
-int64_t shacira_launch_count(void) { return g_launches.load(); }
+const char* shacira_last_error(void) { return last_error_buffer(); }
+int64_t shacira_launch_count(void) { return launch_counter().load(); }
 
 int shacira_device_info(int32_t* sm_count, int64_t* l2_bytes, int64_t* l2_persist_max) {
     int dev = 0;
@@ -352,7 +333,7 @@ int shacira_symbol_histogram(const float* latents, int64_t table_rows, int32_t l
     if (blocks > 148 * 4) blocks = 148 * 4;
     symbol_histogram_kernel<<<(int)blocks, 256, 0, s>>>(latents, total, latent_dim, d_lo, num_bins,
                                                         (unsigned long long*)counts);
-    g_launches.fetch_add(1);
+    launch_counter().fetch_add(1);
     cudaError_t le = cudaGetLastError();
     cudaFreeAsync(d_lo, s);
     if (le != cudaSuccess) return fail(SHACIRA_ERR_CUDA, "histogram launch: %s", cudaGetErrorString(le));

@@ -155,12 +155,11 @@ latent_fwd_kernel(const float* __restrict__ coords, int64_t n, const float* __re
             const int la = per_level ? (l + q) : 0;
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
-                float acc = 0.0f;
+                // torch.round == half-to-even == rintf; contraction order of the reference build
+                float acc = __fmul_rn(round_flag ? rintf(v[1][ch]) : v[1][ch], c.w[1]);
+                acc = __fmaf_rn(round_flag ? rintf(v[0][ch]) : v[0][ch], c.w[0], acc);
 #pragma unroll
-                for (int k = 0; k < NC; ++k) {
-                    const float qv = round_flag ? rintf(v[k][ch]) : v[k][ch];  // torch.round == half-to-even
-                    acc = __fmaf_rn(qv, c.w[k], acc);
-                }
+                for (int k = 2; k < NC; ++k) acc = __fmaf_rn(round_flag ? rintf(v[k][ch]) : v[k][ch], c.w[k], acc);
                 zz[q * C + ch] = acc;
             }
 #pragma unroll
@@ -206,12 +205,16 @@ latent_fwd_kernel(const float* __restrict__ coords, int64_t n, const float* __re
         float zc[C];
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-            float acc = 0.0f;
+            float raw[NC];
 #pragma unroll
             for (int k = 0; k < NC; ++k) {
-                const float raw = __ldg(base + (int64_t)c.idx[k] * C + ch);
-                acc = __fmaf_rn(round_flag ? rintf(raw) : raw, c.w[k], acc);
+                raw[k] = __ldg(base + (int64_t)c.idx[k] * C + ch);
+                if (round_flag) raw[k] = rintf(raw[k]);
             }
+            float acc = __fmul_rn(raw[1], c.w[1]);
+            acc = __fmaf_rn(raw[0], c.w[0], acc);
+#pragma unroll
+            for (int k = 2; k < NC; ++k) acc = __fmaf_rn(raw[k], c.w[k], acc);
             zc[ch] = acc;
             if (zout) zout[l * C + ch] = acc;
         }

@@ -1,0 +1,256 @@
+// tiled_capi.cu -- extern "C" entry points of the tiled fast path: plan create/destroy and the
+// planned fused forward/backward (declared in include/shacira_b200.h).
+#include <cstdlib>
+
+#include "capi_internal.h"
+#include "tiled_kernels.cuh"
+
+using namespace shacira;
+
+struct shacira_plan {
+    int32_t dim;
+    int64_t n;
+    int32_t g;       // tiles per axis
+    int32_t ntiles;
+    int device;
+    void* block;     // one allocation: perm | coords_sorted | tile_off | cursor | counts | tile_id
+    int32_t* perm;
+    float* coords_sorted;
+    int32_t* tile_off;
+};
+
+namespace {
+
+// dynamic shared memory per CTA for node storage (stays under 48 KB); SHACIRA_TILE_SMEM overrides it
+// (the tests shrink it to force the per-level direct fallback)
+int smem_budget() {
+    const char* env = getenv("SHACIRA_TILE_SMEM");
+    int b = env ? atoi(env) : 40 * 1024;
+    if (b < 256) b = 256;
+    if (b > 40 * 1024) b = 40 * 1024;
+    return b;
+}
+
+PlanView view_of(const shacira_plan* p) {
+    PlanView v;
+    v.perm = p->perm;
+    v.coords_sorted = p->coords_sorted;
+    v.tile_off = p->tile_off;
+    v.n = p->n;
+    v.g = p->g;
+    v.ntiles = p->ntiles;
+    return v;
+}
+
+// Upper bound of the node box of any tile, all levels that fit `cap_max` (coarse first, as the kernel does).
+int node_capacity(const shacira_plan* p, const LevelParams& lp, int cap_max) {
+    long long run = 0;
+    for (int l = 0; l < lp.num_lods; ++l) {
+        long long w = lp.res[l] / p->g + 3, nodes = 1;
+        for (int d = 0; d < p->dim; ++d) nodes *= w;
+        if (run + nodes <= cap_max) run += nodes;
+    }
+    if (run < 32) run = 32;
+    return (int)run;
+}
+
+template <int D, int C, int F>
+int launch_fwd(const shacira_plan* p, const float* lat, const LevelParams& lp, const float* A, const float* shift,
+               int per_level, int round_flag, float* feats, cudaStream_t s) {
+    const int nA = per_level ? lp.num_lods : 1;
+    const int cap = node_capacity(p, lp, smem_budget() / (4 * C));
+    const size_t smem = sizeof(float) * ((size_t)cap * C + nA * C * F + nA * F);
+    latent_fwd_tiled_kernel<D, C, F><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), lat, lp, A, shift, per_level,
+                                                                            round_flag, feats, cap);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
+template <int D, int C, int F>
+int launch_bwd(const shacira_plan* p, const float* g, const float* lat, const LevelParams& lp, const float* A,
+               int per_level, int round_flag, float* gl, float* gA, float* gS, cudaStream_t s) {
+    const int nA = per_level ? lp.num_lods : 1;
+    const bool dec = gA != nullptr || gS != nullptr;
+    const int cap = node_capacity(p, lp, smem_budget() / (4 * C * (dec ? 2 : 1)));
+    constexpr int NW = kTileThreads / 32;
+    size_t smem = sizeof(float) * ((size_t)cap * C * (dec ? 2 : 1) + nA * C * F);
+    if (dec) smem += sizeof(float) * (size_t)NW * lp.num_lods * (C * F + F);
+    if (dec)
+        latent_bwd_tiled_kernel<D, C, F, true><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), g, lat, lp, A, per_level,
+                                                                                      round_flag, gl, gA, gS, cap);
+    else
+        latent_bwd_tiled_kernel<D, C, F, false><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), g, lat, lp, A, per_level,
+                                                                                       round_flag, gl, gA, gS, cap);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
+#define T_DISPATCH_F(F_, CALL)                                                                     \
+    switch (F_) {                                                                                  \
+        case 1: { constexpr int kF = 1; return CALL; }                                             \
+        case 2: { constexpr int kF = 2; return CALL; }                                             \
+        case 4: { constexpr int kF = 4; return CALL; }                                             \
+        case 8: { constexpr int kF = 8; return CALL; }                                             \
+        default: return fail(SHACIRA_ERR_UNSUPPORTED, "feature_dim %d not in {1,2,4,8}", (int)F_); \
+    }
+#define T_DISPATCH_CF(C_, F_, CALL)                                                                \
+    switch (C_) {                                                                                  \
+        case 1: { constexpr int kC = 1; T_DISPATCH_F(F_, CALL) }                                   \
+        case 2: { constexpr int kC = 2; T_DISPATCH_F(F_, CALL) }                                   \
+        case 4: { constexpr int kC = 4; T_DISPATCH_F(F_, CALL) }                                   \
+        default: return fail(SHACIRA_ERR_UNSUPPORTED, "latent_dim %d not in {1,2,4}", (int)C_);    \
+    }
+
+}  // namespace
+
+extern "C" {
+
+int shacira_plan_create(int32_t dim, const float* coords, int64_t n, int32_t tile_points, shacira_stream_t stream,
+                        shacira_plan_t** out) {
+    if (!out) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan output pointer is NULL");
+    *out = nullptr;
+    if (dim != 2 && dim != 3) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "dim must be 2 or 3, got %d", dim);
+    if (n <= 0 || !coords) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan needs n > 0 points");
+    if (n > 0x7fffffff) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan supports up to 2^31-1 points");
+    if (tile_points <= 0) {
+        const char* env = getenv("SHACIRA_TILE_POINTS");
+        tile_points = env ? atoi(env) : 384;
+        if (tile_points <= 0) tile_points = 384;
+    }
+    // tiles per axis: power of two, about tile_points points per tile, at most kMaxTiles tiles
+    int g = 1;
+    for (;;) {
+        long long tiles = 1;
+        for (int d = 0; d < dim; ++d) tiles *= 2LL * g;
+        if (tiles > kMaxTiles) break;
+        // stop when doubling would drop below ~tile_points/2 points per tile
+        long long cur = 1;
+        for (int d = 0; d < dim; ++d) cur *= g;
+        if ((double)n / (double)cur <= (double)tile_points * (dim == 2 ? 2.0 : 2.83)) break;
+        g *= 2;
+    }
+    int ntiles = 1;
+    for (int d = 0; d < dim; ++d) ntiles *= g;
+
+    shacira_plan* p = new (std::nothrow) shacira_plan();
+    if (!p) return fail(SHACIRA_ERR_CUDA, "out of host memory");
+    p->dim = dim;
+    p->n = n;
+    p->g = g;
+    p->ntiles = ntiles;
+    p->block = nullptr;
+    cudaGetDevice(&p->device);
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_perm = al(4 * (size_t)n), b_coords = al(4 * (size_t)n * dim), b_off = al(4 * (size_t)(ntiles + 1));
+    const size_t b_cnt = al(4 * (size_t)ntiles), b_tid = al(4 * (size_t)n);
+    const size_t total = b_perm + b_coords + b_off + 2 * b_cnt + b_tid;
+    cudaError_t e = cudaMalloc(&p->block, total);
+    if (e != cudaSuccess) {
+        delete p;
+        return fail(SHACIRA_ERR_CUDA, "cudaMalloc(%zu) for the plan: %s", total, cudaGetErrorString(e));
+    }
+    char* q = (char*)p->block;
+    p->perm = (int32_t*)q; q += b_perm;
+    p->coords_sorted = (float*)q; q += b_coords;
+    p->tile_off = (int32_t*)q; q += b_off;
+    int32_t* cursor = (int32_t*)q; q += b_cnt;
+    int32_t* counts = (int32_t*)q; q += b_cnt;
+    int32_t* tile_id = (int32_t*)q;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = SHACIRA_OK;
+    auto body = [&]() -> int {
+        CUDA_OK(cudaMemsetAsync(counts, 0, 4 * (size_t)ntiles, s));
+        const size_t hist = 4 * (size_t)ntiles;
+        int blocks = (int)((n + 1023) / 1024);
+        const int count_blocks = blocks < 296 ? blocks : 296;
+        if (dim == 2) plan_count_kernel<2><<<count_blocks, 1024, hist, s>>>(coords, n, g, ntiles, tile_id, counts);
+        else plan_count_kernel<3><<<count_blocks, 1024, hist, s>>>(coords, n, g, ntiles, tile_id, counts);
+        LAUNCHED();
+        plan_scan_kernel<<<1, 1024, 0, s>>>(counts, ntiles, p->tile_off, cursor);
+        LAUNCHED();
+        if (dim == 2) plan_scatter_kernel<2><<<blocks, 1024, hist, s>>>(coords, n, ntiles, tile_id, cursor, p->perm, p->coords_sorted);
+        else plan_scatter_kernel<3><<<blocks, 1024, hist, s>>>(coords, n, ntiles, tile_id, cursor, p->perm, p->coords_sorted);
+        LAUNCHED();
+        return SHACIRA_OK;
+    };
+    rc = body();
+    if (rc != SHACIRA_OK) {
+        cudaFree(p->block);
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return SHACIRA_OK;
+}
+
+int shacira_plan_destroy(shacira_plan_t* plan) {
+    if (!plan) return SHACIRA_OK;
+    if (plan->block) cudaFree(plan->block);  // synchronises with outstanding work that uses the plan
+    delete plan;
+    return SHACIRA_OK;
+}
+
+int shacira_plan_info(const shacira_plan_t* plan, int64_t* n, int32_t* dim, int32_t* tiles_per_axis, int32_t* ntiles) {
+    if (!plan) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (n) *n = plan->n;
+    if (dim) *dim = plan->dim;
+    if (tiles_per_axis) *tiles_per_axis = plan->g;
+    if (ntiles) *ntiles = plan->ntiles;
+    return SHACIRA_OK;
+}
+
+int shacira_plan_debug(const shacira_plan_t* plan, const int32_t** perm, const float** coords_sorted,
+                       const int32_t** tile_off) {
+    if (!plan) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (perm) *perm = plan->perm;
+    if (coords_sorted) *coords_sorted = plan->coords_sorted;
+    if (tile_off) *tile_off = plan->tile_off;
+    return SHACIRA_OK;
+}
+
+int shacira_latent_forward_planned(const shacira_plan_t* plan, const float* latents, const int32_t* first_idx,
+                                   const int32_t* resolutions, int32_t num_lods, int32_t codebook_bitwidth,
+                                   int32_t latent_dim, int32_t feature_dim, int32_t round_flag, const float* A,
+                                   const float* shift, int32_t per_level, float* feats, shacira_stream_t stream) {
+    if (!plan) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan is NULL");
+    LevelParams lp;
+    int rc = build_levels(plan->dim, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
+    if (rc) return rc;
+    if (!latents || !feats || !A) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "latents/feats/A is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (plan->dim == 2) {
+        T_DISPATCH_CF(latent_dim, feature_dim,
+                      (launch_fwd<2, kC, kF>(plan, latents, lp, A, shift, per_level, round_flag, feats, s)))
+    }
+    T_DISPATCH_CF(latent_dim, feature_dim,
+                  (launch_fwd<3, kC, kF>(plan, latents, lp, A, shift, per_level, round_flag, feats, s)))
+}
+
+int shacira_latent_backward_planned(const shacira_plan_t* plan, const float* grad_output, const float* latents,
+                                    const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                                    int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim,
+                                    int32_t round_flag, const float* A, int32_t per_level, int64_t table_rows,
+                                    int32_t zero_first, float* grad_latents, float* grad_A, float* grad_shift,
+                                    shacira_stream_t stream) {
+    if (!plan) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan is NULL");
+    LevelParams lp;
+    int rc = build_levels(plan->dim, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
+    if (rc) return rc;
+    if (!grad_latents || !A || !grad_output) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "grad_latents/A/grad_output is NULL");
+    if ((grad_A || grad_shift) && !latents)
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "decoder gradients need the latents (the interpolation is recomputed)");
+    if (latent_dim != 1 && latent_dim != 2 && latent_dim != 4)
+        return fail(SHACIRA_ERR_UNSUPPORTED, "latent_dim %d not in {1,2,4}", latent_dim);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (zero_first) CUDA_OK(cudaMemsetAsync(grad_latents, 0, sizeof(float) * (size_t)table_rows * latent_dim, s));
+    if (plan->dim == 2) {
+        T_DISPATCH_CF(latent_dim, feature_dim,
+                      (launch_bwd<2, kC, kF>(plan, grad_output, latents, lp, A, per_level, round_flag, grad_latents,
+                                             grad_A, grad_shift, s)))
+    }
+    T_DISPATCH_CF(latent_dim, feature_dim,
+                  (launch_bwd<3, kC, kF>(plan, grad_output, latents, lp, A, per_level, round_flag, grad_latents, grad_A,
+                                         grad_shift, s)))
+}
+
+}  // extern "C"

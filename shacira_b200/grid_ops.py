@@ -12,6 +12,48 @@ from . import _lib
 from ._C import ops as _ops
 from ._C.ops import _host_ints
 
+import os
+from collections import OrderedDict
+
+# ---- plan cache --------------------------------------------------------------------------------
+# The tiled kernels need the points binned by spatial tile. The reference's API hands the op a bare
+# coords tensor every step, so plans are cached on the tensor's identity: (storage pointer, version
+# counter, shape). The cache keeps a reference to the tensor, so its storage cannot be freed and
+# handed to different data while the entry lives, and any in-place write bumps the version counter.
+# An image fit calls interpolate() with the same coords tensor for every step (static coordinates,
+# image_trainer.py:234-266): one plan for the whole fit. A workload with fresh coordinates every
+# step (NeRF samples) misses the cache and pays the ~3-kernel plan build each step.
+PLAN_MIN_POINTS = int(os.environ.get("SHACIRA_PLAN_MIN_POINTS", "16384"))
+PLAN_CACHE_SIZE = int(os.environ.get("SHACIRA_PLAN_CACHE", "8"))
+_plans = OrderedDict()
+plan_stats = {"hits": 0, "builds": 0}
+
+
+def plan_for(coords):
+    """Tile plan for `coords` ([N, 2|3] float32 contiguous CUDA) or None when planning is disabled / not worth it."""
+    if os.environ.get("SHACIRA_DISABLE_PLAN") or coords.shape[0] < PLAN_MIN_POINTS:
+        return None
+    key = (coords.data_ptr(), coords._version, tuple(coords.shape), coords.device.index)
+    plan = _plans.get(key)
+    if plan is not None:
+        _plans.move_to_end(key)
+        plan_stats["hits"] += 1
+        return plan
+    plan = _lib.Plan(coords)
+    plan_stats["builds"] += 1
+    _plans[key] = plan
+    while len(_plans) > PLAN_CACHE_SIZE:
+        _, old = _plans.popitem(last=False)
+        old.close()
+    return plan
+
+
+def clear_plans():
+    while _plans:
+        _, old = _plans.popitem()
+        old.close()
+
+
 _amp_fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
 _amp_bwd = torch.amp.custom_bwd(device_type="cuda")
 
@@ -96,9 +138,17 @@ class LatentHashGrid(torch.autograd.Function):
     def forward(ctx, coords, latents, A, shift, first_idx, resolutions, bitwidth, round_flag):
         F = A.shape[2]
         need_dec = bool(ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
-        feats, z = _lib.latent_forward(coords, latents, first_idx, resolutions, bitwidth, A, shift, F, round_flag,
-                                       save_z=need_dec)
-        ctx.save_for_backward(coords, A.detach(), z if z is not None else coords.new_empty(0))
+        plan = plan_for(coords)
+        if plan is not None:
+            feats = _lib.latent_forward_planned(plan, latents, first_idx, resolutions, bitwidth, A, shift, F, round_flag)
+            # the tiled backward recomputes the interpolation from the latents: nothing extra is written here
+            ctx.save_for_backward(coords, A.detach(), latents.detach() if need_dec else coords.new_empty(0))
+        else:
+            feats, z = _lib.latent_forward(coords, latents, first_idx, resolutions, bitwidth, A, shift, F, round_flag,
+                                           save_z=need_dec)
+            ctx.save_for_backward(coords, A.detach(), z if z is not None else coords.new_empty(0))
+        ctx.plan = plan
+        ctx.round_flag = round_flag
         ctx.meta = (first_idx, tuple(resolutions), bitwidth, tuple(latents.shape), F, need_dec, shift is not None,
                     A.shape[0])
         return feats
@@ -108,8 +158,13 @@ class LatentHashGrid(torch.autograd.Function):
     def backward(ctx, grad_output):
         coords, A, z = ctx.saved_tensors
         first_idx, resolutions, bitwidth, (rows, C), F, need_dec, has_shift, nA = ctx.meta
-        gl, gA, gS = _lib.latent_backward(coords, grad_output.contiguous(), z if need_dec else None, first_idx,
-                                          resolutions, bitwidth, A, C, F, rows, need_dec)
+        if ctx.plan is not None:
+            gl, gA, gS = _lib.latent_backward_planned(ctx.plan, grad_output.contiguous(), z if need_dec else None,
+                                                      first_idx, resolutions, bitwidth, A, C, F, rows,
+                                                      ctx.round_flag, need_dec)
+        else:
+            gl, gA, gS = _lib.latent_backward(coords, grad_output.contiguous(), z if need_dec else None, first_idx,
+                                              resolutions, bitwidth, A, C, F, rows, need_dec)
         if need_dec and nA == 1:
             gA = gA.sum(0, keepdim=True)
             gS = gS.sum(0, keepdim=True)

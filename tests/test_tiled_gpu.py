@@ -1,0 +1,195 @@
+"""The tiled fast path (spatial plan + shared-memory node staging + fixed-point accumulation)
+against the point-parallel kernels, the CPU oracle and the golden reference vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+FWD_TOL, BWD_TOL = 1e-5, 1e-4
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _case(dim, L, bw, rmin, rmax, n, C, F, seed, per_level=False, kind="uniform"):
+    rng = np.random.default_rng(seed)
+    res = oracle.geometric_resolutions(rmin, rmax, L)
+    sizes, first, T = oracle.level_layout(res, bw, dim)
+    if kind == "uniform":
+        coords = (rng.random((n, dim), dtype=np.float32) * 2 - 1)
+    elif kind == "arbitrary":
+        coords = np.clip(rng.standard_normal((n, dim)) * 0.5, -1.2, 1.2).astype(np.float32)
+    elif kind == "clustered":  # every point inside one tile: exercises the batch loop of the backward
+        coords = (rng.random((n, dim), dtype=np.float32) * 0.01 + 0.3).astype(np.float32)
+    elif kind == "pixels":
+        H, W = 512, 768
+        ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+        coords = np.stack([(ys.reshape(-1) / H - 0.5) * 2, (xs.reshape(-1) / W - 0.5) * 2], 1).astype(np.float32)
+        coords = coords[rng.permutation(coords.shape[0])][:n]
+    lat = ((rng.random((T, C), dtype=np.float32) - 0.5) * 16).astype(np.float32)
+    nA = L if per_level else 1
+    A = (rng.standard_normal((nA, C, F)) * 0.3).astype(np.float32)
+    S = (rng.standard_normal((nA, F)) * 0.1).astype(np.float32)
+    g = rng.standard_normal((coords.shape[0], L * F)).astype(np.float32)
+    return dict(dim=dim, L=L, bw=bw, res=res, first=first, T=T, coords=np.ascontiguousarray(coords), lat=lat, A=A, S=S,
+                g=g, C=C, F=F, nA=nA)
+
+
+def _oracle_fwd_bwd(c, round_flag=True):
+    """Reference order on the CPU: decode table (float64 affine on rounded latents is exact enough as a
+    yardstick), interpolate with the C oracle; gradients by the oracle's backward + chain rule."""
+    q = np.rint(c["lat"]) if round_flag else c["lat"]
+    L, C, F = c["L"], c["C"], c["F"]
+    z = oracle.forward(c["coords"], q.astype(np.float32), c["first"], c["res"], c["bw"]).reshape(-1, L, C)
+    feats = np.stack([z[:, l].astype(np.float64) @ c["A"][l if c["nA"] > 1 else 0] + c["S"][l if c["nA"] > 1 else 0]
+                      for l in range(L)], 1).reshape(-1, L * F)
+    g = c["g"].reshape(-1, L, F).astype(np.float64)
+    gz = np.stack([g[:, l] @ c["A"][l if c["nA"] > 1 else 0].T for l in range(L)], 1)  # [n, L, C]
+    gl = oracle.backward(c["coords"], gz.reshape(-1, L * C).astype(np.float32), c["T"], c["first"], c["res"], c["bw"], C)
+    gA = np.einsum("nlc,nlf->lcf", z.astype(np.float64), g)
+    gS = g.sum(0)
+    return feats, gl, gA, gS
+
+
+TILED_CASES = [
+    # dim, L, bw, rmin, rmax, n, C, F, per_level, kind
+    (2, 16, 16, 16, 512, 768 * 512, 1, 1, False, "pixels"),   # BASELINE cfg2 (full size)
+    (2, 16, 14, 16, 512, 1 << 18, 1, 1, False, "uniform"),    # BASELINE cfg1 grid
+    (2, 16, 16, 16, 512, 40000, 2, 4, True, "arbitrary"),
+    (2, 24, 11, 16, 512, 50000, 1, 1, False, "uniform"),      # the reference's kodak.yaml grid: 24 levels, 2^11
+    (2, 8, 19, 16, 700, 30000, 4, 2, False, "uniform"),       # dense levels with res >= 257 (Q4)
+    (2, 16, 16, 16, 512, 20000, 1, 1, False, "clustered"),
+    (3, 16, 19, 16, 2048, 1 << 17, 1, 4, False, "uniform"),   # BASELINE cfg4 grid: fine levels fall back to direct
+    (3, 8, 14, 8, 128, 30000, 2, 2, True, "arbitrary"),
+]
+
+
+@pytest.mark.parametrize("dim,L,bw,rmin,rmax,n,C,F,per_level,kind", TILED_CASES)
+def test_tiled_forward_backward(lib, dim, L, bw, rmin, rmax, n, C, F, per_level, kind):
+    c = _case(dim, L, bw, rmin, rmax, n, C, F, seed=dim * 7 + C + F, per_level=per_level, kind=kind)
+    coords, lat, A, S, g = _dev(c["coords"]), _dev(c["lat"]), _dev(c["A"]), _dev(c["S"]), _dev(c["g"])
+    plan = lib.Plan(coords)
+    info = plan.info()
+    assert info["n"] == coords.shape[0] and info["ntiles"] == info["tiles_per_axis"] ** dim
+    feats = lib.latent_forward_planned(plan, lat, c["first"], c["res"], bw, A, S, F, True)
+    # bit-identical to the point-parallel kernel: same indices, weights, rounding and operation order
+    feats_pp, z_pp = lib.latent_forward(coords, lat, c["first"], c["res"], bw, A, S, F, True, True)
+    assert torch.equal(feats, feats_pp)
+    want_f, want_gl, want_gA, want_gS = _oracle_fwd_bwd(c)
+    assert rel_err(feats.cpu().numpy(), want_f) <= FWD_TOL
+    gl, gA, gS = lib.latent_backward_planned(plan, g, lat, c["first"], c["res"], bw, A, C, F, c["T"], True, True)
+    assert rel_err(gl.cpu().numpy(), want_gl) <= BWD_TOL
+    assert rel_err(gA.cpu().numpy(), want_gA) <= BWD_TOL
+    assert rel_err(gS.cpu().numpy(), want_gS) <= BWD_TOL
+    # without decoder gradients (frozen decoder): same latent gradient
+    gl2, _, _ = lib.latent_backward_planned(plan, g, None, c["first"], c["res"], bw, A, C, F, c["T"], True, False)
+    assert rel_err(gl2.cpu().numpy(), want_gl) <= BWD_TOL
+    plan.close()
+
+
+def test_plan_is_a_valid_spatial_binning(lib):
+    c = _case(2, 4, 10, 8, 64, 50000, 1, 1, seed=3, kind="arbitrary")
+    coords = _dev(c["coords"])
+    plan = lib.Plan(coords)
+    perm, cs, off = plan.arrays()
+    info = plan.info()
+    g = info["tiles_per_axis"]
+    assert sorted(perm.tolist()) == list(range(50000))               # a permutation
+    assert np.array_equal(cs, c["coords"][perm])                      # sorted copy of the coordinates
+    assert off[0] == 0 and off[-1] == 50000 and np.all(np.diff(off) >= 0)
+    t = np.clip(np.floor((c["coords"].astype(np.float64) * 0.5 + 0.5) * g), 0, g - 1).astype(np.int64)
+    tile = t[:, 0] + g * t[:, 1]
+    seg = np.repeat(np.arange(info["ntiles"]), np.diff(off))
+    assert np.array_equal(tile[perm], seg)                            # every point sits in its tile's segment
+    plan.close()
+
+
+def test_direct_level_fallback_matches(lib, monkeypatch):
+    """Shrinking the shared-memory budget pushes fine levels to the in-kernel direct path."""
+    c = _case(2, 16, 16, 16, 512, 30000, 1, 1, seed=9, kind="uniform")
+    coords, lat, A, S, g = _dev(c["coords"]), _dev(c["lat"]), _dev(c["A"]), _dev(c["S"]), _dev(c["g"])
+    plan = lib.Plan(coords)
+    want_f, want_gl, want_gA, want_gS = _oracle_fwd_bwd(c)
+    full = lib.latent_forward_planned(plan, lat, c["first"], c["res"], 16, A, S, 1, True)
+    for budget in ("1024", "4096"):
+        monkeypatch.setenv("SHACIRA_TILE_SMEM", budget)
+        f = lib.latent_forward_planned(plan, lat, c["first"], c["res"], 16, A, S, 1, True)
+        assert torch.equal(f, full)
+        gl, gA, gS = lib.latent_backward_planned(plan, g, lat, c["first"], c["res"], 16, A, 1, 1, c["T"], True, True)
+        assert rel_err(gl.cpu().numpy(), want_gl) <= BWD_TOL
+        assert rel_err(gA.cpu().numpy(), want_gA) <= BWD_TOL and rel_err(gS.cpu().numpy(), want_gS) <= BWD_TOL
+    plan.close()
+
+
+def test_tiled_backward_is_deterministic_per_plan(lib):
+    """Fixed-point shared-memory sums are order-independent; only the few per-node flush adds are float."""
+    c = _case(2, 16, 16, 16, 512, 60000, 1, 1, seed=4, kind="uniform")
+    coords, lat, A, g = _dev(c["coords"]), _dev(c["lat"]), _dev(c["A"]), _dev(c["g"])
+    plan = lib.Plan(coords)
+    a, _, _ = lib.latent_backward_planned(plan, g, None, c["first"], c["res"], 16, A, 1, 1, c["T"], True, False)
+    b, _, _ = lib.latent_backward_planned(plan, g, None, c["first"], c["res"], 16, A, 1, 1, c["T"], True, False)
+    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-6
+    plan.close()
+
+
+def test_gradient_magnitude_extremes(lib):
+    """Tiny, huge and zero upstream gradients keep the fixed-point path within tolerance."""
+    c = _case(2, 12, 14, 16, 256, 30000, 1, 1, seed=5, kind="uniform")
+    coords, lat, A = _dev(c["coords"]), _dev(c["lat"]), _dev(c["A"])
+    plan = lib.Plan(coords)
+    for scale in (1e-12, 1.0, 1e12):
+        c["g"] = (np.random.default_rng(6).standard_normal(c["g"].shape) * scale).astype(np.float32)
+        c["g"][:, 3] = 0.0                      # one level with no gradient at all
+        c["g"][7, 5] = 50.0 * scale             # one outlier
+        _, want_gl, _, _ = _oracle_fwd_bwd(c)
+        gl, _, _ = lib.latent_backward_planned(plan, _dev(c["g"]), None, c["first"], c["res"], 14, A, 1, 1, c["T"], True, False)
+        assert rel_err(gl.cpu().numpy(), want_gl) <= BWD_TOL
+        a, b = c["first"][3], c["first"][4]
+        assert not bool(gl[a:b].any())
+    plan.close()
+
+
+def test_latent_grid_api_uses_the_plan_and_matches_unplanned(lib, monkeypatch):
+    from shacira_b200 import grid_ops
+    from shacira_b200.grids import LatentGrid
+    dec = dict(ldecode_enabled=True, ldecode_type="single", use_sga=False, diff_sampling=True, use_shift=True,
+               ldecode_matrix="sq", latent_dim=1, norm="max", norm_every=10, ldec_std=0.1, decay_period=0.9,
+               temperature=0.1)
+    ent = dict(num_prob_layers=2, entropy_reg=1e-3, entropy_reg_end=1e-4, entropy_reg_sched="cosine", noise_freq=1)
+    torch.manual_seed(0)
+    grid = LatentGrid.from_geometric(feature_dim=1, num_lods=16, latent_dim=1, multiscale_type="cat", resolution_dim=2,
+                                     feature_std=0.1, codebook_bitwidth=16, min_grid_res=16, max_grid_res=512,
+                                     init_grid="uniform", conf_latent_decoder=dec, conf_entropy_reg=ent)
+    with torch.no_grad():
+        grid.codebook.mul_(60.0)
+    grid = grid.cuda()
+    coords = (torch.rand(100000, 2, device="cuda") * 2 - 1)
+    gout = torch.randn(100000, 16, device="cuda")
+    grid_ops.clear_plans()
+    h0, b0 = grid_ops.plan_stats["hits"], grid_ops.plan_stats["builds"]
+    outs = []
+    for _ in range(3):                                   # static coordinates: one plan, reused
+        grid.zero_grad()
+        f = grid.interpolate(coords, 0)
+        f.backward(gout)
+        outs.append((f.detach().clone(), grid.codebook.grad.clone(), grid.latent_dec.layers[0].scale.grad.clone(),
+                     grid.latent_dec.layers[0].shift.grad.clone()))
+    assert grid_ops.plan_stats["builds"] == b0 + 1 and grid_ops.plan_stats["hits"] >= h0 + 2
+    coords.mul_(0.5)                                     # in-place change -> version bump -> new plan
+    grid.interpolate(coords, 0)
+    assert grid_ops.plan_stats["builds"] == b0 + 2
+    coords.mul_(2.0)
+    monkeypatch.setenv("SHACIRA_DISABLE_PLAN", "1")
+    grid.zero_grad()
+    f = grid.interpolate(coords, 0)
+    f.backward(gout)
+    assert torch.equal(f, outs[0][0])
+    assert rel_err(outs[0][1].cpu().numpy(), grid.codebook.grad.cpu().numpy()) <= BWD_TOL
+    assert rel_err(outs[0][2].cpu().numpy(), grid.latent_dec.layers[0].scale.grad.cpu().numpy()) <= BWD_TOL
+    assert rel_err(outs[0][3].cpu().numpy(), grid.latent_dec.layers[0].shift.grad.cpu().numpy()) <= BWD_TOL
