@@ -11,7 +11,7 @@ import threading
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libshacira_b200.so")
+LIB_PATH = os.environ.get("SHACIRA_LIB") or os.path.join(_PKG, "libshacira_b200.so")  # env: kernel-tuning builds
 
 OK = 0
 ERR_INVALID_ARGUMENT = -1
@@ -272,7 +272,7 @@ class Plan:
 
         class _Dev:  # alias raw device memory through the CUDA array interface
             def __init__(self, ptr, count, typestr):
-                self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, True),
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False),
                                                  "version": 2}
 
         def grab(ptr, count, dtype):

@@ -31,12 +31,15 @@ def is_stale():
     return any(os.path.getmtime(p) > t for p in _deps())
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and not is_stale():
+def build(force=False, verbose=False, extra=(), out=None, tag=""):
+    """`out`/`tag`/`extra` build tuning variants beside the product library (see benchmarks/)."""
+    global LIB
+    if out is None and not force and not is_stale():
         return LIB
+    lib_path = out or LIB
     # one object per translation unit, compiled in parallel, then one link
     from concurrent.futures import ThreadPoolExecutor
-    objdir = os.path.join(PKG, "build")
+    objdir = os.path.join(PKG, "build" + tag)
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
@@ -49,11 +52,11 @@ def build(force=False, verbose=False, extra=()):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
-    link = ["nvcc", "--shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB]
+    link = ["nvcc", "--shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", lib_path]
     if verbose:
         print(" ".join(link), flush=True)
     subprocess.check_call(link)
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -71,16 +71,21 @@ int launch_bwd(const shacira_plan* p, const float* g, const float* lat, const Le
                int per_level, int round_flag, float* gl, float* gA, float* gS, cudaStream_t s) {
     const int nA = per_level ? lp.num_lods : 1;
     const bool dec = gA != nullptr || gS != nullptr;
-    const int cap = node_capacity(p, lp, smem_budget() / (4 * C * (dec ? 2 : 1)));
+    // shared memory: fixed-point accumulators (kRepBudget ints of lane-replicated copies shared by the C
+    // channels + one slot per node) and, for the decoder gradients, the staged latents
+    const bool big = smem_budget() > 24 * 1024;
+    const int rep = big ? kRepBudget / C : 0;  // per channel
+    const int cap = node_capacity(p, lp, (smem_budget() - rep * 4 * C) / (4 * C * (dec ? 2 : 1)));
+    const int cap_acc = cap + rep;
     constexpr int NW = kTileThreads / 32;
-    size_t smem = sizeof(float) * ((size_t)cap * C * (dec ? 2 : 1) + nA * C * F);
+    size_t smem = sizeof(float) * ((size_t)cap_acc * C + (dec ? (size_t)cap * C : 0) + nA * C * F);
     if (dec) smem += sizeof(float) * (size_t)NW * lp.num_lods * (C * F + F);
     if (dec)
         latent_bwd_tiled_kernel<D, C, F, true><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), g, lat, lp, A, per_level,
-                                                                                      round_flag, gl, gA, gS, cap);
+                                                                                      round_flag, gl, gA, gS, cap, cap_acc);
     else
         latent_bwd_tiled_kernel<D, C, F, false><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), g, lat, lp, A, per_level,
-                                                                                       round_flag, gl, gA, gS, cap);
+                                                                                       round_flag, gl, gA, gS, cap, cap_acc);
     LAUNCHED();
     return SHACIRA_OK;
 }
@@ -217,6 +222,7 @@ int shacira_latent_forward_planned(const shacira_plan_t* plan, const float* late
     int rc = build_levels(plan->dim, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
     if (rc) return rc;
     if (!latents || !feats || !A) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "latents/feats/A is NULL");
+    if (num_lods % 4) return fail(SHACIRA_ERR_UNSUPPORTED, "the tiled path needs num_lods %% 4 == 0 (got %d)", num_lods);
     cudaStream_t s = (cudaStream_t)stream;
     if (plan->dim == 2) {
         T_DISPATCH_CF(latent_dim, feature_dim,
@@ -241,6 +247,7 @@ int shacira_latent_backward_planned(const shacira_plan_t* plan, const float* gra
         return fail(SHACIRA_ERR_INVALID_ARGUMENT, "decoder gradients need the latents (the interpolation is recomputed)");
     if (latent_dim != 1 && latent_dim != 2 && latent_dim != 4)
         return fail(SHACIRA_ERR_UNSUPPORTED, "latent_dim %d not in {1,2,4}", latent_dim);
+    if (num_lods % 4) return fail(SHACIRA_ERR_UNSUPPORTED, "the tiled path needs num_lods %% 4 == 0 (got %d)", num_lods);
     cudaStream_t s = (cudaStream_t)stream;
     if (zero_first) CUDA_OK(cudaMemsetAsync(grad_latents, 0, sizeof(float) * (size_t)table_rows * latent_dim, s));
     if (plan->dim == 2) {

@@ -23,8 +23,12 @@
 
 namespace shacira {
 
-constexpr int kTileThreads = 128;
+#ifndef SHACIRA_TILE_THREADS
+#define SHACIRA_TILE_THREADS 128
+#endif
+constexpr int kTileThreads = SHACIRA_TILE_THREADS;
 constexpr int kMaxTiles = 4096;
+constexpr int kPts = 4;      // points per thread whose loads are issued together (memory-level parallelism)
 constexpr int kBatch = 2048;  // points accumulated between two flushes of a tile (bounds the fixed-point sums)
 
 struct PlanView {
@@ -131,51 +135,104 @@ plan_scatter_kernel(const float* __restrict__ coords, int64_t n, int ntiles, con
 // ---------------------------------------------------------------------------------------------
 template <int D>
 struct TileGeom {
-    int c0[SHACIRA_MAX_LEVELS][D];  // first cell of the tile's box per level/axis
-    int w[SHACIRA_MAX_LEVELS][D];   // nodes per axis (cells + 1)
-    int off[SHACIRA_MAX_LEVELS + 1];
-    unsigned staged;                // bit l: level l lives in shared memory for this tile
+    int c0[SHACIRA_MAX_LEVELS][D];   // first cell of the tile's node box per level/axis
+    int w[SHACIRA_MAX_LEVELS][D];    // nodes per axis (cells + 1)
+    int off[SHACIRA_MAX_LEVELS + 1]; // first shared-memory node slot of the level
+    int offp[SHACIRA_MAX_LEVELS];    // off - sum_d c0[d] * stride[d]: slot = offp + sum_d cell[d] * stride[d]
+    unsigned magic[SHACIRA_MAX_LEVELS][D];  // ceil(2^32 / w): e / w == umulhi(e, magic) for the small e used here
+    unsigned staged;                 // bit l: level l lives in shared memory for this tile
     int total;
+    // backward accumulators: levels with a small node box keep one copy PER LANE (slot = off + node*32 + lane),
+    // so the 32 lanes of a warp never collide on an address -- coarse levels otherwise serialise 32-way
+    int acc_off[SHACIRA_MAX_LEVELS];
+    int acc_mul[SHACIRA_MAX_LEVELS]; // 32 (lane-replicated) or 1
+    int acc_total;
 };
+constexpr int kRepBudget = 4096;     // ints of lane-replicated accumulators per tile (all channels together)
 
-// Cells reachable by points of tile axis-interval [ti/g, (ti+1)/g]: locate() is monotone in t.
+// Cells reachable by points of the tile's axis interval [ti/g, (ti+1)/g]: locate() is monotone in t.
+// Warp 0 computes everything: lane l owns level l; the slot offsets are a warp prefix sum. Levels are
+// staged coarse to fine until the first one that does not fit `cap`; that one and all finer levels
+// use the direct path.
 template <int D>
 __device__ __forceinline__ void tile_geometry(TileGeom<D>& tg, const LevelParams& lp, const int (&ti)[D], int g,
-                                              int cap) {
-    const int l = threadIdx.x;
-    if (l < lp.num_lods) {
+                                              int cap, int cap_acc = 0x3fffffff, int rep_budget = 0) {
+    if (threadIdx.x < 32) {
+        const int l = threadIdx.x;
+        const double inv_g = 1.0 / (double)g;  // g is a power of two: exact
+        int nodes = 0, c0[D], w[D];
+        if (l < lp.num_lods) {
+            nodes = 1;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            int ca, cb;
-            float f, gg;
-            locate((double)ti[d] / (double)g, lp.res[l], lp.hi[l], ca, f, gg);
-            locate((double)(ti[d] + 1) / (double)g, lp.res[l], lp.hi[l], cb, f, gg);
-            tg.c0[l][d] = ca;
-            tg.w[l][d] = cb - ca + 2;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        unsigned staged = 0;
-        for (int q = 0; q < lp.num_lods; ++q) {
-            long long nodes = 1;
-#pragma unroll
-            for (int d = 0; d < D; ++d) nodes *= tg.w[q][d];
-            tg.off[q] = run;
-            if (run + nodes <= cap) {
-                staged |= 1u << q;
-                run += (int)nodes;
+            for (int d = 0; d < D; ++d) {
+                int ca, cb;
+                float f, gg;
+                locate((double)ti[d] * inv_g, lp.res[l], lp.hi[l], ca, f, gg);
+                locate((double)(ti[d] + 1) * inv_g, lp.res[l], lp.hi[l], cb, f, gg);
+                c0[d] = ca;
+                w[d] = cb - ca + 2;
+                nodes = (nodes > cap) ? nodes : nodes * w[d];  // saturate: anything above cap is unstaged anyway
             }
         }
-        tg.off[lp.num_lods] = run;
-        tg.staged = staged;
-        tg.total = run;
+        int incl = nodes;  // inclusive prefix sum over levels (values saturate far below 2^31)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (l >= o) incl = min(incl + v, 0x3fffffff);
+        }
+        // accumulator slots: lane-replicated while the replicated prefix fits kRepBudget
+        int rep_incl = min(nodes, 1 << 20) * 32;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, rep_incl, o);
+            if (l >= o) rep_incl = min(rep_incl + v, 0x3fffffff);
+        }
+        const bool rep = (l < lp.num_lods) && rep_incl <= rep_budget;
+        const int acc_size = rep ? nodes * 32 : nodes;
+        int acc_incl = acc_size;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, acc_incl, o);
+            if (l >= o) acc_incl = min(acc_incl + v, 0x3fffffff);
+        }
+        const bool fits = (l < lp.num_lods) && incl <= cap && acc_incl <= cap_acc;
+        const unsigned fit_mask = __ballot_sync(0xffffffffu, fits);
+        // staged = the leading run of levels that fit
+        const unsigned all = (lp.num_lods >= 32) ? 0xffffffffu : ((1u << lp.num_lods) - 1u);
+        const unsigned miss = ~fit_mask & all;
+        const unsigned staged = miss ? (fit_mask & ((1u << (__ffs(miss) - 1)) - 1u)) : fit_mask;
+        const int first_unstaged = miss ? (__ffs(miss) - 1) : lp.num_lods;
+        const int total = (first_unstaged > 0) ? __shfl_sync(0xffffffffu, incl, first_unstaged - 1) : 0;
+        const int acc_total = (first_unstaged > 0) ? __shfl_sync(0xffffffffu, acc_incl, first_unstaged - 1) : 0;
+        if (l < lp.num_lods) {
+            const bool st = (staged >> l) & 1u;
+            const int off = st ? incl - nodes : total;
+            int offp = off, stride = 1;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                tg.c0[l][d] = c0[d];
+                tg.w[l][d] = w[d];
+                tg.magic[l][d] = (unsigned)((0x100000000ull + (unsigned)w[d] - 1) / (unsigned)w[d]);
+                offp -= c0[d] * stride;
+                stride *= w[d];
+            }
+            tg.off[l] = off;
+            tg.offp[l] = offp;
+            tg.acc_off[l] = st ? acc_incl - acc_size : acc_total;
+            tg.acc_mul[l] = rep ? 32 : 1;
+        }
+        if (l == 0) {
+            tg.off[lp.num_lods] = total;
+            tg.staged = staged;
+            tg.total = total;
+            tg.acc_total = acc_total;
+        }
     }
     __syncthreads();
 }
 
-// node e of staged level l -> (level-local table row, or -1 when the node lies outside the level)
+// node e (0 <= e < prod w) of level l -> level-local table row; -1 (or the last row when clamp_inside)
+// for nodes outside the level, which only ever carry weight 0.
 template <int D>
 __device__ __forceinline__ int node_row(const TileGeom<D>& tg, const LevelParams& lp, int l, int e, bool clamp_inside) {
     const int res = lp.res[l];
@@ -183,20 +240,25 @@ __device__ __forceinline__ int node_row(const TileGeom<D>& tg, const LevelParams
     int r = e;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        nx[d] = tg.c0[l][d] + r % tg.w[l][d];
-        r /= tg.w[l][d];
+        if (d == D - 1) {
+            nx[d] = tg.c0[l][d] + r;
+        } else {
+            const int q = (int)__umulhi((unsigned)r, tg.magic[l][d]);
+            nx[d] = tg.c0[l][d] + (r - q * tg.w[l][d]);
+            r = q;
+        }
     }
     if ((lp.dense_mask >> l) & 1u) {
         long long idx = nx[0];
         long long mul = res;
-        bool outside = nx[0] > res;  // nodes past the grid only ever carry weight 0
+        bool outside = nx[0] >= res;
 #pragma unroll
         for (int d = 1; d < D; ++d) {
             idx += (long long)nx[d] * mul;
             mul *= res;
-            outside |= nx[d] > res;
+            outside |= nx[d] >= res;
         }
-        if (idx >= lp.rows[l] || outside) return clamp_inside ? lp.rows[l] - 1 : -1;
+        if (outside || idx >= lp.rows[l]) return clamp_inside ? lp.rows[l] - 1 : -1;
         return (int)idx;
     }
     uint32_t h = (uint32_t)nx[0];
@@ -205,31 +267,180 @@ __device__ __forceinline__ int node_row(const TileGeom<D>& tg, const LevelParams
     return (int)(h & lp.hash_mask);
 }
 
+// Per-level constants of the hot loop, loaded ONCE per chunk of 4 levels into registers (the compiler
+// cannot hoist them itself: the shared-memory atomics may alias them as far as it can tell).
+struct LevelRegs {
+    double resd;   // (double)res: x = float(resd * t)
+    float hi;      // upper clamp bound
+    int w0, w01;   // slot strides of axis 1 and axis 2
+    int offp;      // slot = offp + sum_d cell[d] * stride[d]
+    int accd;      // accumulator slot = (slot + accd) * amul + alane   (backward)
+    int amul, alane;
+    bool staged;
+};
+
 template <int D>
-__device__ __forceinline__ int level_of_node(const TileGeom<D>& tg, int L, int e) {
-    int a = 0, b = L;  // last level with off <= e (unstaged levels have zero extent)
+__device__ __forceinline__ void load_level_regs(const LevelParams& lp, const TileGeom<D>& tg, int l, LevelRegs& r) {
+    r.resd = (double)lp.res[l];
+    r.hi = lp.hi[l];
+    r.w0 = tg.w[l][0];
+    r.w01 = (D > 2) ? tg.w[l][0] * tg.w[l][1] : 0;
+    r.offp = tg.offp[l];
+    r.amul = tg.acc_mul[l];
+    r.alane = (r.amul == 32) ? (int)(threadIdx.x & 31) : 0;
+    // node index within the level = slot - off; accumulator = acc_off + node * amul + alane
+    r.accd = -tg.off[l];
+    r.alane += tg.acc_off[l];
+    r.staged = (tg.staged >> l) & 1u;
+}
+
+// Cell, weights and the shared-memory slots of the 2^D corners of one point at one staged level.
+template <int D>
+struct Stencil {
+    int slot[1 << D];
+    float w[1 << D];
+};
+
+__device__ __forceinline__ void locate_r(double t, const LevelRegs& r, int32_t& cell, float& f, float& g) {
+    float x = __double2float_rn(__dmul_rn(r.resd, t));
+    x = fmaxf(0.0f, fminf(r.hi, x));
+    cell = __float2int_rd(x);
+    f = __fsub_rn(x, (float)cell);
+    g = __fsub_rn(1.0f, f);
+}
+
+template <int D>
+__device__ __forceinline__ void stencil(const double (&t)[D], const LevelRegs& r, Stencil<D>& s) {
+    int p[D];
+    float f[D], g1[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) locate_r(t[d], r, p[d], f[d], g1[d]);
+    if constexpr (D == 2) {
+        const int base = r.offp + p[0] + p[1] * r.w0;
+        s.w[0] = __fmul_rn(g1[0], g1[1]);
+        s.w[1] = __fmul_rn(g1[0], f[1]);
+        s.w[2] = __fmul_rn(f[0], g1[1]);
+        s.w[3] = __fmul_rn(f[0], f[1]);
+        s.slot[0] = base;              // (x, y)
+        s.slot[1] = base + r.w0;       // (x, y+1)
+        s.slot[2] = base + 1;          // (x+1, y)
+        s.slot[3] = base + r.w0 + 1;   // (x+1, y+1)
+    } else {
+        const int base = r.offp + p[0] + p[1] * r.w0 + p[2] * r.w01;
+        const float gg = __fmul_rn(g1[0], g1[1]), gf = __fmul_rn(g1[0], f[1]);
+        const float fg = __fmul_rn(f[0], g1[1]), ff = __fmul_rn(f[0], f[1]);
+        s.w[0] = __fmul_rn(gg, g1[2]); s.w[1] = __fmul_rn(gg, f[2]);
+        s.w[2] = __fmul_rn(gf, g1[2]); s.w[3] = __fmul_rn(gf, f[2]);
+        s.w[4] = __fmul_rn(fg, g1[2]); s.w[5] = __fmul_rn(fg, f[2]);
+        s.w[6] = __fmul_rn(ff, g1[2]); s.w[7] = __fmul_rn(ff, f[2]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s.slot[k] = base + ((k >> 2) & 1) + ((k >> 1) & 1) * r.w0 + (k & 1) * r.w01;
+    }
+}
+
+// z[ch] = sum_k w_k * q_k in the contraction order of the reference build: fma(v0,w0, v1*w1), then k = 2..
+template <int NC, int C>
+__device__ __forceinline__ void lerp_rows(const float (&v)[NC][C], const float (&w)[NC], float (&z)[C]) {
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        float acc = __fmul_rn(v[1][ch], w[1]);
+        acc = __fmaf_rn(v[0][ch], w[0], acc);
+#pragma unroll
+        for (int k = 2; k < NC; ++k) acc = __fmaf_rn(v[k][ch], w[k], acc);
+        z[ch] = acc;
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void lds_row(const float* p, float (&v)[C]) {
+    if constexpr (C == 1) {
+        v[0] = p[0];
+    } else if constexpr (C == 2) {
+        const float2 a = *reinterpret_cast<const float2*>(p);
+        v[0] = a.x; v[1] = a.y;
+    } else {
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+}
+
+// Interpolated (rounded) latents of one point at one level: from the tile's staged nodes, or by
+// direct global gathers when the level did not fit the tile's shared-memory box.
+template <int D, int C>
+__device__ __forceinline__ void interp_level(const double (&t)[D], const LevelParams& lp, const LevelRegs& r, int l,
+                                             const float* s_nodes, const float* __restrict__ latents, int round_flag,
+                                             float (&z)[C]) {
+    constexpr int NC = 1 << D;
+    float v[NC][C];
+    if (r.staged) {
+        Stencil<D> st;
+        stencil<D>(t, r, st);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) lds_row<C>(s_nodes + (size_t)st.slot[k] * C, v[k]);
+        lerp_rows<NC, C>(v, st.w, z);
+    } else {
+        Corners<D> c;
+        corners<D>(t, lp, l, c);
+        const float* base = latents + (int64_t)lp.first[l] * C;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            load_row<C>(base + (int64_t)c.idx[k] * C, v[k]);
+            if (round_flag) {
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) v[k][ch] = rintf(v[k][ch]);
+            }
+        }
+        lerp_rows<NC, C>(v, c.w, z);
+    }
+}
+
+// staged levels are a prefix of the levels and their slots are contiguous: level of slot e by binary search
+template <int D>
+__device__ __forceinline__ int level_of_slot(const TileGeom<D>& tg, int num_staged, int e) {
+    int a = 0, b = num_staged;  // last staged level with off <= e
     while (b - a > 1) {
         const int m = (a + b) >> 1;
         if (tg.off[m] <= e) a = m; else b = m;
     }
-    // skip back over unstaged (empty) levels that share the same offset
-    while (a > 0 && !((tg.staged >> a) & 1u)) --a;
     return a;
 }
 
-// cell, local node index and weights of one point at one level
-template <int D>
-struct LocalCorners {
-    int base;          // local index of corner 0 in the tile's node box (staged levels)
-    int stride[D];     // local index step per axis
-    float w[1 << D];
-};
+// Stage the (rounded) latents of every node of the tile's staged levels into shared memory. The slot
+// loop is flat over all levels and unrolled so that each thread has kStageUnroll independent gathers
+// in flight (a per-level loop would serialise one global-load latency per level).
+constexpr int kStageUnroll = 4;
+template <int D, int C>
+__device__ __forceinline__ void stage_nodes(const TileGeom<D>& tg, const LevelParams& lp,
+                                            const float* __restrict__ latents, int round_flag, float* s_nodes) {
+    const int total = tg.total;
+    const int ns = __popc(tg.staged);
+    for (int e0 = threadIdx.x; e0 < total; e0 += kTileThreads * kStageUnroll) {
+        float v[kStageUnroll][C];
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u) {
+            const int e = e0 + u * kTileThreads;
+            if (e < total) {
+                const int l = level_of_slot<D>(tg, ns, e);
+                const int row = node_row<D>(tg, lp, l, e - tg.off[l], true);
+                load_row<C>(latents + ((int64_t)lp.first[l] + row) * C, v[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u) {
+            const int e = e0 + u * kTileThreads;
+            if (e < total) {
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) s_nodes[(size_t)e * C + ch] = round_flag ? rintf(v[u][ch]) : v[u][ch];
+            }
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
-// forward
+// forward: 4 levels per iteration, outputs written as 16-byte vectors (needs num_lods % 4 == 0)
 // ---------------------------------------------------------------------------------------------
 template <int D, int C, int F>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, (C * F <= 4) ? 7 : 3)
 latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, const __grid_constant__ LevelParams lp,
                         const float* __restrict__ A, const float* __restrict__ shift, int per_level, int round_flag,
                         float* __restrict__ feats, int cap) {
@@ -252,99 +463,54 @@ latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, co
     for (int e = threadIdx.x; e < nA * C * F; e += kTileThreads) s_A[e] = A[e];
     for (int e = threadIdx.x; e < nA * F; e += kTileThreads) s_shift[e] = shift ? shift[e] : 0.0f;
     tile_geometry<D>(tg, lp, ti, pv.g, cap);
-
-    // stage the tile's nodes: one gather per node instead of 2^D per point
-    for (int e = threadIdx.x; e < tg.total; e += kTileThreads) {
-        const int l = level_of_node<D>(tg, L, e);
-        const int row = node_row<D>(tg, lp, l, e - tg.off[l], true);
-        float v[C];
-        load_row<C>(latents + ((int64_t)lp.first[l] + row) * C, v);
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch) s_nodes[(size_t)e * C + ch] = round_flag ? rintf(v[ch]) : v[ch];
-    }
+    stage_nodes<D, C>(tg, lp, latents, round_flag, s_nodes);
     __syncthreads();
 
-    constexpr int NC = 1 << D;
-    constexpr int G = (F >= 4) ? 1 : 4 / F;  // levels per 16-byte output vector
-    const bool vec_o = (L * F) % 4 == 0 && (L % G) == 0;
-    for (int j = beg + threadIdx.x; j < end; j += kTileThreads) {
-        double t[D];
-        load_unit_coords<D>(pv.coords_sorted, j, t);
-        float* out = feats + (int64_t)__ldg(pv.perm + j) * L * F;
-        float o[G * F];
-        for (int l = 0; l < L; ++l) {
-            float z[C];
-            if ((tg.staged >> l) & 1u) {
-                const int32_t res = lp.res[l];
-                const float hi = lp.hi[l];
-                int p[D];
-                float f[D], g1[D];
+    for (int base = beg; base < end; base += kTileThreads * kPts) {
+        // kPts points per thread: permutation entries and coordinates of all of them are requested first
+        int orig[kPts];
+        double t[kPts][D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) locate(t[d], res, hi, p[d], f[d], g1[d]);
-                int base = tg.off[l], stride = 1, st[D];
+        for (int k = 0; k < kPts; ++k) {
+            const int j = base + k * kTileThreads + threadIdx.x;
+            orig[k] = -1;
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    base += (p[d] - tg.c0[l][d]) * stride;
-                    st[d] = stride;
-                    stride *= tg.w[l][d];
-                }
-                float w[NC];
-                int li[NC];
-                if constexpr (D == 2) {
-                    w[0] = __fmul_rn(g1[0], g1[1]); w[1] = __fmul_rn(g1[0], f[1]);
-                    w[2] = __fmul_rn(f[0], g1[1]);  w[3] = __fmul_rn(f[0], f[1]);
-                    li[0] = base; li[1] = base + st[1]; li[2] = base + st[0]; li[3] = base + st[0] + st[1];
-                } else {
-                    const float gg = __fmul_rn(g1[0], g1[1]), gf = __fmul_rn(g1[0], f[1]);
-                    const float fg = __fmul_rn(f[0], g1[1]), ff = __fmul_rn(f[0], f[1]);
-                    w[0] = __fmul_rn(gg, g1[2]); w[1] = __fmul_rn(gg, f[2]); w[2] = __fmul_rn(gf, g1[2]);
-                    w[3] = __fmul_rn(gf, f[2]);  w[4] = __fmul_rn(fg, g1[2]); w[5] = __fmul_rn(fg, f[2]);
-                    w[6] = __fmul_rn(ff, g1[2]); w[7] = __fmul_rn(ff, f[2]);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        li[k] = base + ((k >> 2) & 1) * st[0] + ((k >> 1) & 1) * st[1] + (k & 1) * st[2];
-                }
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) {
-                    // same contraction order as the reference build: fma(v0,w0, v1*w1), then k = 2..
-                    float acc = __fmul_rn(s_nodes[(size_t)li[1] * C + ch], w[1]);
-                    acc = __fmaf_rn(s_nodes[(size_t)li[0] * C + ch], w[0], acc);
-#pragma unroll
-                    for (int k = 2; k < NC; ++k) acc = __fmaf_rn(s_nodes[(size_t)li[k] * C + ch], w[k], acc);
-                    z[ch] = acc;
-                }
-            } else {  // level too large for the tile's shared-memory box: direct global gathers
-                Corners<D> c;
-                corners<D>(t, lp, l, c);
-                const float* base = latents + (int64_t)lp.first[l] * C;
-                float v[NC][C];
-#pragma unroll
-                for (int k = 0; k < NC; ++k) load_row<C>(base + (int64_t)c.idx[k] * C, v[k]);
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) {
-                    float acc = __fmul_rn(round_flag ? rintf(v[1][ch]) : v[1][ch], c.w[1]);
-                    acc = __fmaf_rn(round_flag ? rintf(v[0][ch]) : v[0][ch], c.w[0], acc);
-#pragma unroll
-                    for (int k = 2; k < NC; ++k) acc = __fmaf_rn(round_flag ? rintf(v[k][ch]) : v[k][ch], c.w[k], acc);
-                    z[ch] = acc;
-                }
+            for (int d = 0; d < D; ++d) t[k][d] = 0.5;
+            if (j < end) {
+                orig[k] = __ldg(pv.perm + j);
+                load_unit_coords<D>(pv.coords_sorted, j, t[k]);
             }
-            const int la = per_level ? l : 0;
-            const int q = l % G;
+        }
+        for (int l0 = 0; l0 < L; l0 += 4) {
+            LevelRegs lr[4];
+            float sh[4][F], Am[4][C * F];
 #pragma unroll
-            for (int jf = 0; jf < F; ++jf) {
-                float acc = s_shift[la * F + jf];
+            for (int q = 0; q < 4; ++q) {
+                load_level_regs<D>(lp, tg, l0 + q, lr[q]);
+                const int la = per_level ? (l0 + q) : 0;
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) acc = __fmaf_rn(z[ch], s_A[(la * C + ch) * F + jf], acc);
-                if (vec_o) {
+                for (int jf = 0; jf < F; ++jf) sh[q][jf] = s_shift[la * F + jf];
 #pragma unroll
-                    for (int qq = 0; qq < G; ++qq)
-                        if (qq == q) o[qq * F + jf] = acc;
-                } else {
-                    out[l * F + jf] = acc;
-                }
+                for (int e = 0; e < C * F; ++e) Am[q][e] = s_A[la * C * F + e];
             }
-            if (vec_o && q == G - 1) store_row<G * F>(out + (l - (G - 1)) * F, o);
+#pragma unroll
+            for (int k = 0; k < kPts; ++k) {
+                if (orig[k] < 0) continue;
+                float o[4 * F];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float z[C];
+                    interp_level<D, C>(t[k], lp, lr[q], l0 + q, s_nodes, latents, round_flag, z);
+#pragma unroll
+                    for (int jf = 0; jf < F; ++jf) {
+                        float acc = sh[q][jf];
+#pragma unroll
+                        for (int ch = 0; ch < C; ++ch) acc = __fmaf_rn(z[ch], Am[q][ch * F + jf], acc);
+                        o[q * F + jf] = acc;
+                    }
+                }
+                store_row<4 * F>(feats + (int64_t)orig[k] * L * F + l0 * F, o);
+            }
         }
     }
 }
@@ -366,23 +532,22 @@ __device__ __forceinline__ float fixed_scale(float m, int k, float& inv) {
 }
 
 template <int D, int C, int F, bool DEC>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, (C * F <= 4) ? 7 : 3)
 latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, const float* __restrict__ latents,
                         const __grid_constant__ LevelParams lp, const float* __restrict__ A, int per_level,
                         int round_flag, float* __restrict__ grad_latents, float* __restrict__ grad_A,
-                        float* __restrict__ grad_shift, int cap) {
+                        float* __restrict__ grad_shift, int cap, int cap_acc) {
     extern __shared__ float s_dyn[];
     __shared__ TileGeom<D> tg;
     __shared__ unsigned s_gmax[SHACIRA_MAX_LEVELS];   // max |A^T g| per level over the batch (float bits)
-    __shared__ unsigned s_omax[SHACIRA_MAX_LEVELS];   // max |g| per level (decoder-gradient scale)
-    __shared__ unsigned s_zmax;                        // max |staged latent|
     __shared__ float s_scale[SHACIRA_MAX_LEVELS], s_inv[SHACIRA_MAX_LEVELS];
-    __shared__ float s_oscale[SHACIRA_MAX_LEVELS], s_oinv[SHACIRA_MAX_LEVELS];
     const int L = lp.num_lods;
     const int nA = per_level ? L : 1;
     constexpr int NW = kTileThreads / 32;
-    int* s_acc = reinterpret_cast<int*>(s_dyn);                           // [cap][C] fixed-point node sums
-    float* s_lat = s_dyn + (size_t)cap * C;                               // [cap][C] staged latents (DEC)
+    constexpr int NC = 1 << D;
+    constexpr int KP = (F == 1) ? kPts : ((F == 2) ? 2 : 1);  // keeps the in-flight rows within ~16 registers
+    int* s_acc = reinterpret_cast<int*>(s_dyn);                           // [cap_acc][C] fixed-point node sums
+    float* s_lat = s_dyn + (size_t)cap_acc * C;                           // [cap][C] staged latents (DEC)
     float* s_A = s_lat + (DEC ? (size_t)cap * C : 0);                     // [nA][C][F]
     float* s_gA = s_A + nA * C * F;                                       // [NW][L][C][F] per-warp partial sums
     float* s_gS = s_gA + (DEC ? NW * L * C * F : 0);                      // [NW][L][F]
@@ -399,68 +564,48 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
     for (int e = threadIdx.x; e < nA * C * F; e += kTileThreads) s_A[e] = A[e];
     if (DEC)
         for (int e = threadIdx.x; e < NW * L * (C * F + F); e += kTileThreads) s_gA[e] = 0.0f;
-    if (threadIdx.x == 0) s_zmax = 0u;
-    tile_geometry<D>(tg, lp, ti, pv.g, cap);
-    if (DEC) {
-        unsigned zm = 0u;
-        for (int e = threadIdx.x; e < tg.total; e += kTileThreads) {
-            const int l = level_of_node<D>(tg, L, e);
-            const int row = node_row<D>(tg, lp, l, e - tg.off[l], true);
-            float v[C];
-            load_row<C>(latents + ((int64_t)lp.first[l] + row) * C, v);
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-                const float q = round_flag ? rintf(v[ch]) : v[ch];
-                s_lat[(size_t)e * C + ch] = q;
-                zm = max(zm, __float_as_uint(fabsf(q)));
-            }
-        }
-        zm = __reduce_max_sync(0xffffffffu, zm);
-        if (lane == 0) atomicMax(&s_zmax, zm);
-    }
-    constexpr int NC = 1 << D;
-    const bool vec_g = (F == 1) || ((L * F) % (F >= 4 ? 4 : F) == 0);
+    tile_geometry<D>(tg, lp, ti, pv.g, cap, cap_acc, kRepBudget / C);
+    if (DEC) stage_nodes<D, C>(tg, lp, latents, round_flag, s_lat);
 
     for (int b0 = beg; b0 < end; b0 += kBatch) {
         const int b1 = min(end, b0 + kBatch);
         int kbits = 0;
         while ((1 << kbits) < (b1 - b0)) ++kbits;
-        for (int e = threadIdx.x; e < tg.total * C; e += kTileThreads) s_acc[e] = 0;
-        if (threadIdx.x < SHACIRA_MAX_LEVELS) { s_gmax[threadIdx.x] = 0u; s_omax[threadIdx.x] = 0u; }
+        for (int e = threadIdx.x; e < tg.acc_total * C; e += kTileThreads) s_acc[e] = 0;
+        if (threadIdx.x < SHACIRA_MAX_LEVELS) s_gmax[threadIdx.x] = 0u;
         __syncthreads();
-        // pass 1: per-level maxima of what will be accumulated
-        for (int j0 = b0; j0 < b1; j0 += kTileThreads) {
-            const int j = j0 + threadIdx.x;
-            const bool live = j < b1;
-            const float* g_row = grad_out + (int64_t)(live ? __ldg(pv.perm + j) : 0) * L * F;
-            for (int l = 0; l < L; ++l) {
-                float g[F];
+        // pass 1: per-level maxima of what will be accumulated. Level chunk outer, points inner: the running
+        // maxima of the chunk's 4 levels stay in registers; one REDUX + shared atomicMax per warp and level.
+        for (int l0 = 0; l0 < L; l0 += 4) {
+            float m[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            for (int base = b0; base < b1; base += kTileThreads * KP) {
+                float g[KP][4 * F];
 #pragma unroll
-                for (int jf = 0; jf < F; ++jf) g[jf] = 0.0f;
-                if (live) {
-                    if (vec_g) load_row<F>(g_row + l * F, g);
-                    else {
+                for (int k = 0; k < KP; ++k) {
+                    const int j = base + k * kTileThreads + threadIdx.x;
 #pragma unroll
-                        for (int jf = 0; jf < F; ++jf) g[jf] = __ldg(g_row + l * F + jf);
+                    for (int e = 0; e < 4 * F; ++e) g[k][e] = 0.0f;
+                    if (j < b1) load_row<4 * F>(grad_out + (int64_t)__ldg(pv.perm + j) * L * F + l0 * F, g[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int la = per_level ? (l0 + q) : 0;
+#pragma unroll
+                        for (int ch = 0; ch < C; ++ch) {
+                            float acc = 0.0f;
+#pragma unroll
+                            for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[k][q * F + jf], s_A[(la * C + ch) * F + jf], acc);
+                            m[q] = fmaxf(m[q], fabsf(acc));
+                        }
                     }
                 }
-                const int la = per_level ? l : 0;
-                float m = 0.0f, mo = 0.0f;
+            }
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) {
-                    float acc = 0.0f;
-#pragma unroll
-                    for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[jf], s_A[(la * C + ch) * F + jf], acc);
-                    m = fmaxf(m, fabsf(acc));
-                }
-#pragma unroll
-                for (int jf = 0; jf < F; ++jf) mo = fmaxf(mo, fabsf(g[jf]));
-                const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
-                if (lane == 0 && wm) atomicMax(&s_gmax[l], wm);
-                if (DEC) {
-                    const unsigned wo = __reduce_max_sync(0xffffffffu, __float_as_uint(mo));
-                    if (lane == 0 && wo) atomicMax(&s_omax[l], wo);
-                }
+            for (int q = 0; q < 4; ++q) {
+                const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m[q]));
+                if (lane == 0 && wm) atomicMax(&s_gmax[l0 + q], wm);
             }
         }
         __syncthreads();
@@ -468,162 +613,170 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
             float inv;
             s_scale[threadIdx.x] = fixed_scale(__uint_as_float(s_gmax[threadIdx.x]), kbits, inv);
             s_inv[threadIdx.x] = inv;
-            if (DEC) {
-                s_oscale[threadIdx.x] = fixed_scale(__uint_as_float(s_omax[threadIdx.x]), 5, inv);  // 32-lane REDUX
-                s_oinv[threadIdx.x] = inv;
-            }
         }
         __syncthreads();
-        float zscale = 0.0f, zinv = 0.0f;
-        if (DEC) {
-            // z is a convex combination of staged values: |z| <= zmax (direct levels use their own bound below)
-            int ex = 0;
-            const float zm = __uint_as_float(s_zmax);
-            if (zm > 0.0f) frexpf(zm, &ex);
-            zscale = ldexpf(1.0f, -ex);  // z * zscale in [-1, 1]
-            zinv = ldexpf(1.0f, ex);
-        }
-        // pass 2: accumulate
-        for (int j0 = b0; j0 < b1; j0 += kTileThreads) {
-            const int j = j0 + threadIdx.x;
-            const bool live = j < b1;
-            double t[D];
-            if (live) load_unit_coords<D>(pv.coords_sorted, j, t);
-            const float* g_row = grad_out + (int64_t)(live ? __ldg(pv.perm + j) : 0) * L * F;
-            for (int l = 0; l < L; ++l) {
-                float g[F];
+        // pass 2: accumulate. Decoder-gradient partial sums of the chunk's levels stay in registers (plain
+        // float per thread) across the points loop and are reduced over the warp once per chunk.
+        for (int l0 = 0; l0 < L; l0 += 4) {
+            float accS[DEC ? 4 * F : 1], accA[DEC ? 4 * C * F : 1];
+            if (DEC) {
 #pragma unroll
-                for (int jf = 0; jf < F; ++jf) g[jf] = 0.0f;
-                float z[C];
+                for (int e = 0; e < 4 * F; ++e) accS[e] = 0.0f;
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) z[ch] = 0.0f;
-                const int la = per_level ? l : 0;
-                if (live) {
-                    if (vec_g) load_row<F>(g_row + l * F, g);
-                    else {
+                for (int e = 0; e < 4 * C * F; ++e) accA[e] = 0.0f;
+            }
+            LevelRegs lr[4];
+            float scq[4], Am[4][C * F];
 #pragma unroll
-                        for (int jf = 0; jf < F; ++jf) g[jf] = __ldg(g_row + l * F + jf);
+            for (int q = 0; q < 4; ++q) {
+                load_level_regs<D>(lp, tg, l0 + q, lr[q]);
+                scq[q] = s_scale[l0 + q];
+                const int la = per_level ? (l0 + q) : 0;
+#pragma unroll
+                for (int e = 0; e < C * F; ++e) Am[q][e] = s_A[la * C * F + e];
+            }
+            for (int base = b0; base < b1; base += kTileThreads * KP) {
+                float gk[KP][4 * F];
+                double tk[KP][D];
+                bool livek[KP];
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    const int j = base + k * kTileThreads + threadIdx.x;
+                    livek[k] = j < b1;
+#pragma unroll
+                    for (int e = 0; e < 4 * F; ++e) gk[k][e] = 0.0f;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) tk[k][d] = 0.5;
+                    if (livek[k]) {
+                        load_row<4 * F>(grad_out + (int64_t)__ldg(pv.perm + j) * L * F + l0 * F, gk[k]);
+                        load_unit_coords<D>(pv.coords_sorted, j, tk[k]);
                     }
-                    float gz[C];
+                }
 #pragma unroll
-                    for (int ch = 0; ch < C; ++ch) {
-                        float acc = 0.0f;
+                for (int k = 0; k < KP; ++k) {
+                    if (!livek[k]) continue;
+                    const double (&t)[D] = tk[k];
+                    const float (&g)[4 * F] = gk[k];
 #pragma unroll
-                        for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[jf], s_A[(la * C + ch) * F + jf], acc);
-                        gz[ch] = acc;
-                    }
-                    if ((tg.staged >> l) & 1u) {
-                        const int32_t res = lp.res[l];
-                        const float hi = lp.hi[l];
-                        int p[D];
-                        float f[D], g1[D];
+                    for (int q = 0; q < 4; ++q) {
+                        const int l = l0 + q;
+                        float gz[C], z[C];
 #pragma unroll
-                        for (int d = 0; d < D; ++d) locate(t[d], res, hi, p[d], f[d], g1[d]);
-                        int base = tg.off[l], stride = 1, st[D];
+                        for (int ch = 0; ch < C; ++ch) {
+                            float acc = 0.0f;
 #pragma unroll
-                        for (int d = 0; d < D; ++d) {
-                            base += (p[d] - tg.c0[l][d]) * stride;
-                            st[d] = stride;
-                            stride *= tg.w[l][d];
+                            for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[q * F + jf], Am[q][ch * F + jf], acc);
+                            gz[ch] = acc;
+                            z[ch] = 0.0f;
                         }
-                        float w[NC];
-                        int li[NC];
-                        if constexpr (D == 2) {
-                            w[0] = __fmul_rn(g1[0], g1[1]); w[1] = __fmul_rn(g1[0], f[1]);
-                            w[2] = __fmul_rn(f[0], g1[1]);  w[3] = __fmul_rn(f[0], f[1]);
-                            li[0] = base; li[1] = base + st[1]; li[2] = base + st[0]; li[3] = base + st[0] + st[1];
-                        } else {
-                            const float gg = __fmul_rn(g1[0], g1[1]), gf = __fmul_rn(g1[0], f[1]);
-                            const float fg = __fmul_rn(f[0], g1[1]), ff = __fmul_rn(f[0], f[1]);
-                            w[0] = __fmul_rn(gg, g1[2]); w[1] = __fmul_rn(gg, f[2]); w[2] = __fmul_rn(gf, g1[2]);
-                            w[3] = __fmul_rn(gf, f[2]);  w[4] = __fmul_rn(fg, g1[2]); w[5] = __fmul_rn(fg, f[2]);
-                            w[6] = __fmul_rn(ff, g1[2]); w[7] = __fmul_rn(ff, f[2]);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                li[k] = base + ((k >> 2) & 1) * st[0] + ((k >> 1) & 1) * st[1] + (k & 1) * st[2];
-                        }
-                        const float sc = s_scale[l];
-#pragma unroll
-                        for (int k = 0; k < NC; ++k) {
+                        if (lr[q].staged) {
+                            Stencil<D> st;
+                            stencil<D>(t, lr[q], st);
+                            const float sc = scq[q];
 #pragma unroll
                             for (int ch = 0; ch < C; ++ch) {
-                                const int q = __float2int_rn(__fmul_rn(__fmul_rn(gz[ch], w[k]), sc));
-                                if (q) atomicAdd(&s_acc[(size_t)li[k] * C + ch], q);
+                                const float gs = __fmul_rn(gz[ch], sc);  // power-of-two scale: exact
+#pragma unroll
+                                for (int kk = 0; kk < NC; ++kk)
+                                    atomicAdd(&s_acc[(size_t)((st.slot[kk] + lr[q].accd) * lr[q].amul + lr[q].alane) * C + ch],
+                                              __float2int_rn(__fmul_rn(gs, st.w[kk])));
+                            }
+                            if (DEC) {
+                                float v[NC][C];
+#pragma unroll
+                                for (int kk = 0; kk < NC; ++kk) lds_row<C>(s_lat + (size_t)st.slot[kk] * C, v[kk]);
+                                lerp_rows<NC, C>(v, st.w, z);
+                            }
+                        } else {  // direct level: float REDG to global, gathers for z
+                            Corners<D> c;
+                            corners<D>(t, lp, l, c);
+                            float* gbase = grad_latents + (int64_t)lp.first[l] * C;
+#pragma unroll
+                            for (int kk = 0; kk < NC; ++kk) {
+                                float gv[C];
+#pragma unroll
+                                for (int ch = 0; ch < C; ++ch) gv[ch] = __fmul_rn(gz[ch], c.w[kk]);
+                                red_add_row<C>(gbase + (int64_t)c.idx[kk] * C, gv);
+                            }
+                            if (DEC) {
+                                const float* lb = latents + (int64_t)lp.first[l] * C;
+                                float v[NC][C];
+#pragma unroll
+                                for (int kk = 0; kk < NC; ++kk) {
+                                    load_row<C>(lb + (int64_t)c.idx[kk] * C, v[kk]);
+                                    if (round_flag) {
+#pragma unroll
+                                        for (int ch = 0; ch < C; ++ch) v[kk][ch] = rintf(v[kk][ch]);
+                                    }
+                                }
+                                lerp_rows<NC, C>(v, c.w, z);
                             }
                         }
                         if (DEC) {
 #pragma unroll
-                            for (int ch = 0; ch < C; ++ch) {
-                                float acc = __fmul_rn(s_lat[(size_t)li[1] * C + ch], w[1]);
-                                acc = __fmaf_rn(s_lat[(size_t)li[0] * C + ch], w[0], acc);
-#pragma unroll
-                                for (int k = 2; k < NC; ++k) acc = __fmaf_rn(s_lat[(size_t)li[k] * C + ch], w[k], acc);
-                                z[ch] = acc;
-                            }
-                        }
-                    } else {  // direct level: float REDG to global, gathers for z
-                        Corners<D> c;
-                        corners<D>(t, lp, l, c);
-                        float* base = grad_latents + (int64_t)lp.first[l] * C;
-#pragma unroll
-                        for (int k = 0; k < NC; ++k) {
-                            float gv[C];
-#pragma unroll
-                            for (int ch = 0; ch < C; ++ch) gv[ch] = __fmul_rn(gz[ch], c.w[k]);
-                            red_add_row<C>(base + (int64_t)c.idx[k] * C, gv);
-                        }
-                        if (DEC) {
-                            const float* lb = latents + (int64_t)lp.first[l] * C;
-#pragma unroll
-                            for (int k = 0; k < NC; ++k) {
-                                float v[C];
-                                load_row<C>(lb + (int64_t)c.idx[k] * C, v);
+                            for (int jf = 0; jf < F; ++jf) {
+                                accS[q * F + jf] += g[q * F + jf];
 #pragma unroll
                                 for (int ch = 0; ch < C; ++ch)
-                                    z[ch] = __fmaf_rn(round_flag ? rintf(v[ch]) : v[ch], c.w[k], z[ch]);
+                                    accA[(q * C + ch) * F + jf] = __fmaf_rn(z[ch], g[q * F + jf], accA[(q * C + ch) * F + jf]);
                             }
                         }
                     }
                 }
-                if (DEC) {
-                    // decoder gradients: fixed-point REDUX over the warp, one float add per warp and value
-                    const float os = s_oscale[l], oi = s_oinv[l];
-                    const bool staged_l = (tg.staged >> l) & 1u;
+            }
+            if (DEC) {
 #pragma unroll
-                    for (int jf = 0; jf < F; ++jf) {
-                        const int qs = __float2int_rn(__fmul_rn(g[jf], os));
-                        const int ss = __reduce_add_sync(0xffffffffu, qs);
-                        if (lane == 0 && ss) s_gS[(warp * L + l) * F + jf] += (float)ss * oi;
+                for (int e = 0; e < 4 * F; ++e) {
+                    const float v = warp_sum(accS[e]);
+                    if (lane == 0) s_gS[(warp * L + l0) * F + e] += v;   // [l0 + q][jf] is contiguous: e = q*F + jf
+                }
 #pragma unroll
-                        for (int ch = 0; ch < C; ++ch) {
-                            if (staged_l) {
-                                const int qa = __float2int_rn(__fmul_rn(__fmul_rn(z[ch], zscale), __fmul_rn(g[jf], os)));
-                                const int sa = __reduce_add_sync(0xffffffffu, qa);
-                                if (lane == 0 && sa) s_gA[((warp * L + l) * C + ch) * F + jf] += (float)sa * oi * zinv;
-                            } else {
-                                const float sa = warp_sum(z[ch] * g[jf]);
-                                if (lane == 0) s_gA[((warp * L + l) * C + ch) * F + jf] += sa;
-                            }
-                        }
-                    }
+                for (int e = 0; e < 4 * C * F; ++e) {
+                    const float v = warp_sum(accA[e]);
+                    if (lane == 0) s_gA[(warp * L + l0) * C * F + e] += v;  // e = (q*C + ch)*F + jf
                 }
             }
         }
         __syncthreads();
         // flush: one float REDG per touched node
-        for (int e = threadIdx.x; e < tg.total; e += kTileThreads) {
-            const int l = level_of_node<D>(tg, L, e);
-            bool any = false;
-            float gv[C];
+        for (int l = 0; l < L; ++l) {
+            if (!((tg.staged >> l) & 1u)) continue;
+            int n_l = 1;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-                const int q = s_acc[(size_t)e * C + ch];
-                any |= (q != 0);
-                gv[ch] = (float)q * s_inv[l];
-            }
-            if (any) {
-                const int row = node_row<D>(tg, lp, l, e - tg.off[l], false);
-                if (row >= 0) red_add_row<C>(grad_latents + ((int64_t)lp.first[l] + row) * C, gv);
+            for (int d = 0; d < D; ++d) n_l *= tg.w[l][d];
+            const float inv = s_inv[l];
+            float* base = grad_latents + (int64_t)lp.first[l] * C;
+            if (tg.acc_mul[l] == 32) {
+                // lane-replicated level: a warp sums the 32 copies of a node with REDUX (exact integers)
+                for (int e = warp; e < n_l; e += NW) {
+                    bool any = false;
+                    float gv[C];
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) {
+                        const int qv = __reduce_add_sync(0xffffffffu, s_acc[(size_t)(tg.acc_off[l] + e * 32 + lane) * C + ch]);
+                        any |= (qv != 0);
+                        gv[ch] = (float)qv * inv;
+                    }
+                    if (any && lane == 0) {
+                        const int row = node_row<D>(tg, lp, l, e, false);
+                        if (row >= 0) red_add_row<C>(base + (int64_t)row * C, gv);
+                    }
+                }
+            } else {
+                for (int e = threadIdx.x; e < n_l; e += kTileThreads) {
+                    bool any = false;
+                    float gv[C];
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) {
+                        const int qv = s_acc[(size_t)(tg.acc_off[l] + e) * C + ch];
+                        any |= (qv != 0);
+                        gv[ch] = (float)qv * inv;
+                    }
+                    if (any) {
+                        const int row = node_row<D>(tg, lp, l, e, false);
+                        if (row >= 0) red_add_row<C>(base + (int64_t)row * C, gv);
+                    }
+                }
             }
         }
         __syncthreads();

@@ -138,7 +138,7 @@ class LatentHashGrid(torch.autograd.Function):
     def forward(ctx, coords, latents, A, shift, first_idx, resolutions, bitwidth, round_flag):
         F = A.shape[2]
         need_dec = bool(ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
-        plan = plan_for(coords)
+        plan = plan_for(coords) if len(resolutions) % 4 == 0 else None  # tiled kernels unroll 4 levels
         if plan is not None:
             feats = _lib.latent_forward_planned(plan, latents, first_idx, resolutions, bitwidth, A, shift, F, round_flag)
             # the tiled backward recomputes the interpolation from the latents: nothing extra is written here
