@@ -1,0 +1,85 @@
+"""Device time of the tiled forward / backward kernels alone, host launch overhead removed by CUDA-graph
+replay (K launches per graph over rotating input sets). Used for kernel tuning; bench.py is the contract."""
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from shacira_b200 import _lib  # noqa: E402
+
+
+def main():
+    K = int(os.environ.get("K", "40"))
+    dev = torch.device("cuda", 0)
+    wl = bench.make_workload(0)
+    d = lambda a: torch.from_numpy(a).to(dev)
+    sets = [dict(coords=d(s["coords"]), grad_out=d(s["grad_out"])) for s in wl["sets"]]
+    lat, A, shift = d(wl["latents"]), d(wl["A"]), d(wl["shift"])
+    first, res, T, L = wl["first"], wl["res"], wl["T"], bench.NUM_LODS
+    n = bench.H * bench.W
+    lib = _lib.load()
+    fi, _ = _lib._i32_array(first)
+    rs, _ = _lib._i32_array(res)
+    for s in sets:
+        s["plan"] = _lib.Plan(s["coords"])
+        s["feats"] = torch.empty((n, L), device=dev)
+        s["gl"] = torch.empty((T, 1), device=dev)
+        s["z"] = torch.empty((n, L), device=dev)
+    gA = torch.zeros((L, 1, 1), device=dev)
+    gS = torch.zeros((L, 1), device=dev)
+    p = _lib._ptr
+
+    def fwd(s, st):
+        _lib._check(lib.shacira_latent_forward_planned(s["plan"].handle, p(lat), fi, rs, L, bench.BITWIDTH, 1, 1, 1, p(A),
+                                                       p(shift), 0, p(s["feats"]), st))
+
+    def bwd(s, st, dec=True):
+        _lib._check(lib.shacira_latent_backward_planned(s["plan"].handle, p(s["grad_out"]), p(lat), fi, rs, L,
+                                                        bench.BITWIDTH, 1, 1, 1, p(A), 0, T, 1, p(s["gl"]),
+                                                        p(gA) if dec else None, p(gS) if dec else None, st))
+
+    def fwd_pp(s, st):
+        _lib._check(lib.shacira_latent_forward(2, p(s["coords"]), n, p(lat), fi, rs, L, bench.BITWIDTH, 1, 1, 1, p(A),
+                                               p(shift), 0, p(s["feats"]), p(s["z"]), st))
+
+    def bwd_pp(s, st):
+        _lib._check(lib.shacira_latent_backward(2, p(s["coords"]), n, p(s["grad_out"]), p(s["z"]), fi, rs, L,
+                                                bench.BITWIDTH, 1, 1, p(A), 0, T, 1, p(s["gl"]), p(gA), p(gS), st))
+
+    out = {}
+    for name, fn in (("fwd_tiled", fwd), ("bwd_tiled_dec", bwd), ("bwd_tiled_nodec", lambda s, st: bwd(s, st, False)),
+                     ("fwd_pointparallel", fwd_pp), ("bwd_pointparallel", bwd_pp),
+                     ("step_tiled", lambda s, st: (fwd(s, st), bwd(s, st)))):
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            st = ctypes.c_void_p(stream.cuda_stream)
+            for i in range(4):
+                fn(sets[i % len(sets)], st)
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                st2 = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+                for i in range(K):
+                    fn(sets[i % len(sets)], st2)
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = 1e9
+            for _ in range(5):
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1) / K * 1e3)
+        out[name] = round(best, 2)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

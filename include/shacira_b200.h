@@ -100,8 +100,9 @@ int shacira_latent_forward(int32_t dim, const float* coords, int64_t n, const fl
 
 /* Backward of the above. grad_latents[table_rows, C] += w_k * sum_f g[i,l,f] * A[la,c,f]
  * (straight-through: the rounding passes gradients unchanged); grad_A[L, C, F] and
- * grad_shift[L, F] (always per level; the caller sums over levels for a single decoder)
- * are ACCUMULATED into (caller zero-fills); either may be NULL. zsave is the forward's
+ * grad_shift[L, F] are ACCUMULATED into (caller zero-fills); either may be NULL. With
+ * per_level != 0 row l is level l's gradient; with one shared decoder (per_level == 0) only
+ * the SUM over the L rows is defined (the caller adds them; a kernel may put it all in row 0). zsave is the forward's
  * z[n, L*C] (required when grad_A != NULL). */
 int shacira_latent_backward(int32_t dim, const float* coords, int64_t n, const float* grad_output,
                             const float* zsave, const int32_t* first_idx, const int32_t* resolutions,

@@ -51,7 +51,7 @@ int node_capacity(const shacira_plan* p, const LevelParams& lp, int cap_max) {
         if (run + nodes <= cap_max) run += nodes;
     }
     if (run < 32) run = 32;
-    return (int)run;
+    return (int)((run + 3) & ~3LL);  // multiple of 4 slots: the arrays behind it stay 16-byte aligned
 }
 
 template <int D, int C, int F>
@@ -71,15 +71,18 @@ int launch_bwd(const shacira_plan* p, const float* g, const float* lat, const Le
                int per_level, int round_flag, float* gl, float* gA, float* gS, cudaStream_t s) {
     const int nA = per_level ? lp.num_lods : 1;
     const bool dec = gA != nullptr || gS != nullptr;
-    // shared memory: fixed-point accumulators (kRepBudget ints of lane-replicated copies shared by the C
-    // channels + one slot per node) and, for the decoder gradients, the staged latents
+    // shared memory: fixed-point accumulators (kRepBudget ints of lane-replicated copies shared by the CA
+    // accumulator channels + one slot per node) and -- only when the decoder gradients need the per-point
+    // interpolation (F > C) -- the staged latents. Mirrors the kernel's SG / ZP / CA constants.
+    const bool sg = dec && (F <= C), zp = dec && !sg;
+    const int CA = sg ? F : C;
     const bool big = smem_budget() > 24 * 1024;
-    const int rep = big ? kRepBudget / C : 0;  // per channel
-    const int cap = node_capacity(p, lp, (smem_budget() - rep * 4 * C) / (4 * C * (dec ? 2 : 1)));
+    const int rep = big ? ((kRepBudget / CA) & ~3) : 0;  // per accumulator channel
+    const int cap = node_capacity(p, lp, (smem_budget() - rep * 4 * CA) / (4 * (CA + (dec ? C : 0))));
     const int cap_acc = cap + rep;
     constexpr int NW = kTileThreads / 32;
-    size_t smem = sizeof(float) * ((size_t)cap_acc * C + (dec ? (size_t)cap * C : 0) + nA * C * F);
-    if (dec) smem += sizeof(float) * (size_t)NW * lp.num_lods * (C * F + F);
+    size_t smem = sizeof(float) * ((size_t)cap_acc * CA + (dec ? (size_t)cap * C : 0) + nA * C * F);
+    if (dec) smem += sizeof(float) * (size_t)(zp ? NW : 1) * lp.num_lods * (C * F + F);
     if (dec)
         latent_bwd_tiled_kernel<D, C, F, true><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), g, lat, lp, A, per_level,
                                                                                       round_flag, gl, gA, gS, cap, cap_acc);

@@ -531,26 +531,36 @@ __device__ __forceinline__ float fixed_scale(float m, int k, float& inv) {
     return ldexpf(1.0f, e);
 }
 
+// Two formulations, chosen at compile time:
+//   scatter-gz (SG = false): accumulate w_k * (A^T g) per node (C channels). Decoder gradients, when wanted,
+//       need the interpolated latents z per point: the tile stages the latents and re-interpolates.
+//   scatter-g  (SG = true, used when decoder gradients are wanted and F <= C): accumulate G[node] = sum w_k * g
+//       per node (F channels). Everything else is linear in G and is applied ONCE PER NODE at flush time:
+//       grad_latent[node] = A G[node];  grad_A += q[node] G[node]^T;  grad_shift += G[node]  (sum_k w_k = 1).
+//       That is ~2-3 nodes per point instead of 2^D * L corner visits per point.
 template <int D, int C, int F, bool DEC>
 __global__ void __launch_bounds__(kTileThreads, (C * F <= 4) ? 7 : 3)
 latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, const float* __restrict__ latents,
                         const __grid_constant__ LevelParams lp, const float* __restrict__ A, int per_level,
                         int round_flag, float* __restrict__ grad_latents, float* __restrict__ grad_A,
                         float* __restrict__ grad_shift, int cap, int cap_acc) {
+    constexpr bool SG = DEC && (F <= C);
+    constexpr bool ZP = DEC && !SG;          // per-point z recomputation
+    constexpr int CA = SG ? F : C;           // accumulator channels
     extern __shared__ float s_dyn[];
     __shared__ TileGeom<D> tg;
-    __shared__ unsigned s_gmax[SHACIRA_MAX_LEVELS];   // max |A^T g| per level over the batch (float bits)
+    __shared__ unsigned s_gmax[SHACIRA_MAX_LEVELS];   // max |accumulated quantity| per level over the batch
     __shared__ float s_scale[SHACIRA_MAX_LEVELS], s_inv[SHACIRA_MAX_LEVELS];
     const int L = lp.num_lods;
     const int nA = per_level ? L : 1;
     constexpr int NW = kTileThreads / 32;
     constexpr int NC = 1 << D;
     constexpr int KP = (F == 1) ? kPts : ((F == 2) ? 2 : 1);  // keeps the in-flight rows within ~16 registers
-    int* s_acc = reinterpret_cast<int*>(s_dyn);                           // [cap_acc][C] fixed-point node sums
-    float* s_lat = s_dyn + (size_t)cap_acc * C;                           // [cap][C] staged latents (DEC)
+    int* s_acc = reinterpret_cast<int*>(s_dyn);                           // [cap_acc][CA] fixed-point node sums
+    float* s_lat = s_dyn + (size_t)cap_acc * CA;                          // [cap][C] staged latents (DEC)
     float* s_A = s_lat + (DEC ? (size_t)cap * C : 0);                     // [nA][C][F]
-    float* s_gA = s_A + nA * C * F;                                       // [NW][L][C][F] per-warp partial sums
-    float* s_gS = s_gA + (DEC ? NW * L * C * F : 0);                      // [NW][L][F]
+    float* s_gA = s_A + nA * C * F;                                       // ZP: [NW][L][C][F]; SG: [L][C][F]
+    float* s_gS = s_gA + (ZP ? NW : 1) * (DEC ? L * C * F : 0);           // ZP: [NW][L][F];    SG: [L][F]
     const int tile = blockIdx.x;
     const int beg = pv.tile_off[tile], end = pv.tile_off[tile + 1];
     if (beg == end) return;
@@ -563,49 +573,67 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
     }
     for (int e = threadIdx.x; e < nA * C * F; e += kTileThreads) s_A[e] = A[e];
     if (DEC)
-        for (int e = threadIdx.x; e < NW * L * (C * F + F); e += kTileThreads) s_gA[e] = 0.0f;
-    tile_geometry<D>(tg, lp, ti, pv.g, cap, cap_acc, kRepBudget / C);
-    if (DEC) stage_nodes<D, C>(tg, lp, latents, round_flag, s_lat);
+        for (int e = threadIdx.x; e < (ZP ? NW : 1) * L * (C * F + F); e += kTileThreads) s_gA[e] = 0.0f;
+    tile_geometry<D>(tg, lp, ti, pv.g, cap, cap_acc, cap_acc - cap);
+    if (DEC) stage_nodes<D, C>(tg, lp, latents, round_flag, s_lat);  // ZP: per-point z; SG: q[node] at flush
 
     for (int b0 = beg; b0 < end; b0 += kBatch) {
         const int b1 = min(end, b0 + kBatch);
         int kbits = 0;
         while ((1 << kbits) < (b1 - b0)) ++kbits;
-        for (int e = threadIdx.x; e < tg.acc_total * C; e += kTileThreads) s_acc[e] = 0;
+        for (int e = threadIdx.x; e < tg.acc_total * CA; e += kTileThreads) s_acc[e] = 0;
         if (threadIdx.x < SHACIRA_MAX_LEVELS) s_gmax[threadIdx.x] = 0u;
         __syncthreads();
-        // pass 1: per-level maxima of what will be accumulated. Level chunk outer, points inner: the running
-        // maxima of the chunk's 4 levels stay in registers; one REDUX + shared atomicMax per warp and level.
-        for (int l0 = 0; l0 < L; l0 += 4) {
-            float m[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            for (int base = b0; base < b1; base += kTileThreads * KP) {
-                float g[KP][4 * F];
+        // pass 1: per-level maxima of what will be accumulated (they fix the fixed-point scales).
+        // Points outer, whole gradient row (all levels) in flight per point: one round trip to memory per
+        // group of KP1 points instead of one per level chunk. Per-level running maxima live in shared memory
+        // (REDUX over the warp, then one shared atomicMax per warp, level and group).
+        {
+            constexpr int KP1 = (F == 1) ? 2 : 1;
+            for (int base = b0; base < b1; base += kTileThreads * KP1) {
+                const float* rows[KP1];
 #pragma unroll
-                for (int k = 0; k < KP; ++k) {
+                for (int k = 0; k < KP1; ++k) {
                     const int j = base + k * kTileThreads + threadIdx.x;
-#pragma unroll
-                    for (int e = 0; e < 4 * F; ++e) g[k][e] = 0.0f;
-                    if (j < b1) load_row<4 * F>(grad_out + (int64_t)__ldg(pv.perm + j) * L * F + l0 * F, g[k]);
+                    rows[k] = (j < b1) ? grad_out + (int64_t)__ldg(pv.perm + j) * L * F : nullptr;
                 }
+                for (int l0 = 0; l0 < L; l0 += 8) {  // 8 levels = two 16-byte vectors per point in flight
+                    float g[KP1][2][4 * F];
 #pragma unroll
-                for (int k = 0; k < KP; ++k) {
+                    for (int k = 0; k < KP1; ++k)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int la = per_level ? (l0 + q) : 0;
+                        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                        for (int ch = 0; ch < C; ++ch) {
-                            float acc = 0.0f;
-#pragma unroll
-                            for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[k][q * F + jf], s_A[(la * C + ch) * F + jf], acc);
-                            m[q] = fmaxf(m[q], fabsf(acc));
+                            for (int e = 0; e < 4 * F; ++e) g[k][h][e] = 0.0f;
+                            if (rows[k] && l0 + 4 * h < L) load_row<4 * F>(rows[k] + (l0 + 4 * h) * F, g[k][h]);
                         }
-                    }
-                }
-            }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m[q]));
-                if (lane == 0 && wm) atomicMax(&s_gmax[l0 + q], wm);
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int l = l0 + 4 * h + q;
+                            float m = 0.0f;
+#pragma unroll
+                            for (int k = 0; k < KP1; ++k) {
+                                if (SG) {
+#pragma unroll
+                                    for (int jf = 0; jf < F; ++jf) m = fmaxf(m, fabsf(g[k][h][q * F + jf]));
+                                } else {
+                                    const int la = per_level ? min(l, L - 1) : 0;
+#pragma unroll
+                                    for (int ch = 0; ch < C; ++ch) {
+                                        float acc = 0.0f;
+#pragma unroll
+                                        for (int jf = 0; jf < F; ++jf)
+                                            acc = __fmaf_rn(g[k][h][q * F + jf], s_A[(la * C + ch) * F + jf], acc);
+                                        m = fmaxf(m, fabsf(acc));
+                                    }
+                                }
+                            }
+                            const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+                            if (lane == 0 && wm && l < L) atomicMax(&s_gmax[l], wm);
+                        }
+                }
             }
         }
         __syncthreads();
@@ -615,25 +643,26 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
             s_inv[threadIdx.x] = inv;
         }
         __syncthreads();
-        // pass 2: accumulate. Decoder-gradient partial sums of the chunk's levels stay in registers (plain
-        // float per thread) across the points loop and are reduced over the warp once per chunk.
+        // pass 2: accumulate
         for (int l0 = 0; l0 < L; l0 += 4) {
-            float accS[DEC ? 4 * F : 1], accA[DEC ? 4 * C * F : 1];
-            if (DEC) {
+            float accS[ZP ? 4 * F : 1], accA[ZP ? 4 * C * F : 1];
+            if (ZP) {
 #pragma unroll
                 for (int e = 0; e < 4 * F; ++e) accS[e] = 0.0f;
 #pragma unroll
                 for (int e = 0; e < 4 * C * F; ++e) accA[e] = 0.0f;
             }
             LevelRegs lr[4];
-            float scq[4], Am[4][C * F];
+            float scq[4], Am[4][SG ? 1 : C * F];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 load_level_regs<D>(lp, tg, l0 + q, lr[q]);
                 scq[q] = s_scale[l0 + q];
-                const int la = per_level ? (l0 + q) : 0;
+                if (!SG) {
+                    const int la = per_level ? (l0 + q) : 0;
 #pragma unroll
-                for (int e = 0; e < C * F; ++e) Am[q][e] = s_A[la * C * F + e];
+                    for (int e = 0; e < C * F; ++e) Am[q][e] = s_A[la * C * F + e];
+                }
             }
             for (int base = b0; base < b1; base += kTileThreads * KP) {
                 float gk[KP][4 * F];
@@ -660,42 +689,62 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int l = l0 + q;
-                        float gz[C], z[C];
+                        float gz[CA], z[C];
 #pragma unroll
-                        for (int ch = 0; ch < C; ++ch) {
-                            float acc = 0.0f;
+                        for (int ch = 0; ch < C; ++ch) z[ch] = 0.0f;
+                        if (SG) {
 #pragma unroll
-                            for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[q * F + jf], Am[q][ch * F + jf], acc);
-                            gz[ch] = acc;
-                            z[ch] = 0.0f;
+                            for (int jf = 0; jf < F; ++jf) gz[jf] = g[q * F + jf];
+                        } else {
+#pragma unroll
+                            for (int ch = 0; ch < C; ++ch) {
+                                float acc = 0.0f;
+#pragma unroll
+                                for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[q * F + jf], Am[q][ch * F + jf], acc);
+                                gz[ch] = acc;
+                            }
                         }
                         if (lr[q].staged) {
                             Stencil<D> st;
                             stencil<D>(t, lr[q], st);
                             const float sc = scq[q];
 #pragma unroll
-                            for (int ch = 0; ch < C; ++ch) {
+                            for (int ch = 0; ch < CA; ++ch) {
                                 const float gs = __fmul_rn(gz[ch], sc);  // power-of-two scale: exact
 #pragma unroll
                                 for (int kk = 0; kk < NC; ++kk)
-                                    atomicAdd(&s_acc[(size_t)((st.slot[kk] + lr[q].accd) * lr[q].amul + lr[q].alane) * C + ch],
+                                    atomicAdd(&s_acc[(size_t)((st.slot[kk] + lr[q].accd) * lr[q].amul + lr[q].alane) * CA + ch],
                                               __float2int_rn(__fmul_rn(gs, st.w[kk])));
                             }
-                            if (DEC) {
+                            if (ZP) {
                                 float v[NC][C];
 #pragma unroll
                                 for (int kk = 0; kk < NC; ++kk) lds_row<C>(s_lat + (size_t)st.slot[kk] * C, v[kk]);
                                 lerp_rows<NC, C>(v, st.w, z);
                             }
-                        } else {  // direct level: float REDG to global, gathers for z
+                        } else {  // direct level: float REDG to global (and, for the decoder, gathers for z)
                             Corners<D> c;
                             corners<D>(t, lp, l, c);
+                            float gl[C];
+                            if (SG) {
+                                const int la = per_level ? l : 0;
+#pragma unroll
+                                for (int ch = 0; ch < C; ++ch) {
+                                    float acc = 0.0f;
+#pragma unroll
+                                    for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[q * F + jf], s_A[(la * C + ch) * F + jf], acc);
+                                    gl[ch] = acc;
+                                }
+                            } else {
+#pragma unroll
+                                for (int ch = 0; ch < C; ++ch) gl[ch] = gz[ch];
+                            }
                             float* gbase = grad_latents + (int64_t)lp.first[l] * C;
 #pragma unroll
                             for (int kk = 0; kk < NC; ++kk) {
                                 float gv[C];
 #pragma unroll
-                                for (int ch = 0; ch < C; ++ch) gv[ch] = __fmul_rn(gz[ch], c.w[kk]);
+                                for (int ch = 0; ch < C; ++ch) gv[ch] = __fmul_rn(gl[ch], c.w[kk]);
                                 red_add_row<C>(gbase + (int64_t)c.idx[kk] * C, gv);
                             }
                             if (DEC) {
@@ -710,9 +759,17 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                                     }
                                 }
                                 lerp_rows<NC, C>(v, c.w, z);
+                                if (SG) {  // direct levels are rare on this path: warp-reduce per point
+#pragma unroll
+                                    for (int jf = 0; jf < F; ++jf) {
+                                        atomicAdd(&s_gS[l * F + jf], g[q * F + jf]);
+#pragma unroll
+                                        for (int ch = 0; ch < C; ++ch) atomicAdd(&s_gA[(l * C + ch) * F + jf], z[ch] * g[q * F + jf]);
+                                    }
+                                }
                             }
                         }
-                        if (DEC) {
+                        if (ZP) {
 #pragma unroll
                             for (int jf = 0; jf < F; ++jf) {
                                 accS[q * F + jf] += g[q * F + jf];
@@ -724,7 +781,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                     }
                 }
             }
-            if (DEC) {
+            if (ZP) {
 #pragma unroll
                 for (int e = 0; e < 4 * F; ++e) {
                     const float v = warp_sum(accS[e]);
@@ -738,60 +795,104 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
             }
         }
         __syncthreads();
-        // flush: one float REDG per touched node
+        // flush: one float REDG per touched node (+ the per-node decoder gradients in scatter-g mode)
+        // scatter-g decoder partial sums: per level for per-level decoders; for one shared decoder the levels
+        // are summed anyway (the caller adds grad_A over levels), so they ride in level slot `dl` = 0 and are
+        // reduced over the warp once per tile instead of once per level
+        float pS[SG ? F : 1], pA[SG ? C * F : 1];
+#pragma unroll
+        for (int e = 0; e < (SG ? F : 1); ++e) pS[e] = 0.0f;
+#pragma unroll
+        for (int e = 0; e < (SG ? C * F : 1); ++e) pA[e] = 0.0f;
+        int last_staged = -1;
+        for (int l = 0; l < L; ++l)
+            if ((tg.staged >> l) & 1u) last_staged = l;
         for (int l = 0; l < L; ++l) {
             if (!((tg.staged >> l) & 1u)) continue;
             int n_l = 1;
 #pragma unroll
             for (int d = 0; d < D; ++d) n_l *= tg.w[l][d];
             const float inv = s_inv[l];
+            const int la = per_level ? l : 0;
             float* base = grad_latents + (int64_t)lp.first[l] * C;
-            if (tg.acc_mul[l] == 32) {
-                // lane-replicated level: a warp sums the 32 copies of a node with REDUX (exact integers)
-                for (int e = warp; e < n_l; e += NW) {
-                    bool any = false;
-                    float gv[C];
+            const bool rep = tg.acc_mul[l] == 32;
+            if (SG && per_level) {
 #pragma unroll
-                    for (int ch = 0; ch < C; ++ch) {
-                        const int qv = __reduce_add_sync(0xffffffffu, s_acc[(size_t)(tg.acc_off[l] + e * 32 + lane) * C + ch]);
-                        any |= (qv != 0);
-                        gv[ch] = (float)qv * inv;
+                for (int e = 0; e < F; ++e) pS[e] = 0.0f;
+#pragma unroll
+                for (int e = 0; e < C * F; ++e) pA[e] = 0.0f;
+            }
+            // one thread per node. Lane-replicated level: the thread sums its node's 32 copies, starting at
+            // its own lane so that the 32 lanes of a warp read 32 different banks (exact integer sums).
+            for (int e = threadIdx.x; e < n_l; e += kTileThreads) {
+                bool any = false;
+                float gv[CA];
+#pragma unroll
+                for (int ch = 0; ch < CA; ++ch) {
+                    int qv = 0;
+                    if (rep) {
+#pragma unroll 8
+                        for (int jj = 0; jj < 32; ++jj)
+                            qv += s_acc[(size_t)(tg.acc_off[l] + e * 32 + ((lane + jj) & 31)) * CA + ch];
+                    } else {
+                        qv = s_acc[(size_t)(tg.acc_off[l] + e) * CA + ch];
                     }
-                    if (any && lane == 0) {
-                        const int row = node_row<D>(tg, lp, l, e, false);
-                        if (row >= 0) red_add_row<C>(base + (int64_t)row * C, gv);
+                    any |= (qv != 0);
+                    gv[ch] = (float)qv * inv;
+                }
+                if (any) {
+                    const int row = node_row<D>(tg, lp, l, e, false);
+                    if (row >= 0) {
+                        if constexpr (SG) {
+                            float qn[C], gl[C];
+                            lds_row<C>(s_lat + (size_t)(tg.off[l] + e) * C, qn);  // staged (already rounded)
+#pragma unroll
+                            for (int ch = 0; ch < C; ++ch) {
+                                float acc = 0.0f;
+#pragma unroll
+                                for (int jf = 0; jf < F; ++jf) {
+                                    acc = __fmaf_rn(gv[jf], s_A[(la * C + ch) * F + jf], acc);
+                                    pA[ch * F + jf] = __fmaf_rn(qn[ch], gv[jf], pA[ch * F + jf]);
+                                }
+                                gl[ch] = acc;
+                            }
+#pragma unroll
+                            for (int jf = 0; jf < F; ++jf) pS[jf] += gv[jf];
+                            red_add_row<C>(base + (int64_t)row * C, gl);
+                        } else {
+                            red_add_row<C>(base + (int64_t)row * C, gv);
+                        }
                     }
                 }
-            } else {
-                for (int e = threadIdx.x; e < n_l; e += kTileThreads) {
-                    bool any = false;
-                    float gv[C];
+            }
+            if (SG && (per_level || l == last_staged)) {
+                const int dl = per_level ? l : 0;
 #pragma unroll
-                    for (int ch = 0; ch < C; ++ch) {
-                        const int qv = s_acc[(size_t)(tg.acc_off[l] + e) * C + ch];
-                        any |= (qv != 0);
-                        gv[ch] = (float)qv * inv;
-                    }
-                    if (any) {
-                        const int row = node_row<D>(tg, lp, l, e, false);
-                        if (row >= 0) red_add_row<C>(base + (int64_t)row * C, gv);
-                    }
+                for (int e = 0; e < F; ++e) {
+                    const float v = warp_sum(pS[e]);
+                    if (lane == 0 && v != 0.0f) atomicAdd(&s_gS[dl * F + e], v);
+                }
+#pragma unroll
+                for (int e = 0; e < C * F; ++e) {
+                    const float v = warp_sum(pA[e]);
+                    if (lane == 0 && v != 0.0f) atomicAdd(&s_gA[dl * C * F + e], v);
                 }
             }
         }
         __syncthreads();
     }
     if (DEC) {
+        constexpr int NP = ZP ? NW : 1;
         for (int e = threadIdx.x; e < L * C * F; e += kTileThreads) {
             float s = 0.0f;
 #pragma unroll
-            for (int wq = 0; wq < NW; ++wq) s += s_gA[wq * L * C * F + e];
+            for (int wq = 0; wq < NP; ++wq) s += s_gA[wq * L * C * F + e];
             if (grad_A && s != 0.0f) red_add(grad_A + e, s);
         }
         for (int e = threadIdx.x; e < L * F; e += kTileThreads) {
             float s = 0.0f;
 #pragma unroll
-            for (int wq = 0; wq < NW; ++wq) s += s_gS[wq * L * F + e];
+            for (int wq = 0; wq < NP; ++wq) s += s_gS[wq * L * F + e];
             if (grad_shift && s != 0.0f) red_add(grad_shift + e, s);
         }
     }

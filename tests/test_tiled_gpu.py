@@ -57,6 +57,16 @@ def _oracle_fwd_bwd(c, round_flag=True):
     return feats, gl, gA, gS
 
 
+def _check_decoder_grads(c, gA, gS, want_gA, want_gS):
+    """Per-level decoders: every level's gradient. One shared decoder: only the sum over levels is defined
+    (include/shacira_b200.h) -- the tiled kernel reports it in level slot 0."""
+    gA, gS = gA.cpu().numpy().astype(np.float64), gS.cpu().numpy().astype(np.float64)
+    if c["nA"] == 1:
+        gA, gS, want_gA, want_gS = gA.sum(0), gS.sum(0), want_gA.sum(0), want_gS.sum(0)
+    assert rel_err(gA, want_gA) <= BWD_TOL
+    assert rel_err(gS, want_gS) <= BWD_TOL
+
+
 TILED_CASES = [
     # dim, L, bw, rmin, rmax, n, C, F, per_level, kind
     (2, 16, 16, 16, 512, 768 * 512, 1, 1, False, "pixels"),   # BASELINE cfg2 (full size)
@@ -85,8 +95,7 @@ def test_tiled_forward_backward(lib, dim, L, bw, rmin, rmax, n, C, F, per_level,
     assert rel_err(feats.cpu().numpy(), want_f) <= FWD_TOL
     gl, gA, gS = lib.latent_backward_planned(plan, g, lat, c["first"], c["res"], bw, A, C, F, c["T"], True, True)
     assert rel_err(gl.cpu().numpy(), want_gl) <= BWD_TOL
-    assert rel_err(gA.cpu().numpy(), want_gA) <= BWD_TOL
-    assert rel_err(gS.cpu().numpy(), want_gS) <= BWD_TOL
+    _check_decoder_grads(c, gA, gS, want_gA, want_gS)
     # without decoder gradients (frozen decoder): same latent gradient
     gl2, _, _ = lib.latent_backward_planned(plan, g, None, c["first"], c["res"], bw, A, C, F, c["T"], True, False)
     assert rel_err(gl2.cpu().numpy(), want_gl) <= BWD_TOL
@@ -123,7 +132,7 @@ def test_direct_level_fallback_matches(lib, monkeypatch):
         assert torch.equal(f, full)
         gl, gA, gS = lib.latent_backward_planned(plan, g, lat, c["first"], c["res"], 16, A, 1, 1, c["T"], True, True)
         assert rel_err(gl.cpu().numpy(), want_gl) <= BWD_TOL
-        assert rel_err(gA.cpu().numpy(), want_gA) <= BWD_TOL and rel_err(gS.cpu().numpy(), want_gS) <= BWD_TOL
+        _check_decoder_grads(c, gA, gS, want_gA, want_gS)
     plan.close()
 
 
