@@ -123,6 +123,10 @@ int shacira_latent_backward(int32_t dim, const float* coords, int64_t n, const f
 typedef struct shacira_plan shacira_plan_t;
 int shacira_plan_create(int32_t dim, const float* coords, int64_t n, int32_t tile_points, shacira_stream_t stream,
                         shacira_plan_t** plan);
+/* Re-bin `plan` for a new coordinate set, reusing its device allocation when large enough
+ * (workloads whose coordinates change every step, e.g. NeRF samples). */
+int shacira_plan_rebuild(shacira_plan_t* plan, int32_t dim, const float* coords, int64_t n, int32_t tile_points,
+                         shacira_stream_t stream);
 int shacira_plan_destroy(shacira_plan_t* plan);
 int shacira_plan_info(const shacira_plan_t* plan, int64_t* n, int32_t* dim, int32_t* tiles_per_axis,
                       int32_t* ntiles);

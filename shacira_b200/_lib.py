@@ -39,6 +39,7 @@ SIGNATURES = {
     "shacira_latent_forward": (ctypes.c_int, [_i32, _vp, _i64, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "shacira_latent_backward": (ctypes.c_int, [_i32, _vp, _i64, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "shacira_plan_create": (ctypes.c_int, [_i32, _vp, _i64, _i32, _vp, ctypes.POINTER(_vp)]),
+    "shacira_plan_rebuild": (ctypes.c_int, [_vp, _i32, _vp, _i64, _i32, _vp]),
     "shacira_plan_destroy": (ctypes.c_int, [_vp]),
     "shacira_plan_info": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), _c_int32_p, _c_int32_p, _c_int32_p]),
     "shacira_plan_debug": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),

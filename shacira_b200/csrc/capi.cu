@@ -378,6 +378,7 @@ int shacira_ac_decode(const uint8_t* in, int64_t nbytes, const uint32_t* cdf, in
 // ---- host-buffer step ------------------------------------------------------------------
 namespace {
 struct HostStepScratch {
+    shacira_plan_t* plan = nullptr;
     void* ptr = nullptr;
     size_t bytes = 0;
     cudaStream_t stream[2] = {nullptr, nullptr};
@@ -432,17 +433,35 @@ int shacira_latent_step_host(int32_t dim, const float* coords, int64_t n, const 
     CUDA_OK(cudaMemcpyAsync(d_A, A, sizeof(float) * nA * latent_dim * feature_dim, cudaMemcpyHostToDevice, s0));
     if (shift) CUDA_OK(cudaMemcpyAsync(d_shift, shift, sizeof(float) * nA * feature_dim, cudaMemcpyHostToDevice, s0));
     CUDA_OK(cudaMemcpyAsync(d_coords, coords, sizeof(float) * n * dim, cudaMemcpyHostToDevice, s0));
-    CUDA_OK(cudaEventRecord(sc.up_done, s0));
     CUDA_OK(cudaMemcpyAsync(d_gout, grad_output, sizeof(float) * n * LF, cudaMemcpyHostToDevice, s1));
-    int rc = shacira_latent_forward(dim, d_coords, n, d_lat, first_idx, resolutions, num_lods, codebook_bitwidth,
+    // the coordinates are new to the device every call: bin them (3 small kernels, allocation reused),
+    // then run the tiled kernels; configurations the tiled path does not cover use the point-parallel ones
+    const bool tiled = (num_lods % 4 == 0) && n >= 16384;
+    int rc = SHACIRA_OK;
+    if (tiled) {
+        rc = sc.plan ? shacira_plan_rebuild(sc.plan, dim, d_coords, n, 0, s0)
+                     : shacira_plan_create(dim, d_coords, n, 0, s0, &sc.plan);
+        if (rc) return rc;
+        rc = shacira_latent_forward_planned(sc.plan, d_lat, first_idx, resolutions, num_lods, codebook_bitwidth,
+                                            latent_dim, feature_dim, round_flag, d_A, shift ? d_shift : nullptr,
+                                            per_level, d_feats, s0);
+    } else {
+        rc = shacira_latent_forward(dim, d_coords, n, d_lat, first_idx, resolutions, num_lods, codebook_bitwidth,
                                     latent_dim, feature_dim, round_flag, d_A, shift ? d_shift : nullptr, per_level,
                                     d_feats, nullptr, s0);
+    }
     if (rc) return rc;
+    CUDA_OK(cudaEventRecord(sc.up_done, s0));  // plan + forward inputs resident
     CUDA_OK(cudaMemcpyAsync(feats, d_feats, sizeof(float) * n * LF, cudaMemcpyDeviceToHost, s0));
     CUDA_OK(cudaStreamWaitEvent(s1, sc.up_done, 0));
-    rc = shacira_latent_backward(dim, d_coords, n, d_gout, nullptr, first_idx, resolutions, num_lods,
-                                 codebook_bitwidth, latent_dim, feature_dim, d_A, per_level, table_rows, 1, d_glat,
-                                 nullptr, nullptr, s1);
+    if (tiled)
+        rc = shacira_latent_backward_planned(sc.plan, d_gout, nullptr, first_idx, resolutions, num_lods,
+                                             codebook_bitwidth, latent_dim, feature_dim, round_flag, d_A, per_level,
+                                             table_rows, 1, d_glat, nullptr, nullptr, s1);
+    else
+        rc = shacira_latent_backward(dim, d_coords, n, d_gout, nullptr, first_idx, resolutions, num_lods,
+                                     codebook_bitwidth, latent_dim, feature_dim, d_A, per_level, table_rows, 1, d_glat,
+                                     nullptr, nullptr, s1);
     if (rc) return rc;
     CUDA_OK(cudaMemcpyAsync(grad_latents, d_glat, sizeof(float) * table_rows * latent_dim, cudaMemcpyDeviceToHost, s1));
     CUDA_OK(cudaStreamSynchronize(s0));

@@ -14,6 +14,7 @@ struct shacira_plan {
     int32_t ntiles;
     int device;
     void* block;     // one allocation: perm | coords_sorted | tile_off | cursor | counts | tile_id
+    size_t block_bytes;
     int32_t* perm;
     float* coords_sorted;
     int32_t* tile_off;
@@ -111,52 +112,49 @@ int launch_bwd(const shacira_plan* p, const float* g, const float* lat, const Le
 
 }  // namespace
 
-extern "C" {
+namespace {
 
-int shacira_plan_create(int32_t dim, const float* coords, int64_t n, int32_t tile_points, shacira_stream_t stream,
-                        shacira_plan_t** out) {
-    if (!out) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan output pointer is NULL");
-    *out = nullptr;
-    if (dim != 2 && dim != 3) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "dim must be 2 or 3, got %d", dim);
-    if (n <= 0 || !coords) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan needs n > 0 points");
-    if (n > 0x7fffffff) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan supports up to 2^31-1 points");
+int choose_tiles_per_axis(int dim, int64_t n, int tile_points) {
     if (tile_points <= 0) {
         const char* env = getenv("SHACIRA_TILE_POINTS");
         tile_points = env ? atoi(env) : 384;
         if (tile_points <= 0) tile_points = 384;
     }
-    // tiles per axis: power of two, about tile_points points per tile, at most kMaxTiles tiles
+    // power of two per axis, about tile_points points per tile, at most kMaxTiles tiles
     int g = 1;
     for (;;) {
-        long long tiles = 1;
-        for (int d = 0; d < dim; ++d) tiles *= 2LL * g;
+        long long tiles = 1, cur = 1;
+        for (int d = 0; d < dim; ++d) { tiles *= 2LL * g; cur *= g; }
         if (tiles > kMaxTiles) break;
         // stop when doubling would drop below ~tile_points/2 points per tile
-        long long cur = 1;
-        for (int d = 0; d < dim; ++d) cur *= g;
         if ((double)n / (double)cur <= (double)tile_points * (dim == 2 ? 2.0 : 2.83)) break;
         g *= 2;
     }
+    return g;
+}
+
+size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// (Re)build the plan's arrays for `coords` on `stream`; the allocation is reused when it is large enough.
+int plan_build(shacira_plan* p, int32_t dim, const float* coords, int64_t n, int32_t tile_points, cudaStream_t s) {
+    const int g = choose_tiles_per_axis(dim, n, tile_points);
     int ntiles = 1;
     for (int d = 0; d < dim; ++d) ntiles *= g;
-
-    shacira_plan* p = new (std::nothrow) shacira_plan();
-    if (!p) return fail(SHACIRA_ERR_CUDA, "out of host memory");
+    const size_t b_perm = align256(4 * (size_t)n), b_coords = align256(4 * (size_t)n * dim);
+    const size_t b_off = align256(4 * (size_t)(ntiles + 1)), b_cnt = align256(4 * (size_t)ntiles), b_tid = align256(4 * (size_t)n);
+    const size_t total = b_perm + b_coords + b_off + 2 * b_cnt + b_tid;
+    if (!p->block || p->block_bytes < total) {
+        if (p->block) cudaFree(p->block);
+        p->block = nullptr;
+        p->block_bytes = 0;
+        cudaError_t e = cudaMalloc(&p->block, total);
+        if (e != cudaSuccess) return fail(SHACIRA_ERR_CUDA, "cudaMalloc(%zu) for the plan: %s", total, cudaGetErrorString(e));
+        p->block_bytes = total;
+    }
     p->dim = dim;
     p->n = n;
     p->g = g;
     p->ntiles = ntiles;
-    p->block = nullptr;
-    cudaGetDevice(&p->device);
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t b_perm = al(4 * (size_t)n), b_coords = al(4 * (size_t)n * dim), b_off = al(4 * (size_t)(ntiles + 1));
-    const size_t b_cnt = al(4 * (size_t)ntiles), b_tid = al(4 * (size_t)n);
-    const size_t total = b_perm + b_coords + b_off + 2 * b_cnt + b_tid;
-    cudaError_t e = cudaMalloc(&p->block, total);
-    if (e != cudaSuccess) {
-        delete p;
-        return fail(SHACIRA_ERR_CUDA, "cudaMalloc(%zu) for the plan: %s", total, cudaGetErrorString(e));
-    }
     char* q = (char*)p->block;
     p->perm = (int32_t*)q; q += b_perm;
     p->coords_sorted = (float*)q; q += b_coords;
@@ -164,31 +162,59 @@ int shacira_plan_create(int32_t dim, const float* coords, int64_t n, int32_t til
     int32_t* cursor = (int32_t*)q; q += b_cnt;
     int32_t* counts = (int32_t*)q; q += b_cnt;
     int32_t* tile_id = (int32_t*)q;
-    cudaStream_t s = (cudaStream_t)stream;
-    int rc = SHACIRA_OK;
-    auto body = [&]() -> int {
-        CUDA_OK(cudaMemsetAsync(counts, 0, 4 * (size_t)ntiles, s));
-        const size_t hist = 4 * (size_t)ntiles;
-        int blocks = (int)((n + 1023) / 1024);
-        const int count_blocks = blocks < 296 ? blocks : 296;
-        if (dim == 2) plan_count_kernel<2><<<count_blocks, 1024, hist, s>>>(coords, n, g, ntiles, tile_id, counts);
-        else plan_count_kernel<3><<<count_blocks, 1024, hist, s>>>(coords, n, g, ntiles, tile_id, counts);
-        LAUNCHED();
-        plan_scan_kernel<<<1, 1024, 0, s>>>(counts, ntiles, p->tile_off, cursor);
-        LAUNCHED();
-        if (dim == 2) plan_scatter_kernel<2><<<blocks, 1024, hist, s>>>(coords, n, ntiles, tile_id, cursor, p->perm, p->coords_sorted);
-        else plan_scatter_kernel<3><<<blocks, 1024, hist, s>>>(coords, n, ntiles, tile_id, cursor, p->perm, p->coords_sorted);
-        LAUNCHED();
-        return SHACIRA_OK;
-    };
-    rc = body();
+    CUDA_OK(cudaMemsetAsync(counts, 0, 4 * (size_t)ntiles, s));
+    const size_t hist = 4 * (size_t)ntiles;
+    const int blocks = (int)((n + 1023) / 1024);
+    const int count_blocks = blocks < 296 ? blocks : 296;
+    if (dim == 2) plan_count_kernel<2><<<count_blocks, 1024, hist, s>>>(coords, n, g, ntiles, tile_id, counts);
+    else plan_count_kernel<3><<<count_blocks, 1024, hist, s>>>(coords, n, g, ntiles, tile_id, counts);
+    LAUNCHED();
+    plan_scan_kernel<<<1, 1024, 0, s>>>(counts, ntiles, p->tile_off, cursor);
+    LAUNCHED();
+    if (dim == 2) plan_scatter_kernel<2><<<blocks, 1024, hist, s>>>(coords, n, ntiles, tile_id, cursor, p->perm, p->coords_sorted);
+    else plan_scatter_kernel<3><<<blocks, 1024, hist, s>>>(coords, n, ntiles, tile_id, cursor, p->perm, p->coords_sorted);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
+int check_plan_args(int32_t dim, const float* coords, int64_t n) {
+    if (dim != 2 && dim != 3) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "dim must be 2 or 3, got %d", dim);
+    if (n <= 0 || !coords) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan needs n > 0 points");
+    if (n > 0x7fffffff) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan supports up to 2^31-1 points");
+    return SHACIRA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int shacira_plan_create(int32_t dim, const float* coords, int64_t n, int32_t tile_points, shacira_stream_t stream,
+                        shacira_plan_t** out) {
+    if (!out) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan output pointer is NULL");
+    *out = nullptr;
+    int rc = check_plan_args(dim, coords, n);
+    if (rc) return rc;
+    shacira_plan* p = new (std::nothrow) shacira_plan();
+    if (!p) return fail(SHACIRA_ERR_CUDA, "out of host memory");
+    p->block = nullptr;
+    p->block_bytes = 0;
+    cudaGetDevice(&p->device);
+    rc = plan_build(p, dim, coords, n, tile_points, (cudaStream_t)stream);
     if (rc != SHACIRA_OK) {
-        cudaFree(p->block);
+        if (p->block) cudaFree(p->block);
         delete p;
         return rc;
     }
     *out = p;
     return SHACIRA_OK;
+}
+
+int shacira_plan_rebuild(shacira_plan_t* plan, int32_t dim, const float* coords, int64_t n, int32_t tile_points,
+                         shacira_stream_t stream) {
+    if (!plan) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan is NULL");
+    int rc = check_plan_args(dim, coords, n);
+    if (rc) return rc;
+    return plan_build(plan, dim, coords, n, tile_points, (cudaStream_t)stream);
 }
 
 int shacira_plan_destroy(shacira_plan_t* plan) {
