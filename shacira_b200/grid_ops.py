@@ -33,6 +33,10 @@ def plan_for(coords):
     """Tile plan for `coords` ([N, 2|3] float32 contiguous CUDA) or None when planning is disabled / not worth it."""
     if os.environ.get("SHACIRA_DISABLE_PLAN") or coords.shape[0] < PLAN_MIN_POINTS:
         return None
+    if coords.shape[1] == 3 and not os.environ.get("SHACIRA_PLAN_3D"):
+        # measured (benchmarks/sweep.py, cfg4 shape): most 3D levels do not fit a tile's shared-memory box and
+        # the point-parallel kernels are faster there today
+        return None
     key = (coords.data_ptr(), coords._version, tuple(coords.shape), coords.device.index)
     plan = _plans.get(key)
     if plan is not None:
