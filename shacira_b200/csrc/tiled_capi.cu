@@ -32,6 +32,13 @@ int smem_budget() {
     return b;
 }
 
+// experiment knob: pad the dynamic shared memory so that fewer CTAs are resident per SM
+size_t smem_pad(size_t smem) {
+    const char* env = getenv("SHACIRA_TILE_SMEM_TOTAL");
+    const size_t want = env ? (size_t)atoi(env) : 0;
+    return (want > smem && want <= 48 * 1024) ? want : smem;
+}
+
 PlanView view_of(const shacira_plan* p) {
     PlanView v;
     v.perm = p->perm;
@@ -60,7 +67,7 @@ int launch_fwd(const shacira_plan* p, const float* lat, const LevelParams& lp, c
                int per_level, int round_flag, float* feats, cudaStream_t s) {
     const int nA = per_level ? lp.num_lods : 1;
     const int cap = node_capacity(p, lp, smem_budget() / (4 * C));
-    const size_t smem = sizeof(float) * ((size_t)cap * C + nA * C * F + nA * F);
+    const size_t smem = smem_pad(sizeof(float) * ((size_t)cap * C + nA * C * F + nA * F));
     latent_fwd_tiled_kernel<D, C, F><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), lat, lp, A, shift, per_level,
                                                                             round_flag, feats, cap);
     LAUNCHED();
@@ -84,6 +91,7 @@ int launch_bwd(const shacira_plan* p, const float* g, const float* lat, const Le
     constexpr int NW = kTileThreads / 32;
     size_t smem = sizeof(float) * ((size_t)cap_acc * CA + (dec ? (size_t)cap * C : 0) + nA * C * F);
     if (dec) smem += sizeof(float) * (size_t)(zp ? NW : 1) * lp.num_lods * (C * F + F);
+    smem = smem_pad(smem);
     if (dec)
         latent_bwd_tiled_kernel<D, C, F, true><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), g, lat, lp, A, per_level,
                                                                                       round_flag, gl, gA, gS, cap, cap_acc);

@@ -28,7 +28,10 @@ namespace shacira {
 #endif
 constexpr int kTileThreads = SHACIRA_TILE_THREADS;
 constexpr int kMaxTiles = 4096;
-constexpr int kPts = 4;      // points per thread whose loads are issued together (memory-level parallelism)
+#ifndef SHACIRA_KPTS
+#define SHACIRA_KPTS 2
+#endif
+constexpr int kPts = SHACIRA_KPTS;  // points per thread whose loads are issued together (memory-level parallelism)
 constexpr int kBatch = 2048;  // points accumulated between two flushes of a tile (bounds the fixed-point sums)
 
 struct PlanView {
@@ -148,7 +151,10 @@ struct TileGeom {
     int acc_mul[SHACIRA_MAX_LEVELS]; // 32 (lane-replicated) or 1
     int acc_total;
 };
-constexpr int kRepBudget = 4096;     // ints of lane-replicated accumulators per tile (all channels together)
+#ifndef SHACIRA_REP_BUDGET
+#define SHACIRA_REP_BUDGET 2048
+#endif
+constexpr int kRepBudget = SHACIRA_REP_BUDGET;  // ints of lane-replicated accumulators per tile (all channels together)
 
 // Cells reachable by points of the tile's axis interval [ti/g, (ti+1)/g]: locate() is monotone in t.
 // Warp 0 computes everything: lane l owns level l; the slot offsets are a warp prefix sum. Levels are
@@ -409,6 +415,13 @@ __device__ __forceinline__ int level_of_slot(const TileGeom<D>& tg, int num_stag
 // loop is flat over all levels and unrolled so that each thread has kStageUnroll independent gathers
 // in flight (a per-level loop would serialise one global-load latency per level).
 constexpr int kStageUnroll = 4;
+#ifndef SHACIRA_MIN_CTAS
+#define SHACIRA_MIN_CTAS 7
+#endif
+#ifndef SHACIRA_LV
+#define SHACIRA_LV 4
+#endif
+constexpr int kLv = SHACIRA_LV;  // levels per inner iteration (register blocking of the level loop): 4 or 2
 template <int D, int C>
 __device__ __forceinline__ void stage_nodes(const TileGeom<D>& tg, const LevelParams& lp,
                                             const float* __restrict__ latents, int round_flag, float* s_nodes) {
@@ -440,7 +453,7 @@ __device__ __forceinline__ void stage_nodes(const TileGeom<D>& tg, const LevelPa
 // forward: 4 levels per iteration, outputs written as 16-byte vectors (needs num_lods % 4 == 0)
 // ---------------------------------------------------------------------------------------------
 template <int D, int C, int F>
-__global__ void __launch_bounds__(kTileThreads, (C * F <= 4) ? 7 : 3)
+__global__ void __launch_bounds__(kTileThreads, (C * F <= 4) ? SHACIRA_MIN_CTAS : 3)
 latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, const __grid_constant__ LevelParams lp,
                         const float* __restrict__ A, const float* __restrict__ shift, int per_level, int round_flag,
                         float* __restrict__ feats, int cap) {
@@ -481,11 +494,11 @@ latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, co
                 load_unit_coords<D>(pv.coords_sorted, j, t[k]);
             }
         }
-        for (int l0 = 0; l0 < L; l0 += 4) {
-            LevelRegs lr[4];
-            float sh[4][F], Am[4][C * F];
+        for (int l0 = 0; l0 < L; l0 += kLv) {
+            LevelRegs lr[kLv];
+            float sh[kLv][F], Am[kLv][C * F];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < kLv; ++q) {
                 load_level_regs<D>(lp, tg, l0 + q, lr[q]);
                 const int la = per_level ? (l0 + q) : 0;
 #pragma unroll
@@ -496,9 +509,9 @@ latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, co
 #pragma unroll
             for (int k = 0; k < kPts; ++k) {
                 if (orig[k] < 0) continue;
-                float o[4 * F];
+                float o[kLv * F];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < kLv; ++q) {
                     float z[C];
                     interp_level<D, C>(t[k], lp, lr[q], l0 + q, s_nodes, latents, round_flag, z);
 #pragma unroll
@@ -509,7 +522,7 @@ latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, co
                         o[q * F + jf] = acc;
                     }
                 }
-                store_row<4 * F>(feats + (int64_t)orig[k] * L * F + l0 * F, o);
+                store_row<kLv * F>(feats + (int64_t)orig[k] * L * F + l0 * F, o);
             }
         }
     }
@@ -539,7 +552,7 @@ __device__ __forceinline__ float fixed_scale(float m, int k, float& inv) {
 //       grad_latent[node] = A G[node];  grad_A += q[node] G[node]^T;  grad_shift += G[node]  (sum_k w_k = 1).
 //       That is ~2-3 nodes per point instead of 2^D * L corner visits per point.
 template <int D, int C, int F, bool DEC>
-__global__ void __launch_bounds__(kTileThreads, (C * F <= 4) ? 7 : 3)
+__global__ void __launch_bounds__(kTileThreads, (C * F <= 4) ? SHACIRA_MIN_CTAS : 3)
 latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, const float* __restrict__ latents,
                         const __grid_constant__ LevelParams lp, const float* __restrict__ A, int per_level,
                         int round_flag, float* __restrict__ grad_latents, float* __restrict__ grad_A,
@@ -644,18 +657,18 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
         }
         __syncthreads();
         // pass 2: accumulate
-        for (int l0 = 0; l0 < L; l0 += 4) {
-            float accS[ZP ? 4 * F : 1], accA[ZP ? 4 * C * F : 1];
+        for (int l0 = 0; l0 < L; l0 += kLv) {
+            float accS[ZP ? kLv * F : 1], accA[ZP ? kLv * C * F : 1];
             if (ZP) {
 #pragma unroll
-                for (int e = 0; e < 4 * F; ++e) accS[e] = 0.0f;
+                for (int e = 0; e < kLv * F; ++e) accS[e] = 0.0f;
 #pragma unroll
-                for (int e = 0; e < 4 * C * F; ++e) accA[e] = 0.0f;
+                for (int e = 0; e < kLv * C * F; ++e) accA[e] = 0.0f;
             }
-            LevelRegs lr[4];
-            float scq[4], Am[4][SG ? 1 : C * F];
+            LevelRegs lr[kLv];
+            float scq[kLv], Am[kLv][SG ? 1 : C * F];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < kLv; ++q) {
                 load_level_regs<D>(lp, tg, l0 + q, lr[q]);
                 scq[q] = s_scale[l0 + q];
                 if (!SG) {
@@ -665,7 +678,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                 }
             }
             for (int base = b0; base < b1; base += kTileThreads * KP) {
-                float gk[KP][4 * F];
+                float gk[KP][kLv * F];
                 double tk[KP][D];
                 bool livek[KP];
 #pragma unroll
@@ -673,11 +686,11 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                     const int j = base + k * kTileThreads + threadIdx.x;
                     livek[k] = j < b1;
 #pragma unroll
-                    for (int e = 0; e < 4 * F; ++e) gk[k][e] = 0.0f;
+                    for (int e = 0; e < kLv * F; ++e) gk[k][e] = 0.0f;
 #pragma unroll
                     for (int d = 0; d < D; ++d) tk[k][d] = 0.5;
                     if (livek[k]) {
-                        load_row<4 * F>(grad_out + (int64_t)__ldg(pv.perm + j) * L * F + l0 * F, gk[k]);
+                        load_row<kLv * F>(grad_out + (int64_t)__ldg(pv.perm + j) * L * F + l0 * F, gk[k]);
                         load_unit_coords<D>(pv.coords_sorted, j, tk[k]);
                     }
                 }
@@ -685,9 +698,9 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                 for (int k = 0; k < KP; ++k) {
                     if (!livek[k]) continue;
                     const double (&t)[D] = tk[k];
-                    const float (&g)[4 * F] = gk[k];
+                    const float (&g)[kLv * F] = gk[k];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < kLv; ++q) {
                         const int l = l0 + q;
                         float gz[CA], z[C];
 #pragma unroll
@@ -783,12 +796,12 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
             }
             if (ZP) {
 #pragma unroll
-                for (int e = 0; e < 4 * F; ++e) {
+                for (int e = 0; e < kLv * F; ++e) {
                     const float v = warp_sum(accS[e]);
                     if (lane == 0) s_gS[(warp * L + l0) * F + e] += v;   // [l0 + q][jf] is contiguous: e = q*F + jf
                 }
 #pragma unroll
-                for (int e = 0; e < 4 * C * F; ++e) {
+                for (int e = 0; e < kLv * C * F; ++e) {
                     const float v = warp_sum(accA[e]);
                     if (lane == 0) s_gA[(warp * L + l0) * C * F + e] += v;  // e = (q*C + ch)*F + jf
                 }
