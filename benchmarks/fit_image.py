@@ -1,0 +1,238 @@
+"""Kodak-shape image INR fit (BASELINE cfg2 / cfg3): end-to-end PSNR / bpp parity and fits/hour.
+
+The fit follows the reference's ImageTrainer (wisp/trainers/image_trainer.py:269-359):
+768x512 synthetic image, full-image steps on shuffled pixel-centre coordinates (y, x); 2D LatentGrid (16 levels
+16->512, 2^16 rows, C = F = 1, single affine decoder with shift, norm='max' at iterations 1,2,5,10), MLP
+16->16->16->3 ReLU, Adam groups {decoder lr 1e-3, grid lr 2e-2, latent_dec lr 1e-2 wd 1e-2, prob_model lr 1e-4
+wd 1e-2}, loss = mse + lambda(epoch) * bits / rows with lambda cosine 1e-3 -> 1e-4, num_prob_layers = 2, noise
+every step. SGA is OFF (it is RNG-bound; SURVEY 8d asks for SGA-off parity runs).
+
+  --impl ours   shacira_b200.grids.LatentGrid (fused + tiled kernels)
+  --impl ref    the reference path restated with ITS OWN CUDA kernels (oracle/_ref): table-side
+                round/decode in torch, repeat(1,2), one kernel launch per level, torch ent_loss  -- the checker
+  --graph       capture the whole training step (grid, MLP, loss, backward, Adam) in one CUDA graph
+  --images K    fit K images (seeds 0..K-1), sharded round-robin over the ranks (torchrun): fits/hour
+
+Prints one JSON line: PSNR (clamped, uint8-quantised like ops/image/metrics.py:39-57), bpp (entropy of the
+rounded latents + 32 bit per decoder/MLP parameter, image_trainer.py:162-168), ms/step, fits/hour
+(60 000-step fits, the reference's kodak.yaml budget).
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+H, W = 512, 768
+
+
+def synthetic_image(seed):
+    g = torch.Generator().manual_seed(seed)
+    ys, xs = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+    img = torch.zeros(H, W, 3)
+    for k in range(6):  # smooth multi-scale pattern + mild noise, in [0, 1]
+        fx, fy, ph = torch.rand(3, generator=g) * torch.tensor([6.0 + 6 * k, 6.0 + 6 * k, 6.28])
+        col = torch.rand(3, generator=g)
+        img += (torch.sin(2 * math.pi * (fx * xs + fy * ys) + ph)[..., None] * 0.5 + 0.5) * col / (k + 1)
+    img = img / img.amax()
+    img = (img + 0.02 * torch.randn(H, W, 3, generator=g)).clamp(0, 1)
+    return img
+
+
+def make_data(seed, dev):
+    img = synthetic_image(seed)
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    coords = torch.stack([(ys.reshape(-1) / H - 0.5) * 2, (xs.reshape(-1) / W - 0.5) * 2], 1).float()
+    perm = torch.randperm(H * W, generator=torch.Generator().manual_seed(seed))  # multi_image_dataset.py:156-158
+    return coords[perm].contiguous().to(dev), img.reshape(-1, 3)[perm].contiguous().to(dev)
+
+
+DEC = dict(ldecode_enabled=True, ldecode_type="single", use_sga=False, diff_sampling=True, use_shift=True,
+           ldecode_matrix="sq", latent_dim=1, norm="max", norm_every=10, ldec_std=0.1, decay_period=0.9, temperature=0.1)
+ENT = dict(num_prob_layers=2, entropy_reg=1e-3, entropy_reg_end=1e-4, entropy_reg_sched="cosine", noise_freq=1)
+
+
+class RefGrid(nn.Module):
+    """The reference's LatentGrid.interpolate / ent_loss restated around the reference's own kernels."""
+
+    def __init__(self, ours):
+        super().__init__()
+        from oracle import build_ref
+        self.ref = build_ref.load()
+        assert self.ref is not None, "oracle/_ref/wisp_ref_ops.so missing"
+        self.codebook = nn.Parameter(ours.codebook.detach().clone())
+        import copy
+        self.latent_dec = copy.deepcopy(ours.latent_dec)
+        self.prob_model = copy.deepcopy(ours.prob_model)
+        self.register_buffer("first_idx", ours.codebook_lod_first_idx.clone())   # device tensor, as the reference passes it
+        self.resolutions, self.bw = list(ours.resolutions), ours.codebook_bitwidth
+        ref, grid_self = self.ref, self
+        res, bw = self.resolutions, self.bw
+
+        class Fn(torch.autograd.Function):  # wisp/ops/grid.py:135-176
+            @staticmethod
+            def forward(ctx, coords, table):
+                ctx.save_for_backward(coords, table)
+                return ref.hashgrid_interpolate2d_cuda(coords, table, grid_self.first_idx, res, bw)
+
+            @staticmethod
+            def backward(ctx, g):
+                coords, table = ctx.saved_tensors
+                return None, ref.hashgrid_interpolate2d_backward_cuda(coords, g.contiguous(), table, grid_self.first_idx,
+                                                                      res, bw, table.shape[1], False)
+        self.fn = Fn
+
+    def interpolate(self, coords, lod_idx):
+        table = self.latent_dec(self.codebook).repeat(1, 2)       # latent_grid.py:359-363
+        return self.fn.apply(coords, table)[:, ::2]                # :370
+
+    def ent_loss(self, noise):
+        weight = self.codebook + noise                             # latent_grid.py:132-136
+        prob = self.prob_model(weight + 0.5) - self.prob_model(weight - 0.5)
+        bits = torch.sum(torch.clamp(-1.0 * torch.log(prob + 1e-10) / np.log(2.0), 0, 50))
+        return bits / self.codebook.shape[0], bits
+
+
+def clamped_psnr(pred, gt):
+    a = (torch.clamp(pred, 0, 1) * 255).to(torch.uint8).float()
+    b = (torch.clamp(gt, 0, 1) * 255).to(torch.uint8).float()
+    mse = torch.mean((a - b) ** 2).item()
+    return 20 * np.log10(255.0) - 10 * np.log10(max(mse, 1e-12))
+
+
+def fit(seed, impl, steps, dev, use_graph, noise_cpu):
+    from shacira_b200.grids import LatentGrid
+    torch.manual_seed(seed)
+    grid = LatentGrid.from_geometric(feature_dim=1, num_lods=16, latent_dim=1, multiscale_type="cat", resolution_dim=2,
+                                     feature_std=0.1, codebook_bitwidth=16, min_grid_res=16, max_grid_res=512,
+                                     init_grid="uniform", conf_latent_decoder=dict(DEC), conf_entropy_reg=dict(ENT))
+    mlp = nn.Sequential(nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 3))
+    grid, mlp = grid.to(dev), mlp.to(dev)
+    grid.noise_on_device = not noise_cpu
+    if impl == "ref":
+        grid = RefGrid(grid).to(dev)
+    coords, gt = make_data(seed, dev)
+    T = grid.codebook.shape[0]
+    cap = dict(capturable=True) if use_graph else {}
+    groups = [dict(params=list(mlp.parameters()), lr=1e-3, weight_decay=0.0),
+              dict(params=[grid.codebook], lr=2e-2, weight_decay=0.0),
+              dict(params=[p for p in grid.latent_dec.parameters() if p.requires_grad], lr=1e-2, weight_decay=1e-2),
+              dict(params=list(grid.prob_model.parameters()), lr=1e-4, weight_decay=1e-2)]
+    opt = torch.optim.Adam(groups, eps=1e-8, **cap)
+    lam = torch.zeros((), device=dev)
+    noise_gen = torch.Generator().manual_seed(10_000 + seed)
+    noise_buf = torch.zeros((T, 1), device=dev)
+    out = {}
+
+    def train_step():
+        opt.zero_grad(set_to_none=False)
+        feats = grid.interpolate(coords, 0)
+        pred = mlp(feats)
+        rgb_loss = ((pred - gt) ** 2).mean()
+        if impl == "ref":
+            avg_bits, bits = grid.ent_loss(noise_buf)
+        else:
+            grid.noise = noise_buf
+            grid.noise_freq = 2                      # odd idx: use the preset grid.noise (filled below)
+            avg_bits, bits = grid.ent_loss(1)
+        loss = rgb_loss + lam * avg_bits
+        loss.backward()
+        opt.step()
+        out["pred"], out["rgb_loss"], out["bits"] = pred.detach(), rgb_loss.detach(), bits.detach()
+
+    def host_side(it):
+        # schedules and the noise draw happen outside the (possibly captured) device step
+        lam.fill_(1e-4 + 0.5 * (1e-3 - 1e-4) * (1 + math.cos(math.pi * it / steps)))   # schedulers.py:26-27
+        if noise_cpu:
+            noise_buf.copy_(torch.rand((T, 1), generator=noise_gen) - 0.5)
+        else:
+            noise_buf.uniform_(-0.5, 0.5)
+        if it + 1 in (1, 2, 5, 10):                  # norm_every % total_iterations == 0 (reversed modulo, Q7)
+            with torch.no_grad():
+                w = grid.codebook
+                grid.latent_dec.div.data.copy_(torch.max(torch.abs(w.min(dim=0)[0]), torch.abs(w.max(dim=0)[0])))
+
+    graph = None
+    if use_graph:
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for it in range(3):                      # warm-up on a side stream (allocator, plan, Adam state)
+                host_side(it)
+                train_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            train_step()
+        start_it = 3
+    else:
+        start_it = 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for it in range(start_it, steps):
+        host_side(it)
+        if graph is not None:
+            graph.replay()
+        else:
+            train_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    with torch.no_grad():
+        pred = mlp(grid.interpolate(coords, 0))
+        psnr = clamped_psnr(pred, gt)
+        q = torch.round(grid.codebook.detach()[:, 0]).long()
+        _, counts = torch.unique(q, return_counts=True)
+        p = counts / counts.sum()
+        latent_bits = float(torch.sum(torch.clamp(-torch.log(p + 1e-10) / np.log(2.0), 0, 1000) * counts))
+        n_other = sum(p.numel() for p in mlp.parameters()) + sum(p.numel() for p in grid.latent_dec.parameters())
+        bpp = (latent_bits + 32 * n_other) / (H * W)
+    return dict(seed=seed, psnr=psnr, bpp=bpp, latent_bits=latent_bits, ms_per_step=dt / (steps - start_it) * 1e3,
+                rgb_loss=float(out["rgb_loss"]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--impl", default="ours", choices=["ours", "ref"])
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--images", type=int, default=1)
+    ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--noise-cpu", action="store_true", help="draw the entropy noise with the CPU generator (parity runs)")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from shacira_b200 import dp
+    mine = dp.shard_units(args.images, rank, world)      # independent images: round-robin, no collective
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    results = [fit(s, args.impl, args.steps, dev, args.graph, args.noise_cpu) for s in mine]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    allres = dp.gather_results(dict(rank=rank, wall=wall, fits=results))
+    if rank == 0:
+        wall = max(r["wall"] for r in allres)
+        fits = [f for r in allres for f in r["fits"]]
+        ms = float(np.mean([f["ms_per_step"] for f in fits]))
+        print(json.dumps({"workload": "Kodak-shape image INR fit (BASELINE cfg2/cfg3)", "impl": args.impl,
+                          "n_gpus": world, "images": args.images, "steps_per_fit": args.steps, "cuda_graph": args.graph,
+                          "ms_per_step": ms, "psnr": [round(f["psnr"], 3) for f in fits], "bpp": [round(f["bpp"], 4) for f in fits],
+                          "wall_s": wall,
+                          "fits_per_hour_at_60000_steps": world * 3600.0 / (60000 * ms * 1e-3) if fits else None}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
