@@ -32,6 +32,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 H, W = 512, 768
+LATENT_SCALE = 20.0
 
 
 def synthetic_image(seed):
@@ -115,6 +116,11 @@ def fit(seed, impl, steps, dev, use_graph, noise_cpu):
                                      feature_std=0.1, codebook_bitwidth=16, min_grid_res=16, max_grid_res=512,
                                      init_grid="uniform", conf_latent_decoder=dict(DEC), conf_entropy_reg=dict(ENT))
     mlp = nn.Sequential(nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 3))
+    with torch.no_grad():
+        # SGA-off runs start with every latent rounding to 0 at the reference's feature_std = 0.1 and frequently
+        # never leave that state (both arms collapse identically); SURVEY 8d: scale the latents so that rounding
+        # is non-trivial from step 0.
+        grid.codebook.mul_(LATENT_SCALE)
     grid, mlp = grid.to(dev), mlp.to(dev)
     grid.noise_on_device = not noise_cpu
     if impl == "ref":
