@@ -414,7 +414,10 @@ __device__ __forceinline__ int level_of_slot(const TileGeom<D>& tg, int num_stag
 // Stage the (rounded) latents of every node of the tile's staged levels into shared memory. The slot
 // loop is flat over all levels and unrolled so that each thread has kStageUnroll independent gathers
 // in flight (a per-level loop would serialise one global-load latency per level).
-constexpr int kStageUnroll = 4;
+#ifndef SHACIRA_STAGE_UNROLL
+#define SHACIRA_STAGE_UNROLL 4
+#endif
+constexpr int kStageUnroll = SHACIRA_STAGE_UNROLL;
 #ifndef SHACIRA_MIN_CTAS
 #define SHACIRA_MIN_CTAS 7
 #endif
@@ -588,13 +591,17 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
     if (DEC)
         for (int e = threadIdx.x; e < (ZP ? NW : 1) * L * (C * F + F); e += kTileThreads) s_gA[e] = 0.0f;
     tile_geometry<D>(tg, lp, ti, pv.g, cap, cap_acc, cap_acc - cap);
-    if (DEC) stage_nodes<D, C>(tg, lp, latents, round_flag, s_lat);  // ZP: per-point z; SG: q[node] at flush
+    bool staged_lat = false;
 
     for (int b0 = beg; b0 < end; b0 += kBatch) {
         const int b1 = min(end, b0 + kBatch);
         int kbits = 0;
         while ((1 << kbits) < (b1 - b0)) ++kbits;
-        for (int e = threadIdx.x; e < tg.acc_total * CA; e += kTileThreads) s_acc[e] = 0;
+        {
+            const int n4 = (tg.acc_total * CA + 3) >> 2;  // capacities are multiples of 4 slots: whole int4 stores
+            int4* z4 = reinterpret_cast<int4*>(s_acc);
+            for (int e = threadIdx.x; e < n4; e += kTileThreads) z4[e] = make_int4(0, 0, 0, 0);
+        }
         if (threadIdx.x < SHACIRA_MAX_LEVELS) s_gmax[threadIdx.x] = 0u;
         __syncthreads();
         // pass 1: per-level maxima of what will be accumulated (they fix the fixed-point scales).
@@ -648,6 +655,12 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                         }
                 }
             }
+        }
+        // latents for the decoder gradients (ZP: per-point z in pass 2; SG: q[node] at flush). Staged here, behind
+        // pass 1, so that their gather latency overlaps the other warps' work instead of the kernel prologue.
+        if (DEC && !staged_lat) {
+            stage_nodes<D, C>(tg, lp, latents, round_flag, s_lat);
+            staged_lat = true;
         }
         __syncthreads();
         if (threadIdx.x < L) {
@@ -809,86 +822,82 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
         }
         __syncthreads();
         // flush: one float REDG per touched node (+ the per-node decoder gradients in scatter-g mode)
-        // scatter-g decoder partial sums: per level for per-level decoders; for one shared decoder the levels
-        // are summed anyway (the caller adds grad_A over levels), so they ride in level slot `dl` = 0 and are
-        // reduced over the warp once per tile instead of once per level
+        // flush: one float REDG per touched node (+ the per-node decoder gradients in scatter-g mode).
+        // pS / pA: scatter-g decoder partial sums of this thread.
         float pS[SG ? F : 1], pA[SG ? C * F : 1];
 #pragma unroll
         for (int e = 0; e < (SG ? F : 1); ++e) pS[e] = 0.0f;
 #pragma unroll
         for (int e = 0; e < (SG ? C * F : 1); ++e) pA[e] = 0.0f;
-        int last_staged = -1;
-        for (int l = 0; l < L; ++l)
-            if ((tg.staged >> l) & 1u) last_staged = l;
-        for (int l = 0; l < L; ++l) {
-            if (!((tg.staged >> l) & 1u)) continue;
-            int n_l = 1;
-#pragma unroll
-            for (int d = 0; d < D; ++d) n_l *= tg.w[l][d];
-            const float inv = s_inv[l];
-            const int la = per_level ? l : 0;
-            float* base = grad_latents + (int64_t)lp.first[l] * C;
-            const bool rep = tg.acc_mul[l] == 32;
-            if (SG && per_level) {
-#pragma unroll
-                for (int e = 0; e < F; ++e) pS[e] = 0.0f;
-#pragma unroll
-                for (int e = 0; e < C * F; ++e) pA[e] = 0.0f;
-            }
-            // one thread per node. Lane-replicated level: the thread sums its node's 32 copies, starting at
-            // its own lane so that the 32 lanes of a warp read 32 different banks (exact integer sums).
-            for (int e = threadIdx.x; e < n_l; e += kTileThreads) {
+        const int num_staged = __popc(tg.staged);
+        const int total_nodes = tg.total;
+        // One thread per node over ALL staged levels at once (flat slot index, level by binary search): full lanes
+        // on the small coarse levels and no per-level loop overhead. With per-level decoders in scatter-g mode the
+        // partial sums must be kept per level, so that (rare) case walks level by level instead.
+        const bool by_level = SG && per_level;
+        for (int lvl = 0; lvl < (by_level ? num_staged : 1); ++lvl) {
+            const int e_begin = by_level ? tg.off[lvl] : 0;
+            const int e_end = by_level ? ((lvl + 1 < num_staged) ? tg.off[lvl + 1] : total_nodes) : total_nodes;
+            for (int e = e_begin + threadIdx.x; e < e_end; e += kTileThreads) {
+                const int l = by_level ? lvl : level_of_slot<D>(tg, num_staged, e);
+                const int nloc = e - tg.off[l];
+                const float inv = s_inv[l];
+                const bool rep = tg.acc_mul[l] == 32;
+                const int abase = tg.acc_off[l];
                 bool any = false;
                 float gv[CA];
 #pragma unroll
                 for (int ch = 0; ch < CA; ++ch) {
                     int qv = 0;
                     if (rep) {
+                        // the node's 32 lane copies, read starting at this thread's lane: 32 different banks per warp
 #pragma unroll 8
-                        for (int jj = 0; jj < 32; ++jj)
-                            qv += s_acc[(size_t)(tg.acc_off[l] + e * 32 + ((lane + jj) & 31)) * CA + ch];
+                        for (int jj = 0; jj < 32; ++jj) qv += s_acc[(size_t)(abase + nloc * 32 + ((lane + jj) & 31)) * CA + ch];
                     } else {
-                        qv = s_acc[(size_t)(tg.acc_off[l] + e) * CA + ch];
+                        qv = s_acc[(size_t)(abase + nloc) * CA + ch];
                     }
                     any |= (qv != 0);
                     gv[ch] = (float)qv * inv;
                 }
-                if (any) {
-                    const int row = node_row<D>(tg, lp, l, e, false);
-                    if (row >= 0) {
-                        if constexpr (SG) {
-                            float qn[C], gl[C];
-                            lds_row<C>(s_lat + (size_t)(tg.off[l] + e) * C, qn);  // staged (already rounded)
+                if (!any) continue;
+                const int row = node_row<D>(tg, lp, l, nloc, false);
+                if (row < 0) continue;
+                float* dst = grad_latents + ((int64_t)lp.first[l] + row) * C;
+                if constexpr (SG) {
+                    const int la = per_level ? l : 0;
+                    float qn[C], gl[C];
+                    lds_row<C>(s_lat + (size_t)e * C, qn);  // staged (already rounded)
 #pragma unroll
-                            for (int ch = 0; ch < C; ++ch) {
-                                float acc = 0.0f;
+                    for (int ch = 0; ch < C; ++ch) {
+                        float acc = 0.0f;
 #pragma unroll
-                                for (int jf = 0; jf < F; ++jf) {
-                                    acc = __fmaf_rn(gv[jf], s_A[(la * C + ch) * F + jf], acc);
-                                    pA[ch * F + jf] = __fmaf_rn(qn[ch], gv[jf], pA[ch * F + jf]);
-                                }
-                                gl[ch] = acc;
-                            }
-#pragma unroll
-                            for (int jf = 0; jf < F; ++jf) pS[jf] += gv[jf];
-                            red_add_row<C>(base + (int64_t)row * C, gl);
-                        } else {
-                            red_add_row<C>(base + (int64_t)row * C, gv);
+                        for (int jf = 0; jf < F; ++jf) {
+                            acc = __fmaf_rn(gv[jf], s_A[(la * C + ch) * F + jf], acc);
+                            pA[ch * F + jf] = __fmaf_rn(qn[ch], gv[jf], pA[ch * F + jf]);
                         }
+                        gl[ch] = acc;
                     }
+#pragma unroll
+                    for (int jf = 0; jf < F; ++jf) pS[jf] += gv[jf];
+                    red_add_row<C>(dst, gl);
+                } else {
+                    red_add_row<C>(dst, gv);
                 }
             }
-            if (SG && (per_level || l == last_staged)) {
-                const int dl = per_level ? l : 0;
+            if (SG) {
+                // one shared decoder: everything rides in level slot 0 (the caller sums grad_A over levels anyway)
+                const int dl = by_level ? lvl : 0;
 #pragma unroll
                 for (int e = 0; e < F; ++e) {
                     const float v = warp_sum(pS[e]);
                     if (lane == 0 && v != 0.0f) atomicAdd(&s_gS[dl * F + e], v);
+                    pS[e] = 0.0f;
                 }
 #pragma unroll
                 for (int e = 0; e < C * F; ++e) {
                     const float v = warp_sum(pA[e]);
                     if (lane == 0 && v != 0.0f) atomicAdd(&s_gA[dl * C * F + e], v);
+                    pA[e] = 0.0f;
                 }
             }
         }
