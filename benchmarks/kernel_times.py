@@ -52,10 +52,22 @@ def main():
         _lib._check(lib.shacira_latent_backward(2, p(s["coords"]), n, p(s["grad_out"]), p(s["z"]), fi, rs, L,
                                                 bench.BITWIDTH, 1, 1, p(A), 0, T, 1, p(s["gl"]), p(gA), p(gS), st))
 
+    noise, prob = d(wl["noise"]), d(wl["prob"])
+    bits = torch.empty((1 + L,), dtype=torch.float64, device=dev)
+    egl = torch.empty((T, 1), device=dev)
+    egp = torch.empty((4, 3, 1), device=dev)
+
+    scratch = torch.zeros(int(lib.shacira_entropy_scratch_bytes(1, L)), dtype=torch.uint8, device=dev)
+
+    def ent(s, st):
+        _lib._check(lib.shacira_entropy_bits(p(lat), p(noise), T, 1, p(prob), 2, fi, L, p(bits), p(egl), p(egp),
+                                             p(scratch), scratch.numel(), st))
+
     out = {}
-    for name, fn in (("fwd_tiled", fwd), ("bwd_tiled_dec", bwd), ("bwd_tiled_nodec", lambda s, st: bwd(s, st, False)),
+    only_ent = bool(os.environ.get("ONLY_ENT"))
+    for name, fn in ((("entropy_fwd_bwd", ent),) if only_ent else (("entropy_fwd_bwd", ent), ("fwd_tiled", fwd), ("bwd_tiled_dec", bwd), ("bwd_tiled_nodec", lambda s, st: bwd(s, st, False)),
                      ("fwd_pointparallel", fwd_pp), ("bwd_pointparallel", bwd_pp),
-                     ("step_tiled", lambda s, st: (fwd(s, st), bwd(s, st)))):
+                     ("step_tiled", lambda s, st: (fwd(s, st), bwd(s, st))))):
         stream = torch.cuda.Stream()
         with torch.cuda.stream(stream):
             st = ctypes.c_void_p(stream.cuda_stream)

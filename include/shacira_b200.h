@@ -156,11 +156,16 @@ int shacira_latent_backward_planned(const shacira_plan_t* plan, const float* gra
  * params: float32 [4, 3, C] = {f1,f2,f3,f4} x {h,b,a} x channel (f4.a unused).
  * Outputs (all nullable except bits): bits[1 + num_lods] double = total, then per level;
  * grad_latents[T, C] = d total / d latents (written, not accumulated; zero when noise==NULL);
- * grad_params[4, 3, C] float32 = d total / d params (ACCUMULATED; caller zero-fills).
+ * grad_params[4, 3, C] float32 = d total / d params (written).
  * first_idx (host, nullable with num_lods = 0) gives the per-level reduction. */
 int shacira_entropy_bits(const float* latents, const float* noise, int64_t table_rows, int32_t latent_dim,
                          const float* params, int32_t num_layers, const int32_t* first_idx, int32_t num_lods,
-                         double* bits, float* grad_latents, float* grad_params, shacira_stream_t stream);
+                         double* bits, float* grad_latents, float* grad_params, void* scratch, int64_t scratch_bytes,
+                         shacira_stream_t stream);
+/* Device scratch for the block partials of shacira_entropy_bits: zero-fill it ONCE, then reuse it for every call
+ * on the same stream (the kernel leaves it ready). scratch == NULL makes the call allocate from the stream's
+ * memory pool instead (more launch overhead). */
+int64_t shacira_entropy_scratch_bytes(int32_t latent_dim, int32_t num_lods);
 
 /* ---- symbols / histogram for LatentGrid.size() --------------------------------------- */
 /* latent_grid.py:138-153: per channel q = rint(latents[:,c]); symbols[T, C] (int16,

@@ -45,7 +45,8 @@ SIGNATURES = {
     "shacira_plan_debug": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     "shacira_latent_forward_planned": (ctypes.c_int, [_vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "shacira_latent_backward_planned": (ctypes.c_int, [_vp, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
-    "shacira_entropy_bits": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _c_int32_p, _i32, _vp, _vp, _vp, _vp]),
+    "shacira_entropy_bits": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _c_int32_p, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "shacira_entropy_scratch_bytes": (_i64, [_i32, _i32]),
     "shacira_quantize_symbols": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "shacira_symbol_histogram": (ctypes.c_int, [_vp, _i64, _i32, _c_int32_p, _i32, _vp, _vp]),
     "shacira_ac_encode": (_i64, [_vp, _i64, _vp, _i32, _vp, _i64]),
@@ -340,6 +341,23 @@ def latent_backward_planned(plan, grad_output, latents, first_idx, resolutions, 
     return gl, gA, gS
 
 
+_ent_scratch = {}
+
+
+def _entropy_scratch(device, C, L):
+    """Zero-initialised scratch per (device, stream): reused by every entropy call on that stream."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, C, L)
+    buf = _ent_scratch.get(key)
+    if buf is None:
+        nbytes = int(load().shacira_entropy_scratch_bytes(C, L))
+        side = torch.cuda.is_current_stream_capturing()
+        if side:  # first use inside a graph capture: let the call allocate from the pool instead
+            return None
+        buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _ent_scratch[key] = buf
+    return buf
+
+
 def entropy_bits(latents, noise, params, num_layers, first_idx=None, want_grads=True):
     """params [4, 3, C]. Returns (bits[1+L] float64, grad_latents[T, C] | None, grad_params[4,3,C] | None)."""
     lib = load()
@@ -356,8 +374,10 @@ def entropy_bits(latents, noise, params, num_layers, first_idx=None, want_grads=
     gl = torch.empty_like(latents) if want_grads else None
     gp = torch.empty((4, 3, C), dtype=torch.float32, device=dev) if want_grads else None
     with torch.cuda.device(dev):
+        scratch = _entropy_scratch(dev, C, L)
         _check(lib.shacira_entropy_bits(_ptr(latents), _ptr(noise), T, C, _ptr(params), num_layers, fi, L,
-                                        _ptr(bits), _ptr(gl), _ptr(gp), _stream()))
+                                        _ptr(bits), _ptr(gl), _ptr(gp), _ptr(scratch),
+                                        scratch.numel() if scratch is not None else 0, _stream()))
     return bits, gl, gp
 
 

@@ -1,5 +1,7 @@
 // capi.cu -- the extern "C" surface declared in include/shacira_b200.h: argument validation,
 // level metadata, template dispatch and launches. No torch, no exceptions across the ABI.
+#include <cstdlib>
+
 #include "arith_coder.inl"
 #include "capi_internal.h"
 #include "entropy_kernels.cuh"
@@ -269,7 +271,8 @@ int shacira_latent_backward(int32_t dim, const float* coords, int64_t n, const f
 
 int shacira_entropy_bits(const float* latents, const float* noise, int64_t table_rows, int32_t latent_dim,
                          const float* params, int32_t num_layers, const int32_t* first_idx, int32_t num_lods,
-                         double* bits, float* grad_latents, float* grad_params, shacira_stream_t stream) {
+                         double* bits, float* grad_latents, float* grad_params, void* scratch, int64_t scratch_bytes,
+                         shacira_stream_t stream) {
     if (!latents || !params || !bits) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "latents/params/bits is NULL");
     if (table_rows < 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "table_rows is negative");
     if (latent_dim < 1 || latent_dim > kMaxEntC || (latent_dim & (latent_dim - 1)))
@@ -278,10 +281,12 @@ int shacira_entropy_bits(const float* latents, const float* noise, int64_t table
     if (num_lods < 0 || num_lods > SHACIRA_MAX_LEVELS || (num_lods > 0 && !first_idx))
         return fail(SHACIRA_ERR_INVALID_ARGUMENT, "bad num_lods/first_idx");
     cudaStream_t s = (cudaStream_t)stream;
-    CUDA_OK(cudaMemsetAsync(bits, 0, sizeof(double) * (size_t)(1 + num_lods), s));
-    if (grad_params) CUDA_OK(cudaMemsetAsync(grad_params, 0, sizeof(float) * 12 * (size_t)latent_dim, s));
     const int64_t total = table_rows * latent_dim;
-    if (total == 0) return SHACIRA_OK;
+    if (total == 0) {
+        CUDA_OK(cudaMemsetAsync(bits, 0, sizeof(double) * (size_t)(1 + num_lods), s));
+        if (grad_params) CUDA_OK(cudaMemsetAsync(grad_params, 0, sizeof(float) * 12 * (size_t)latent_dim, s));
+        return SHACIRA_OK;
+    }
     LevelBounds lb;
     memset(&lb, 0, sizeof(lb));
     lb.num_lods = num_lods;
@@ -291,12 +296,36 @@ int shacira_entropy_bits(const float* latents, const float* noise, int64_t table
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int64_t blocks = (total + kEntBlock - 1) / kEntBlock;
-    const int64_t cap = (int64_t)sms * 8;  // persistent-ish: a few resident blocks per SM
+    static const int per_sm = [] { const char* e = getenv("SHACIRA_ENT_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
+    const int64_t cap = (int64_t)sms * per_sm;  // per-block prologue/epilogue (~500 instructions) vs parallelism: tuned on B200
     if (blocks > cap) blocks = cap;
+    // scratch for the block partials + arrival ticket: the caller's (zero-initialised once, reusable: the kernel
+    // leaves the ticket at 0), else a stream-ordered pool allocation (3 more graph nodes per call)
+    const int P = 1 + num_lods + 12 * latent_dim;
+    const size_t part_bytes = ((sizeof(float) * (size_t)blocks * P) + 255) & ~(size_t)255;
+    char* buf = (char*)scratch;
+    const bool own = !buf || (size_t)scratch_bytes < part_bytes + 256;
+    if (own) {
+        buf = nullptr;
+        CUDA_OK(cudaMallocAsync((void**)&buf, part_bytes + 256, s));
+        CUDA_OK(cudaMemsetAsync(buf + part_bytes, 0, sizeof(unsigned), s));
+    }
+    unsigned* ticket = (unsigned*)(buf + part_bytes);
     entropy_kernel<<<(int)blocks, kEntBlock, 0, s>>>(latents, noise, total, latent_dim, params, num_layers, lb, bits,
-                                                     grad_latents, grad_params);
-    LAUNCHED();
+                                                     grad_latents, grad_params, (float*)buf, ticket);
+    launch_counter().fetch_add(1);
+    const cudaError_t le = cudaGetLastError();
+    if (own) cudaFreeAsync(buf, s);
+    if (le != cudaSuccess) return fail(SHACIRA_ERR_CUDA, "entropy launch: %s", cudaGetErrorString(le));
     return SHACIRA_OK;
+}
+
+int64_t shacira_entropy_scratch_bytes(int32_t latent_dim, int32_t num_lods) {
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t blocks = (int64_t)sms * 8;  // upper bound of the launch grid
+    const int64_t P = 1 + num_lods + 12 * (int64_t)latent_dim;
+    return ((4 * blocks * P + 255) & ~(int64_t)255) + 256;
 }
 
 int shacira_quantize_symbols(const float* latents, int64_t table_rows, int32_t latent_dim, int16_t* symbols,

@@ -255,17 +255,17 @@ __device__ __forceinline__ int node_row(const TileGeom<D>& tg, const LevelParams
         }
     }
     if ((lp.dense_mask >> l) & 1u) {
-        long long idx = nx[0];
-        long long mul = res;
+        // dense level: res^D < 2^30 rows, node coordinates <= res: the index fits 32 bits
         bool outside = nx[0] >= res;
+        int idx = nx[0], mul = res;
 #pragma unroll
         for (int d = 1; d < D; ++d) {
-            idx += (long long)nx[d] * mul;
-            mul *= res;
             outside |= nx[d] >= res;
+            idx += nx[d] * mul;
+            mul *= res;
         }
         if (outside || idx >= lp.rows[l]) return clamp_inside ? lp.rows[l] - 1 : -1;
-        return (int)idx;
+        return idx;
     }
     uint32_t h = (uint32_t)nx[0];
     if (D > 1) h ^= (uint32_t)nx[1] * kPrimeY;
