@@ -38,9 +38,10 @@
  *
  * Parity pin: the reference ships no CPU implementation, tests or golden vectors for
  * this path. The pin is (1) oracle/_ref -- the reference's own .cu
- * files compiled for sm_100a (oracle/Makefile) and compared with this file on the GPU
- * box (tests/test_ref_kernels_gpu.py), and (2) tests/golden/hashgrid_ref_*.npz, outputs
- * of those reference kernels captured on a B200 (tests/golden/make_golden_gpu.py).
+ * files compiled unmodified for sm_100a (oracle/build_ref.py) and compared with this file
+ * on the GPU box (tests/test_ref_kernels_gpu.py: forward bit-identical), and (2)
+ * tests/golden/hashgrid_ref_kernels.npz, outputs of those reference kernels captured on a
+ * B200 by tests/golden/make_golden_gpu.py and checked on CPU (tests/test_oracle_golden.py).
  */
 #include <math.h>
 #include <stdint.h>
