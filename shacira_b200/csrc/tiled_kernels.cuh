@@ -400,6 +400,21 @@ __device__ __forceinline__ void interp_level(const double (&t)[D], const LevelPa
     }
 }
 
+// Staged-level interpolation without the staged/direct branch: used when a whole chunk of levels is staged, so
+// that the unrolled levels form ONE basic block and their dependent chains (DMUL -> F2F -> F2I -> LDS -> FMA)
+// interleave -- the per-level branch otherwise serialises them.
+template <int D, int C>
+__device__ __forceinline__ void interp_staged(const double (&t)[D], const LevelRegs& r, const float* s_nodes,
+                                              float (&z)[C]) {
+    constexpr int NC = 1 << D;
+    Stencil<D> st;
+    stencil<D>(t, r, st);
+    float v[NC][C];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) lds_row<C>(s_nodes + (size_t)st.slot[k] * C, v[k]);
+    lerp_rows<NC, C>(v, st.w, z);
+}
+
 // staged levels are a prefix of the levels and their slots are contiguous: level of slot e by binary search
 template <int D>
 __device__ __forceinline__ int level_of_slot(const TileGeom<D>& tg, int num_staged, int e) {
@@ -509,19 +524,29 @@ latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, co
 #pragma unroll
                 for (int e = 0; e < C * F; ++e) Am[q][e] = s_A[la * C * F + e];
             }
+            bool all_staged = true;
+#pragma unroll
+            for (int q = 0; q < kLv; ++q) all_staged &= lr[q].staged;
 #pragma unroll
             for (int k = 0; k < kPts; ++k) {
                 if (orig[k] < 0) continue;
                 float o[kLv * F];
+                float z[kLv][C];
+                if (all_staged) {  // uniform: one basic block for the kLv levels
+#pragma unroll
+                    for (int q = 0; q < kLv; ++q) interp_staged<D, C>(t[k], lr[q], s_nodes, z[q]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < kLv; ++q)
+                        interp_level<D, C>(t[k], lp, lr[q], l0 + q, s_nodes, latents, round_flag, z[q]);
+                }
 #pragma unroll
                 for (int q = 0; q < kLv; ++q) {
-                    float z[C];
-                    interp_level<D, C>(t[k], lp, lr[q], l0 + q, s_nodes, latents, round_flag, z);
 #pragma unroll
                     for (int jf = 0; jf < F; ++jf) {
                         float acc = sh[q][jf];
 #pragma unroll
-                        for (int ch = 0; ch < C; ++ch) acc = __fmaf_rn(z[ch], Am[q][ch * F + jf], acc);
+                        for (int ch = 0; ch < C; ++ch) acc = __fmaf_rn(z[q][ch], Am[q][ch * F + jf], acc);
                         o[q * F + jf] = acc;
                     }
                 }
@@ -690,6 +715,9 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                     for (int e = 0; e < C * F; ++e) Am[q][e] = s_A[la * C * F + e];
                 }
             }
+            bool all_staged = true;
+#pragma unroll
+            for (int q = 0; q < kLv; ++q) all_staged &= lr[q].staged;
             for (int base = b0; base < b1; base += kTileThreads * KP) {
                 float gk[KP][kLv * F];
                 double tk[KP][D];
@@ -712,6 +740,51 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                     if (!livek[k]) continue;
                     const double (&t)[D] = tk[k];
                     const float (&g)[kLv * F] = gk[k];
+                    if (all_staged) {
+                        // every level of the chunk is staged (uniform): stencils first, as one basic block, so the
+                        // kLv dependent chains interleave; then the shared-memory adds
+                        Stencil<D> st[kLv];
+#pragma unroll
+                        for (int q = 0; q < kLv; ++q) stencil<D>(t, lr[q], st[q]);
+#pragma unroll
+                        for (int q = 0; q < kLv; ++q) {
+                            float gz[CA];
+                            if (SG) {
+#pragma unroll
+                                for (int jf = 0; jf < F; ++jf) gz[jf] = g[q * F + jf];
+                            } else {
+#pragma unroll
+                                for (int ch = 0; ch < C; ++ch) {
+                                    float acc = 0.0f;
+#pragma unroll
+                                    for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[q * F + jf], Am[q][ch * F + jf], acc);
+                                    gz[ch] = acc;
+                                }
+                            }
+#pragma unroll
+                            for (int ch = 0; ch < CA; ++ch) {
+                                const float gs = __fmul_rn(gz[ch], scq[q]);  // power-of-two scale: exact
+#pragma unroll
+                                for (int kk = 0; kk < NC; ++kk)
+                                    atomicAdd(&s_acc[(size_t)((st[q].slot[kk] + lr[q].accd) * lr[q].amul + lr[q].alane) * CA + ch],
+                                              __float2int_rn(__fmul_rn(gs, st[q].w[kk])));
+                            }
+                            if (ZP) {
+                                float v[NC][C], z[C];
+#pragma unroll
+                                for (int kk = 0; kk < NC; ++kk) lds_row<C>(s_lat + (size_t)st[q].slot[kk] * C, v[kk]);
+                                lerp_rows<NC, C>(v, st[q].w, z);
+#pragma unroll
+                                for (int jf = 0; jf < F; ++jf) {
+                                    accS[q * F + jf] += g[q * F + jf];
+#pragma unroll
+                                    for (int ch = 0; ch < C; ++ch)
+                                        accA[(q * C + ch) * F + jf] = __fmaf_rn(z[ch], g[q * F + jf], accA[(q * C + ch) * F + jf]);
+                                }
+                            }
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int q = 0; q < kLv; ++q) {
                         const int l = l0 + q;
