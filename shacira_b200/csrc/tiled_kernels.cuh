@@ -562,7 +562,9 @@ latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, co
 // Power-of-two scale so that the sum of up to 2^k terms of magnitude <= m stays below 2^30.
 __device__ __forceinline__ float fixed_scale(float m, int k, float& inv) {
     if (!(m > 0.0f) || !isfinite(m)) {
-        inv = 0.0f;
+        // all-zero level: nothing to add. Inf/NaN upstream gradients cannot be scaled: poison the level's nodes of
+        // this tile with NaN at flush time, like the reference's float atomics would
+        inv = (m != m || m > 3.0e38f) ? __int_as_float(0x7fc00000) : 0.0f;
         return 0.0f;
     }
     int ex;
@@ -931,6 +933,11 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                     }
                     any |= (qv != 0);
                     gv[ch] = (float)qv * inv;
+                }
+                if (inv != inv) {  // non-finite upstream gradient in this tile/level (see fixed_scale)
+                    any = true;
+#pragma unroll
+                    for (int ch = 0; ch < CA; ++ch) gv[ch] = inv;
                 }
                 if (!any) continue;
                 const int row = node_row<D>(tg, lp, l, nloc, false);

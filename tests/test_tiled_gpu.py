@@ -164,6 +164,21 @@ def test_gradient_magnitude_extremes(lib):
     plan.close()
 
 
+def test_non_finite_upstream_gradient_propagates(lib):
+    """Fixed-point accumulation cannot represent Inf/NaN: the affected tile/level is poisoned with NaN, as the
+    reference's float atomics would do, instead of silently dropping the gradient."""
+    c = _case(2, 8, 12, 16, 128, 20000, 1, 1, seed=12, kind="uniform")
+    coords, lat, A = _dev(c["coords"]), _dev(c["lat"]), _dev(c["A"])
+    g = c["g"].copy()
+    g[123, 2] = np.inf
+    plan = lib.Plan(coords)
+    gl, _, _ = lib.latent_backward_planned(plan, _dev(g), None, c["first"], c["res"], 12, A, 1, 1, c["T"], True, False)
+    a, b = c["first"][2], c["first"][3]
+    assert bool(torch.isnan(gl[a:b]).any())                   # level 2 carries the poison
+    assert bool(torch.isfinite(gl[:a]).all()) and bool(torch.isfinite(gl[b:]).all())
+    plan.close()
+
+
 def test_latent_grid_api_uses_the_plan_and_matches_unplanned(lib, monkeypatch):
     from shacira_b200 import grid_ops
     from shacira_b200.grids import LatentGrid
