@@ -253,11 +253,23 @@ class Plan:
         self.n = coords.shape[0]
         self.device = coords.device
         self.coords = coords
+        self.users = 0  # autograd graphs that still need this plan for their backward (see grid_ops.plan_for)
         handle = ctypes.c_void_p(0)
         with torch.cuda.device(coords.device):
             _check(lib.shacira_plan_create(self.dim, _ptr(coords), self.n, int(tile_points), _stream(),
                                            ctypes.byref(handle)))
         self.handle = handle
+
+    def rebuild(self, coords, tile_points=0):
+        """Re-bin this plan for another coordinate set, reusing the device allocation (no cudaMalloc)."""
+        coords = _f32c(coords, "coords")
+        if coords.device != self.device:
+            raise ShaciraError(ERR_INVALID_ARGUMENT, "plan and coords live on different devices")
+        dim = _dim_of(coords)
+        with torch.cuda.device(self.device):
+            _check(load().shacira_plan_rebuild(self.handle, dim, _ptr(coords), coords.shape[0], int(tile_points), _stream()))
+        self.dim, self.n, self.coords = dim, coords.shape[0], coords
+        return self
 
     def info(self):
         n, d, g, t = ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)

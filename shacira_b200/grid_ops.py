@@ -43,12 +43,21 @@ def plan_for(coords):
         _plans.move_to_end(key)
         plan_stats["hits"] += 1
         return plan
-    plan = _lib.Plan(coords)
+    plan = None
+    if len(_plans) >= PLAN_CACHE_SIZE:
+        # recycle the least recently used plan: its device allocation is reused (no cudaMalloc on the hot path
+        # of workloads whose coordinates change every step)
+        _, old = _plans.popitem(last=False)
+        if old.users > 0:
+            pass        # a pending backward still needs it: leave it to its owner (freed when the graph dies)
+        elif old.device == coords.device:
+            plan = old.rebuild(coords)
+        else:
+            old.close()
+    if plan is None:
+        plan = _lib.Plan(coords)
     plan_stats["builds"] += 1
     _plans[key] = plan
-    while len(_plans) > PLAN_CACHE_SIZE:
-        _, old = _plans.popitem(last=False)
-        old.close()
     return plan
 
 
@@ -152,6 +161,8 @@ class LatentHashGrid(torch.autograd.Function):
                                            save_z=need_dec)
             ctx.save_for_backward(coords, A.detach(), z if z is not None else coords.new_empty(0))
         ctx.plan = plan
+        if plan is not None and any(ctx.needs_input_grad):
+            plan.users += 1  # released in backward; keeps the cache from recycling it under a live graph
         ctx.round_flag = round_flag
         ctx.meta = (first_idx, tuple(resolutions), bitwidth, tuple(latents.shape), F, need_dec, shift is not None,
                     A.shape[0])
@@ -166,6 +177,7 @@ class LatentHashGrid(torch.autograd.Function):
             gl, gA, gS = _lib.latent_backward_planned(ctx.plan, grad_output.contiguous(), z if need_dec else None,
                                                       first_idx, resolutions, bitwidth, A, C, F, rows,
                                                       ctx.round_flag, need_dec)
+            ctx.plan.users = max(0, ctx.plan.users - 1)
         else:
             gl, gA, gS = _lib.latent_backward(coords, grad_output.contiguous(), z if need_dec else None, first_idx,
                                               resolutions, bitwidth, A, C, F, rows, need_dec)

@@ -217,3 +217,35 @@ def test_latent_grid_api_uses_the_plan_and_matches_unplanned(lib, monkeypatch):
     assert rel_err(outs[0][1].cpu().numpy(), grid.codebook.grad.cpu().numpy()) <= BWD_TOL
     assert rel_err(outs[0][2].cpu().numpy(), grid.latent_dec.layers[0].scale.grad.cpu().numpy()) <= BWD_TOL
     assert rel_err(outs[0][3].cpu().numpy(), grid.latent_dec.layers[0].shift.grad.cpu().numpy()) <= BWD_TOL
+
+
+def test_plan_cache_recycles_allocations_for_changing_coordinates(lib, monkeypatch):
+    """Fresh coordinates every step (NeRF-like): the cache recycles plan objects instead of allocating."""
+    from shacira_b200 import grid_ops
+    c = _case(2, 8, 12, 16, 128, 20000, 1, 1, seed=21, kind="uniform")
+    lat, A, S = _dev(c["lat"]).requires_grad_(True), _dev(c["A"]), _dev(c["S"])
+    grid_ops.clear_plans()
+    monkeypatch.setattr(grid_ops, "PLAN_CACHE_SIZE", 2)
+    handles = set()
+    for step in range(6):
+        coords = torch.rand(20000, 2, device="cuda") * 2 - 1
+        f = grid_ops.latent_hashgrid(coords, lat, A, S, c["first"], c["res"], 12, True)
+        want, _ = lib.latent_forward(coords, lat.detach(), c["first"], c["res"], 12, A, S, 1, True, False)
+        assert torch.equal(f.detach(), want)
+        f.sum().backward()
+        handles.update(p.handle.value for p in grid_ops._plans.values())
+    assert len(grid_ops._plans) == 2 and len(handles) == 2   # two plan objects serve all six coordinate sets
+    # a plan that a live autograd graph still needs is never recycled under it
+    grid_ops.clear_plans()
+    pending = []
+    for step in range(4):
+        coords = torch.rand(20000, 2, device="cuda") * 2 - 1
+        pending.append((coords, grid_ops.latent_hashgrid(coords, lat, A, S, c["first"], c["res"], 12, True)))
+    lat.grad = None
+    pending[0][1].sum().backward()      # its plan left the cache two forwards ago
+    g_first = lat.grad.clone()
+    grid_ops.clear_plans()
+    lat.grad = None
+    grid_ops.latent_hashgrid(pending[0][0], lat, A, S, c["first"], c["res"], 12, True).sum().backward()
+    assert rel_err(g_first.cpu().numpy(), lat.grad.cpu().numpy()) <= 1e-6
+    grid_ops.clear_plans()
