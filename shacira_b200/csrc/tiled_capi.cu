@@ -15,6 +15,11 @@ struct shacira_plan {
     int device;
     void* block;     // one allocation: perm | coords_sorted | tile_off | cursor | counts | tile_id
     size_t block_bytes;
+    // node table of the last level configuration used with this plan (PlanView::node_tab)
+    int2* node_tab;
+    size_t node_tab_bytes;
+    int32_t node_stride, node_g, node_dim;
+    uint64_t node_sig;
     int32_t* perm;
     float* coords_sorted;
     int32_t* tile_off;
@@ -47,7 +52,42 @@ PlanView view_of(const shacira_plan* p) {
     v.n = p->n;
     v.g = p->g;
     v.ntiles = p->ntiles;
+    v.node_tab = p->node_tab;
+    v.node_stride = p->node_stride;
     return v;
+}
+
+int node_capacity(const shacira_plan* p, const LevelParams& lp, int cap_max);
+
+// The node table depends on the tile grid and the level configuration only. It is (re)built when either
+// changes -- once per fit -- with the largest node capacity any kernel uses, so that every kernel's staged
+// prefix of levels finds its slots in it. Allocation is synchronous: like plan creation it has to happen
+// before a CUDA-graph capture (any eager warm-up call does it).
+int ensure_node_table(shacira_plan* p, const LevelParams& lp, cudaStream_t s) {
+    uint64_t sig = 1469598103934665603ull;  // FNV-1a over everything the geometry depends on
+    auto mix = [&](uint64_t v) { sig = (sig ^ v) * 1099511628211ull; };
+    mix((uint64_t)lp.num_lods); mix(lp.hash_mask); mix(lp.dense_mask);
+    for (int l = 0; l < lp.num_lods; ++l) { mix((uint64_t)lp.res[l]); mix((uint64_t)lp.first[l]); mix((uint64_t)lp.rows[l]); }
+    const int cap = node_capacity(p, lp, smem_budget() / 4);
+    mix((uint64_t)cap);
+    if (p->node_tab && p->node_sig == sig && p->node_g == p->g && p->node_dim == p->dim) return SHACIRA_OK;
+    const size_t bytes = sizeof(int2) * (size_t)p->ntiles * cap;
+    if (!p->node_tab || p->node_tab_bytes < bytes) {
+        if (p->node_tab) cudaFree(p->node_tab);
+        p->node_tab = nullptr;
+        p->node_tab_bytes = 0;
+        cudaError_t e = cudaMalloc((void**)&p->node_tab, bytes);
+        if (e != cudaSuccess) return fail(SHACIRA_ERR_CUDA, "cudaMalloc(%zu) for the node table: %s", bytes, cudaGetErrorString(e));
+        p->node_tab_bytes = bytes;
+    }
+    if (p->dim == 2) plan_nodes_kernel<2><<<p->ntiles, kTileThreads, 0, s>>>(lp, p->g, cap, p->node_tab);
+    else plan_nodes_kernel<3><<<p->ntiles, kTileThreads, 0, s>>>(lp, p->g, cap, p->node_tab);
+    LAUNCHED();
+    p->node_stride = cap;
+    p->node_sig = sig;
+    p->node_g = p->g;
+    p->node_dim = p->dim;
+    return SHACIRA_OK;
 }
 
 // Upper bound of the node box of any tile, all levels that fit `cap_max` (coarse first, as the kernel does).
@@ -63,10 +103,12 @@ int node_capacity(const shacira_plan* p, const LevelParams& lp, int cap_max) {
 }
 
 template <int D, int C, int F>
-int launch_fwd(const shacira_plan* p, const float* lat, const LevelParams& lp, const float* A, const float* shift,
+int launch_fwd(shacira_plan* p, const float* lat, const LevelParams& lp, const float* A, const float* shift,
                int per_level, int round_flag, float* feats, cudaStream_t s) {
     const int nA = per_level ? lp.num_lods : 1;
     const int cap = node_capacity(p, lp, smem_budget() / (4 * C));
+    const int rc_tab = ensure_node_table(p, lp, s);
+    if (rc_tab) return rc_tab;
     const size_t smem = smem_pad(sizeof(float) * ((size_t)cap * C + nA * C * F + nA * F));
     latent_fwd_tiled_kernel<D, C, F><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), lat, lp, A, shift, per_level,
                                                                             round_flag, feats, cap);
@@ -75,7 +117,7 @@ int launch_fwd(const shacira_plan* p, const float* lat, const LevelParams& lp, c
 }
 
 template <int D, int C, int F>
-int launch_bwd(const shacira_plan* p, const float* g, const float* lat, const LevelParams& lp, const float* A,
+int launch_bwd(shacira_plan* p, const float* g, const float* lat, const LevelParams& lp, const float* A,
                int per_level, int round_flag, float* gl, float* gA, float* gS, cudaStream_t s) {
     const int nA = per_level ? lp.num_lods : 1;
     const bool dec = gA != nullptr || gS != nullptr;
@@ -88,6 +130,8 @@ int launch_bwd(const shacira_plan* p, const float* g, const float* lat, const Le
     const int rep = big ? ((kRepBudget / CA) & ~3) : 0;  // per accumulator channel
     const int cap = node_capacity(p, lp, (smem_budget() - rep * 4 * CA) / (4 * (CA + (dec ? C : 0))));
     const int cap_acc = cap + rep;
+    const int rc_tab = ensure_node_table(p, lp, s);
+    if (rc_tab) return rc_tab;
     constexpr int NW = kTileThreads / 32;
     size_t smem = sizeof(float) * ((size_t)cap_acc * CA + (dec ? (size_t)cap * C : 0) + nA * C * F);
     if (dec) smem += sizeof(float) * (size_t)(zp ? NW : 1) * lp.num_lods * (C * F + F);
@@ -206,10 +250,15 @@ int shacira_plan_create(int32_t dim, const float* coords, int64_t n, int32_t til
     if (!p) return fail(SHACIRA_ERR_CUDA, "out of host memory");
     p->block = nullptr;
     p->block_bytes = 0;
+    p->node_tab = nullptr;
+    p->node_tab_bytes = 0;
+    p->node_sig = 0;
+    p->node_g = p->node_dim = p->node_stride = 0;
     cudaGetDevice(&p->device);
     rc = plan_build(p, dim, coords, n, tile_points, (cudaStream_t)stream);
     if (rc != SHACIRA_OK) {
         if (p->block) cudaFree(p->block);
+        if (p->node_tab) cudaFree(p->node_tab);
         delete p;
         return rc;
     }
@@ -228,6 +277,7 @@ int shacira_plan_rebuild(shacira_plan_t* plan, int32_t dim, const float* coords,
 int shacira_plan_destroy(shacira_plan_t* plan) {
     if (!plan) return SHACIRA_OK;
     if (plan->block) cudaFree(plan->block);  // synchronises with outstanding work that uses the plan
+    if (plan->node_tab) cudaFree(plan->node_tab);
     delete plan;
     return SHACIRA_OK;
 }
@@ -263,10 +313,10 @@ int shacira_latent_forward_planned(const shacira_plan_t* plan, const float* late
     cudaStream_t s = (cudaStream_t)stream;
     if (plan->dim == 2) {
         T_DISPATCH_CF(latent_dim, feature_dim,
-                      (launch_fwd<2, kC, kF>(plan, latents, lp, A, shift, per_level, round_flag, feats, s)))
+                      (launch_fwd<2, kC, kF>(const_cast<shacira_plan*>(plan), latents, lp, A, shift, per_level, round_flag, feats, s)))
     }
     T_DISPATCH_CF(latent_dim, feature_dim,
-                  (launch_fwd<3, kC, kF>(plan, latents, lp, A, shift, per_level, round_flag, feats, s)))
+                  (launch_fwd<3, kC, kF>(const_cast<shacira_plan*>(plan), latents, lp, A, shift, per_level, round_flag, feats, s)))
 }
 
 int shacira_latent_backward_planned(const shacira_plan_t* plan, const float* grad_output, const float* latents,
@@ -289,11 +339,11 @@ int shacira_latent_backward_planned(const shacira_plan_t* plan, const float* gra
     if (zero_first) CUDA_OK(cudaMemsetAsync(grad_latents, 0, sizeof(float) * (size_t)table_rows * latent_dim, s));
     if (plan->dim == 2) {
         T_DISPATCH_CF(latent_dim, feature_dim,
-                      (launch_bwd<2, kC, kF>(plan, grad_output, latents, lp, A, per_level, round_flag, grad_latents,
+                      (launch_bwd<2, kC, kF>(const_cast<shacira_plan*>(plan), grad_output, latents, lp, A, per_level, round_flag, grad_latents,
                                              grad_A, grad_shift, s)))
     }
     T_DISPATCH_CF(latent_dim, feature_dim,
-                  (launch_bwd<3, kC, kF>(plan, grad_output, latents, lp, A, per_level, round_flag, grad_latents, grad_A,
+                  (launch_bwd<3, kC, kF>(const_cast<shacira_plan*>(plan), grad_output, latents, lp, A, per_level, round_flag, grad_latents, grad_A,
                                          grad_shift, s)))
 }
 

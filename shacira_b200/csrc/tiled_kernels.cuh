@@ -41,7 +41,13 @@ struct PlanView {
     int64_t n;
     int32_t g;                    // tiles per axis (power of two)
     int32_t ntiles;
+    // per (plan, level configuration): for every tile and staged node slot, the absolute table row (.x) and the
+    // level | kNodeInvalid (.y). Depends on the tile grid and the levels only -- not on coordinates or latents --
+    // so it is built once (plan_nodes_kernel) and turns the per-node index math of staging / flush into a load.
+    const int2* node_tab;         // [ntiles][node_stride]
+    int32_t node_stride;
 };
+constexpr int kNodeInvalid = 0x100;  // node outside its level: only ever carries weight 0
 
 // ---------------------------------------------------------------------------------------------
 // plan construction: tile id -> histogram -> scan -> scatter
@@ -426,9 +432,8 @@ __device__ __forceinline__ int level_of_slot(const TileGeom<D>& tg, int num_stag
     return a;
 }
 
-// Stage the (rounded) latents of every node of the tile's staged levels into shared memory. The slot
-// loop is flat over all levels and unrolled so that each thread has kStageUnroll independent gathers
-// in flight (a per-level loop would serialise one global-load latency per level).
+// Stage the (rounded) latents of every node of the tile's staged levels into shared memory: row index from the
+// plan's node table, then the gather; unrolled so that each thread has kStageUnroll independent chains in flight.
 #ifndef SHACIRA_STAGE_UNROLL
 #define SHACIRA_STAGE_UNROLL 4
 #endif
@@ -441,21 +446,19 @@ constexpr int kStageUnroll = SHACIRA_STAGE_UNROLL;
 #endif
 constexpr int kLv = SHACIRA_LV;  // levels per inner iteration (register blocking of the level loop): 4 or 2
 template <int D, int C>
-__device__ __forceinline__ void stage_nodes(const TileGeom<D>& tg, const LevelParams& lp,
+__device__ __forceinline__ void stage_nodes(const TileGeom<D>& tg, const int2* __restrict__ tab,
                                             const float* __restrict__ latents, int round_flag, float* s_nodes) {
     const int total = tg.total;
-    const int ns = __popc(tg.staged);
     for (int e0 = threadIdx.x; e0 < total; e0 += kTileThreads * kStageUnroll) {
-        float v[kStageUnroll][C];
+        int row[kStageUnroll];
 #pragma unroll
         for (int u = 0; u < kStageUnroll; ++u) {
             const int e = e0 + u * kTileThreads;
-            if (e < total) {
-                const int l = level_of_slot<D>(tg, ns, e);
-                const int row = node_row<D>(tg, lp, l, e - tg.off[l], true);
-                load_row<C>(latents + ((int64_t)lp.first[l] + row) * C, v[u]);
-            }
+            row[u] = (e < total) ? __ldg(&tab[e]).x : 0;
         }
+        float v[kStageUnroll][C];
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u) load_row<C>(latents + (int64_t)row[u] * C, v[u]);
 #pragma unroll
         for (int u = 0; u < kStageUnroll; ++u) {
             const int e = e0 + u * kTileThreads;
@@ -464,6 +467,28 @@ __device__ __forceinline__ void stage_nodes(const TileGeom<D>& tg, const LevelPa
                 for (int ch = 0; ch < C; ++ch) s_nodes[(size_t)e * C + ch] = round_flag ? rintf(v[u][ch]) : v[u][ch];
             }
         }
+    }
+}
+
+// Fills one tile's row of the node table (see PlanView::node_tab). One CTA per tile.
+template <int D>
+__global__ void __launch_bounds__(kTileThreads)
+plan_nodes_kernel(const __grid_constant__ LevelParams lp, int g, int cap, int2* __restrict__ node_tab) {
+    __shared__ TileGeom<D> tg;
+    int ti[D];
+    {
+        int r = blockIdx.x;
+#pragma unroll
+        for (int d = 0; d < D; ++d) { ti[d] = r % g; r /= g; }
+    }
+    tile_geometry<D>(tg, lp, ti, g, cap);
+    const int ns = __popc(tg.staged);
+    int2* tab = node_tab + (size_t)blockIdx.x * cap;
+    for (int e = threadIdx.x; e < tg.total; e += kTileThreads) {
+        const int l = level_of_slot<D>(tg, ns, e);
+        const int row = node_row<D>(tg, lp, l, e - tg.off[l], false);
+        const int inside = (row >= 0) ? row : lp.rows[l] - 1;  // a readable row for the staging gather
+        tab[e] = make_int2(lp.first[l] + inside, l | (row >= 0 ? 0 : kNodeInvalid));
     }
 }
 
@@ -494,7 +519,7 @@ latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, co
     for (int e = threadIdx.x; e < nA * C * F; e += kTileThreads) s_A[e] = A[e];
     for (int e = threadIdx.x; e < nA * F; e += kTileThreads) s_shift[e] = shift ? shift[e] : 0.0f;
     tile_geometry<D>(tg, lp, ti, pv.g, cap);
-    stage_nodes<D, C>(tg, lp, latents, round_flag, s_nodes);
+    stage_nodes<D, C>(tg, pv.node_tab + (size_t)tile * pv.node_stride, latents, round_flag, s_nodes);
     __syncthreads();
 
     for (int base = beg; base < end; base += kTileThreads * kPts) {
@@ -686,7 +711,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
         // latents for the decoder gradients (ZP: per-point z in pass 2; SG: q[node] at flush). Staged here, behind
         // pass 1, so that their gather latency overlaps the other warps' work instead of the kernel prologue.
         if (DEC && !staged_lat) {
-            stage_nodes<D, C>(tg, lp, latents, round_flag, s_lat);
+            stage_nodes<D, C>(tg, pv.node_tab + (size_t)tile * pv.node_stride, latents, round_flag, s_lat);
             staged_lat = true;
         }
         __syncthreads();
@@ -906,15 +931,17 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
         for (int e = 0; e < (SG ? C * F : 1); ++e) pA[e] = 0.0f;
         const int num_staged = __popc(tg.staged);
         const int total_nodes = tg.total;
-        // One thread per node over ALL staged levels at once (flat slot index, level by binary search): full lanes
-        // on the small coarse levels and no per-level loop overhead. With per-level decoders in scatter-g mode the
-        // partial sums must be kept per level, so that (rare) case walks level by level instead.
+        const int2* tab = pv.node_tab + (size_t)tile * pv.node_stride;
+        // One thread per node over ALL staged levels at once (flat slot index; level and table row come from the
+        // plan's node table): full lanes on the small coarse levels, no per-node index math. With per-level
+        // decoders in scatter-g mode the partial sums must be kept per level, so that (rare) case walks level by level.
         const bool by_level = SG && per_level;
         for (int lvl = 0; lvl < (by_level ? num_staged : 1); ++lvl) {
             const int e_begin = by_level ? tg.off[lvl] : 0;
             const int e_end = by_level ? ((lvl + 1 < num_staged) ? tg.off[lvl + 1] : total_nodes) : total_nodes;
             for (int e = e_begin + threadIdx.x; e < e_end; e += kTileThreads) {
-                const int l = by_level ? lvl : level_of_slot<D>(tg, num_staged, e);
+                const int2 ent = __ldg(&tab[e]);
+                const int l = ent.y & 0xff;
                 const int nloc = e - tg.off[l];
                 const float inv = s_inv[l];
                 const bool rep = tg.acc_mul[l] == 32;
@@ -939,10 +966,8 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
 #pragma unroll
                     for (int ch = 0; ch < CA; ++ch) gv[ch] = inv;
                 }
-                if (!any) continue;
-                const int row = node_row<D>(tg, lp, l, nloc, false);
-                if (row < 0) continue;
-                float* dst = grad_latents + ((int64_t)lp.first[l] + row) * C;
+                if (!any || (ent.y & kNodeInvalid)) continue;
+                float* dst = grad_latents + (int64_t)ent.x * C;
                 if constexpr (SG) {
                     const int la = per_level ? l : 0;
                     float qn[C], gl[C];
