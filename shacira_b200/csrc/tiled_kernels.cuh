@@ -470,6 +470,42 @@ __device__ __forceinline__ void stage_nodes(const TileGeom<D>& tg, const int2* _
     }
 }
 
+// Forward-kernel variant: the table rows of the thread's first kPre slots are requested at kernel entry, BEFORE the
+// tile geometry is known (they only depend on the tile id), so their latency hides behind the tile_off load, the
+// geometry and its barrier; the gathers of all kPre slots are then in flight together.
+constexpr int kPre = 8;
+__device__ __forceinline__ void prefetch_rows(const int2* __restrict__ tab, int stride, int (&pre)[kPre]) {
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+        const int e = threadIdx.x + u * kTileThreads;
+        pre[u] = (e < stride) ? __ldg(reinterpret_cast<const int*>(tab + e)) : 0;  // .x = absolute row
+    }
+}
+template <int D, int C>
+__device__ __forceinline__ void stage_nodes_prefetched(const TileGeom<D>& tg, const int2* __restrict__ tab,
+                                                       const int (&pre)[kPre], const float* __restrict__ latents,
+                                                       int round_flag, float* s_nodes) {
+    const int total = tg.total;
+    float v[kPre][C];
+#pragma unroll
+    for (int u = 0; u < kPre; ++u)
+        if (threadIdx.x + u * kTileThreads < total) load_row<C>(latents + (int64_t)pre[u] * C, v[u]);
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+        const int e = threadIdx.x + u * kTileThreads;
+        if (e < total) {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) s_nodes[(size_t)e * C + ch] = round_flag ? rintf(v[u][ch]) : v[u][ch];
+        }
+    }
+    for (int e = threadIdx.x + kPre * kTileThreads; e < total; e += kTileThreads) {  // larger node boxes
+        float w[C];
+        load_row<C>(latents + (int64_t)__ldg(&tab[e]).x * C, w);
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) s_nodes[(size_t)e * C + ch] = round_flag ? rintf(w[ch]) : w[ch];
+    }
+}
+
 // Fills one tile's row of the node table (see PlanView::node_tab). One CTA per tile.
 template <int D>
 __global__ void __launch_bounds__(kTileThreads)
@@ -516,10 +552,13 @@ latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, co
 #pragma unroll
         for (int d = 0; d < D; ++d) { ti[d] = r % pv.g; r /= pv.g; }
     }
+    const int2* tab = pv.node_tab + (size_t)tile * pv.node_stride;
+    int pre[kPre];
+    prefetch_rows(tab, pv.node_stride, pre);
     for (int e = threadIdx.x; e < nA * C * F; e += kTileThreads) s_A[e] = A[e];
     for (int e = threadIdx.x; e < nA * F; e += kTileThreads) s_shift[e] = shift ? shift[e] : 0.0f;
     tile_geometry<D>(tg, lp, ti, pv.g, cap);
-    stage_nodes<D, C>(tg, pv.node_tab + (size_t)tile * pv.node_stride, latents, round_flag, s_nodes);
+    stage_nodes_prefetched<D, C>(tg, tab, pre, latents, round_flag, s_nodes);
     __syncthreads();
 
     for (int base = beg; base < end; base += kTileThreads * kPts) {
