@@ -109,7 +109,8 @@ def clamped_psnr(pred, gt):
     return 20 * np.log10(255.0) - 10 * np.log10(max(mse, 1e-12))
 
 
-def fit(seed, impl, steps, dev, use_graph, noise_cpu):
+def fit(seed, impl, steps, dev, use_graph, noise_cpu, fused_mlp=False):
+    from shacira_b200 import grid_ops
     from shacira_b200.grids import LatentGrid
     torch.manual_seed(seed)
     grid = LatentGrid.from_geometric(feature_dim=1, num_lods=16, latent_dim=1, multiscale_type="cat", resolution_dim=2,
@@ -128,6 +129,8 @@ def fit(seed, impl, steps, dev, use_graph, noise_cpu):
     coords, gt = make_data(seed, dev)
     T = grid.codebook.shape[0]
     cap = dict(capturable=True) if use_graph else {}
+    if fused_mlp:
+        cap["fused"] = True   # one multi-tensor Adam kernel per group instead of ~10 elementwise launches
     groups = [dict(params=list(mlp.parameters()), lr=1e-3, weight_decay=0.0),
               dict(params=[grid.codebook], lr=2e-2, weight_decay=0.0),
               dict(params=[p for p in grid.latent_dec.parameters() if p.requires_grad], lr=1e-2, weight_decay=1e-2),
@@ -141,8 +144,11 @@ def fit(seed, impl, steps, dev, use_graph, noise_cpu):
     def train_step():
         opt.zero_grad(set_to_none=False)
         feats = grid.interpolate(coords, 0)
-        pred = mlp(feats)
-        rgb_loss = ((pred - gt) ** 2).mean()
+        if fused_mlp:   # MLP + MSE + all their gradients in one kernel
+            rgb_loss, pred = grid_ops.mlp_mse_loss(feats, gt, mlp)
+        else:
+            pred = mlp(feats)
+            rgb_loss = ((pred - gt) ** 2).mean()
         if impl == "ref":
             avg_bits, bits = grid.ent_loss(noise_buf)
         else:
@@ -211,6 +217,7 @@ def main():
     ap.add_argument("--images", type=int, default=1)
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--noise-cpu", action="store_true", help="draw the entropy noise with the CPU generator (parity runs)")
+    ap.add_argument("--fused-mlp", action="store_true", help="fused decoder MLP + MSE kernel (SURVEY 8 f-1) and fused Adam")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -223,7 +230,7 @@ def main():
     mine = dp.shard_units(args.images, rank, world)      # independent images: round-robin, no collective
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    results = [fit(s, args.impl, args.steps, dev, args.graph, args.noise_cpu) for s in mine]
+    results = [fit(s, args.impl, args.steps, dev, args.graph, args.noise_cpu, args.fused_mlp) for s in mine]
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     allres = dp.gather_results(dict(rank=rank, wall=wall, fits=results))
@@ -232,7 +239,7 @@ def main():
         fits = [f for r in allres for f in r["fits"]]
         ms = float(np.mean([f["ms_per_step"] for f in fits]))
         print(json.dumps({"workload": "Kodak-shape image INR fit (BASELINE cfg2/cfg3)", "impl": args.impl,
-                          "n_gpus": world, "images": args.images, "steps_per_fit": args.steps, "cuda_graph": args.graph,
+                          "n_gpus": world, "images": args.images, "steps_per_fit": args.steps, "cuda_graph": args.graph, "fused_mlp": args.fused_mlp,
                           "ms_per_step": ms, "psnr": [round(f["psnr"], 3) for f in fits], "bpp": [round(f["bpp"], 4) for f in fits],
                           "wall_s": wall,
                           "fits_per_hour_at_60000_steps": world * 3600.0 / (60000 * ms * 1e-3) if fits else None}), flush=True)

@@ -177,6 +177,20 @@ int shacira_quantize_symbols(const float* latents, int64_t table_rows, int32_t l
 int shacira_symbol_histogram(const float* latents, int64_t table_rows, int32_t latent_dim, const int32_t* lo,
                              int32_t num_bins, int64_t* counts, shacira_stream_t stream);
 
+/* ---- fused decoder MLP + image loss ----------------------- */
+/* The reference's NeuralImage decoder (BasicDecoder: Linear(in,16) ReLU Linear(16,16) ReLU Linear(16,3), bias;
+ * wisp/models/nefs/image.py:109-120, wisp/models/decoders/basic_decoders.py:60-100) applied to the grid
+ * features, the loss ((pred - target)^2).mean() (wisp/trainers/image_trainer.py:298-300), and ALL gradients in
+ * one pass: grad_features[n, in_dim] = dL/dfeatures (feed it to shacira_latent_backward*), pred[n, 3] (nullable).
+ * Weights use the torch.nn.Linear layout W[out][in]. `out` is a device buffer of
+ * 8 + 4*(16*in + 16 + 256 + 16 + 48 + 3) bytes, written by the call:
+ *   double sum of squared errors (loss = sum / (3 n)) | float dL/dW1 | db1 | dW2 | db2 | dW3 | db3.
+ * in_dim in {16, 24, 32}, hidden_dim = 16, out_dim = 3. */
+int shacira_mlp_mse_step(const float* features, const float* target, int64_t n, int32_t in_dim, int32_t hidden_dim,
+                         int32_t out_dim, const float* W1, const float* b1, const float* W2, const float* b2,
+                         const float* W3, const float* b3, float* grad_features, float* pred, void* out,
+                         shacira_stream_t stream);
+
 /* ---- latent bitstream (host side) ---------------------------------------------------- */
 /* Static arithmetic coder over dense symbol ranks 0..num_symbols-1 with 16-bit cumulative
  * frequencies cdf[num_symbols+1] (cdf[0] = 0, strictly increasing, cdf[num_symbols] = 65536).

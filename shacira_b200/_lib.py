@@ -49,6 +49,7 @@ SIGNATURES = {
     "shacira_entropy_scratch_bytes": (_i64, [_i32, _i32]),
     "shacira_quantize_symbols": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "shacira_symbol_histogram": (ctypes.c_int, [_vp, _i64, _i32, _c_int32_p, _i32, _vp, _vp]),
+    "shacira_mlp_mse_step": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "shacira_ac_encode": (_i64, [_vp, _i64, _vp, _i32, _vp, _i64]),
     "shacira_ac_decode": (ctypes.c_int, [_vp, _i64, _vp, _i32, _vp, _i64]),
     "shacira_latent_step_host": (ctypes.c_int, [_i32, _vp, _i64, _vp, _i64, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
@@ -391,6 +392,30 @@ def entropy_bits(latents, noise, params, num_layers, first_idx=None, want_grads=
                                         _ptr(bits), _ptr(gl), _ptr(gp), _ptr(scratch),
                                         scratch.numel() if scratch is not None else 0, _stream()))
     return bits, gl, gp
+
+
+def mlp_mse_step(features, target, W1, b1, W2, b2, W3, b3, want_pred=False):
+    """Fused decoder MLP + MSE: returns (loss scalar tensor, grad_features, pred | None, grads dict)."""
+    lib = load()
+    features, target = _f32c(features, "features"), _f32c(target, "target")
+    ws = [_f32c(t, "weights") for t in (W1, b1, W2, b2, W3, b3)]
+    n, IN = features.shape
+    H, OUT = ws[0].shape[0], ws[4].shape[0]
+    dev = features.device
+    gx = torch.empty_like(features)
+    pred = torch.empty((n, OUT), dtype=torch.float32, device=dev) if want_pred else None
+    n_par = H * IN + H + H * H + H + OUT * H + OUT
+    out = torch.empty(2 + n_par, dtype=torch.float32, device=dev)  # 8-byte loss + packed gradients
+    with torch.cuda.device(dev):
+        _check(lib.shacira_mlp_mse_step(_ptr(features), _ptr(target), n, IN, H, OUT, *[_ptr(w) for w in ws], _ptr(gx),
+                                        _ptr(pred), _ptr(out), _stream()))
+    sse = out[:2].view(torch.float64)[0]
+    loss = (sse / (n * OUT)).to(torch.float32)
+    g = out[2:]
+    sizes = [H * IN, H, H * H, H, OUT * H, OUT]
+    parts = torch.split(g, sizes)
+    grads = [parts[0].view(H, IN), parts[1], parts[2].view(H, H), parts[3], parts[4].view(OUT, H), parts[5]]
+    return loss, gx, pred, grads
 
 
 def quantize_symbols(latents, want_symbols=True):

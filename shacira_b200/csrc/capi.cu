@@ -6,6 +6,7 @@
 #include "capi_internal.h"
 #include "entropy_kernels.cuh"
 #include "hashgrid_kernels.cuh"
+#include "mlp_kernels.cuh"
 
 using namespace shacira;
 
@@ -127,6 +128,34 @@ int launch_latent_bwd(const float* coords, int64_t n, const float* g, const floa
     }
 
 }  // namespace
+
+namespace {
+template <int IN>
+int launch_mlp(const float* x, const float* gt, int64_t n, const float* W1, const float* b1, const float* W2,
+               const float* b2, const float* W3, const float* b3, float* gx, float* pred, void* out, cudaStream_t s) {
+    using Smem = MlpSmem<IN, 16, 3>;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_OK(cudaFuncSetAttribute(mlp_mse_step_kernel<IN, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(Smem)));
+        configured = true;
+    }
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t out_bytes = 8 + sizeof(float) * (16 * IN + 16 + 16 * 16 + 16 + 3 * 16 + 3);
+    CUDA_OK(cudaMemsetAsync(out, 0, out_bytes, s));
+    int64_t warps = (n + 31) / 32;
+    int64_t blocks = (warps + kMlpWarps - 1) / kMlpWarps;
+    const int64_t cap = (int64_t)sms * 2;  // persistent: 2 CTAs per SM fit the shared memory
+    if (blocks > cap) blocks = cap;
+    const float scale = (float)(2.0 / ((double)n * 3.0));
+    mlp_mse_step_kernel<IN, 16, 3><<<(int)blocks, kMlpThreads, sizeof(Smem), s>>>(
+        x, gt, n, W1, b1, W2, b2, W3, b3, scale, gx, pred, (double*)out, (float*)((char*)out + 8));
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+}  // namespace
+
 
 extern "C" {
 
@@ -367,6 +396,25 @@ int shacira_symbol_histogram(const float* latents, int64_t table_rows, int32_t l
     cudaFreeAsync(d_lo, s);
     if (le != cudaSuccess) return fail(SHACIRA_ERR_CUDA, "histogram launch: %s", cudaGetErrorString(le));
     return SHACIRA_OK;
+}
+
+// ---- fused decoder MLP + MSE ------------------------------------------------------------
+int shacira_mlp_mse_step(const float* features, const float* target, int64_t n, int32_t in_dim, int32_t hidden_dim,
+                         int32_t out_dim, const float* W1, const float* b1, const float* W2, const float* b2,
+                         const float* W3, const float* b3, float* grad_features, float* pred, void* out,
+                         shacira_stream_t stream) {
+    if (!features || !target || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !grad_features || !out)
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "mlp_mse_step: NULL argument");
+    if (n <= 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "mlp_mse_step: n must be positive");
+    if (hidden_dim != 16 || out_dim != 3)
+        return fail(SHACIRA_ERR_UNSUPPORTED, "mlp_mse_step: hidden %d / out %d (compiled: 16 / 3)", hidden_dim, out_dim);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (in_dim) {
+        case 16: return launch_mlp<16>(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
+        case 24: return launch_mlp<24>(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
+        case 32: return launch_mlp<32>(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
+        default: return fail(SHACIRA_ERR_UNSUPPORTED, "mlp_mse_step: in_dim %d not in {16,24,32}", in_dim);
+    }
 }
 
 // ---- latent bitstream (host) ---------------------------------------------------------------

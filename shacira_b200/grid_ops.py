@@ -216,3 +216,34 @@ class EntropyBits(torch.autograd.Function):
 def entropy_bits(latents, noise, params, num_layers, first_idx=None):
     fi = _host_ints(first_idx) if first_idx is not None else None
     return EntropyBits.apply(latents, noise, params, int(num_layers), fi)
+
+
+class FusedMLPMSE(torch.autograd.Function):
+    """decoder MLP (Linear-ReLU-Linear-ReLU-Linear) + ((pred - target)**2).mean() in one
+    kernel that also produces every gradient; backward only scales them by the upstream scalar."""
+
+    @staticmethod
+    def forward(ctx, features, target, W1, b1, W2, b2, W3, b3, want_pred):
+        loss, gx, pred, grads = _lib.mlp_mse_step(features, target, W1, b1, W2, b2, W3, b3, want_pred)
+        ctx.save_for_backward(gx, *grads)
+        if pred is None:
+            pred = features.new_empty(0)
+        ctx.mark_non_differentiable(pred)
+        return loss, pred
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_pred):
+        gx, gW1, gb1, gW2, gb2, gW3, gb3 = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        s = grad_loss
+        return (gx * s if need[0] else None, None, gW1 * s if need[2] else None, gb1 * s if need[3] else None,
+                gW2 * s if need[4] else None, gb2 * s if need[5] else None, gW3 * s if need[6] else None,
+                gb3 * s if need[7] else None, None)
+
+
+def mlp_mse_loss(features, target, mlp, want_pred=False):
+    """`mlp`: nn.Sequential(Linear(in,16), ReLU, Linear(16,16), ReLU, Linear(16,3)) (the reference's image decoder).
+    Returns (mse loss, pred [N,3] or an empty tensor)."""
+    l1, l2, l3 = mlp[0], mlp[2], mlp[4]
+    return FusedMLPMSE.apply(features.contiguous(), target.contiguous(), l1.weight, l1.bias, l2.weight, l2.bias,
+                             l3.weight, l3.bias, bool(want_pred))
