@@ -142,7 +142,7 @@ def fit(seed, impl, steps, dev, use_graph, noise_cpu, fused_mlp=False):
     out = {}
 
     def train_step():
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad(set_to_none=use_graph)   # captured step: gradients are re-created from the graph's pool, no fills
         feats = grid.interpolate(coords, 0)
         if fused_mlp:   # MLP + MSE + all their gradients in one kernel
             rgb_loss, pred = grid_ops.mlp_mse_loss(feats, gt, mlp)

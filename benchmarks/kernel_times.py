@@ -63,9 +63,20 @@ def main():
         _lib._check(lib.shacira_entropy_bits(p(lat), p(noise), T, 1, p(prob), 2, fi, L, p(bits), p(egl), p(egp),
                                              p(scratch), scratch.numel(), st))
 
+    import torch.nn as nn
+    torch.manual_seed(0)
+    mlp = nn.Sequential(nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 3)).to(dev)
+    gt = torch.rand(n, 3, device=dev)
+    mgx = torch.empty((n, L), device=dev)
+    mout = torch.empty(2 + 16 * 16 + 16 + 256 + 16 + 48 + 3, device=dev)
+    mw = [mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias, mlp[4].weight, mlp[4].bias]
+
+    def mlpk(s, st):
+        _lib._check(lib.shacira_mlp_mse_step(p(s["feats"]), p(gt), n, 16, 16, 3, *[p(w) for w in mw], p(mgx), None, p(mout), st))
+
     out = {}
     only_ent = bool(os.environ.get("ONLY_ENT"))
-    for name, fn in ((("entropy_fwd_bwd", ent),) if only_ent else (("entropy_fwd_bwd", ent), ("fwd_tiled", fwd), ("bwd_tiled_dec", bwd), ("bwd_tiled_nodec", lambda s, st: bwd(s, st, False)),
+    for name, fn in ((("entropy_fwd_bwd", ent),) if only_ent else (("entropy_fwd_bwd", ent), ("mlp_mse_step", mlpk), ("fwd_tiled", fwd), ("bwd_tiled_dec", bwd), ("bwd_tiled_nodec", lambda s, st: bwd(s, st, False)),
                      ("fwd_pointparallel", fwd_pp), ("bwd_pointparallel", bwd_pp),
                      ("step_tiled", lambda s, st: (fwd(s, st), bwd(s, st))))):
         stream = torch.cuda.Stream()

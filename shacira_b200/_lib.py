@@ -411,11 +411,12 @@ def mlp_mse_step(features, target, W1, b1, W2, b2, W3, b3, want_pred=False):
                                         _ptr(pred), _ptr(out), _stream()))
     sse = out[:2].view(torch.float64)[0]
     loss = (sse / (n * OUT)).to(torch.float32)
-    g = out[2:]
-    sizes = [H * IN, H, H * H, H, OUT * H, OUT]
-    parts = torch.split(g, sizes)
-    grads = [parts[0].view(H, IN), parts[1], parts[2].view(H, H), parts[3], parts[4].view(OUT, H), parts[5]]
-    return loss, gx, pred, grads
+    return loss, gx, pred, out[2:]  # packed gradients: W1 | b1 | W2 | b2 | W3 | b3
+
+
+def split_mlp_grads(packed, IN, H, OUT):
+    parts = torch.split(packed, [H * IN, H, H * H, H, OUT * H, OUT])
+    return [parts[0].view(H, IN), parts[1], parts[2].view(H, H), parts[3], parts[4].view(OUT, H), parts[5]]
 
 
 def quantize_symbols(latents, want_symbols=True):

@@ -224,8 +224,9 @@ class FusedMLPMSE(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, features, target, W1, b1, W2, b2, W3, b3, want_pred):
-        loss, gx, pred, grads = _lib.mlp_mse_step(features, target, W1, b1, W2, b2, W3, b3, want_pred)
-        ctx.save_for_backward(gx, *grads)
+        loss, gx, pred, packed = _lib.mlp_mse_step(features, target, W1, b1, W2, b2, W3, b3, want_pred)
+        ctx.save_for_backward(gx, packed)
+        ctx.dims = (features.shape[1], W1.shape[0], W3.shape[0])
         if pred is None:
             pred = features.new_empty(0)
         ctx.mark_non_differentiable(pred)
@@ -233,12 +234,13 @@ class FusedMLPMSE(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_pred):
-        gx, gW1, gb1, gW2, gb2, gW3, gb3 = ctx.saved_tensors
+        gx, packed = ctx.saved_tensors
         need = ctx.needs_input_grad
-        s = grad_loss
-        return (gx * s if need[0] else None, None, gW1 * s if need[2] else None, gb1 * s if need[3] else None,
-                gW2 * s if need[4] else None, gb2 * s if need[5] else None, gW3 * s if need[6] else None,
-                gb3 * s if need[7] else None, None)
+        # two kernels in total: the feature gradient and ALL weight gradients (packed) times the upstream scalar
+        g = _lib.split_mlp_grads(packed * grad_loss, *ctx.dims) if any(need[2:8]) else [None] * 6
+        return (gx * grad_loss if need[0] else None, None, g[0] if need[2] else None, g[1] if need[3] else None,
+                g[2] if need[4] else None, g[3] if need[5] else None, g[4] if need[6] else None,
+                g[5] if need[7] else None, None)
 
 
 def mlp_mse_loss(features, target, mlp, want_pred=False):
