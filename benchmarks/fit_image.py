@@ -131,8 +131,12 @@ def fit(seed, impl, steps, dev, use_graph, noise_cpu, fused_mlp=False):
     cap = dict(capturable=True) if use_graph else {}
     if fused_mlp:
         cap["fused"] = True   # one multi-tensor Adam kernel per group instead of ~10 elementwise launches
-    groups = [dict(params=list(mlp.parameters()), lr=1e-3, weight_decay=0.0),
-              dict(params=[grid.codebook], lr=2e-2, weight_decay=0.0),
+    table_opt = None
+    if fused_mlp and impl == "ours":
+        from shacira_b200._lib import TableAdam
+        table_opt = TableAdam(grid.codebook, lr=2e-2)     # one kernel for the 375 k-row table
+    groups = [dict(params=list(mlp.parameters()), lr=1e-3, weight_decay=0.0)] + \
+             ([] if table_opt else [dict(params=[grid.codebook], lr=2e-2, weight_decay=0.0)]) + [
               dict(params=[p for p in grid.latent_dec.parameters() if p.requires_grad], lr=1e-2, weight_decay=1e-2),
               dict(params=list(grid.prob_model.parameters()), lr=1e-4, weight_decay=1e-2)]
     opt = torch.optim.Adam(groups, eps=1e-8, **cap)
@@ -158,6 +162,9 @@ def fit(seed, impl, steps, dev, use_graph, noise_cpu, fused_mlp=False):
         loss = rgb_loss + lam * avg_bits
         loss.backward()
         opt.step()
+        if table_opt is not None:
+            table_opt.step()
+            grid.codebook.grad = None
         out["pred"], out["rgb_loss"], out["bits"] = pred.detach(), rgb_loss.detach(), bits.detach()
 
     def host_side(it):

@@ -191,6 +191,14 @@ int shacira_mlp_mse_step(const float* features, const float* target, int64_t n, 
                          const float* W3, const float* b3, float* grad_features, float* pred, void* out,
                          shacira_stream_t stream);
 
+/* ---- fused Adam over the latent table ------------------------ */
+/* torch.optim.Adam semantics (L2 weight decay added to the gradient, bias correction, eps outside the sqrt) for
+ * ONE float32 tensor in place; `step` is a device float counter (starts at 0) that the call advances, so the
+ * launch is CUDA-graph capturable. zero_grad != 0 also clears the gradient. */
+int shacira_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, float* step, int32_t zero_grad,
+                      shacira_stream_t stream);
+
 /* ---- latent bitstream (host side) ---------------------------------------------------- */
 /* Static arithmetic coder over dense symbol ranks 0..num_symbols-1 with 16-bit cumulative
  * frequencies cdf[num_symbols+1] (cdf[0] = 0, strictly increasing, cdf[num_symbols] = 65536).

@@ -50,6 +50,7 @@ SIGNATURES = {
     "shacira_quantize_symbols": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "shacira_symbol_histogram": (ctypes.c_int, [_vp, _i64, _i32, _c_int32_p, _i32, _vp, _vp]),
     "shacira_mlp_mse_step": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "shacira_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _i32, _vp]),
     "shacira_ac_encode": (_i64, [_vp, _i64, _vp, _i32, _vp, _i64]),
     "shacira_ac_decode": (ctypes.c_int, [_vp, _i64, _vp, _i32, _vp, _i64]),
     "shacira_latent_step_host": (ctypes.c_int, [_i32, _vp, _i64, _vp, _i64, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
@@ -491,3 +492,25 @@ def ac_decode(stream, cdf, n):
     out = np.empty(n, dtype=np.int16)
     _check(lib.shacira_ac_decode(buf.ctypes.data, buf.size, cdf.ctypes.data, cdf.size - 1, out.ctypes.data, n))
     return out
+
+
+class TableAdam:
+    """Adam for ONE large float32 tensor (the latent table) with torch.optim.Adam semantics, one kernel per step
+    (SURVEY section 8 row f-4). State lives on the device; `step()` is CUDA-graph capturable."""
+
+    def __init__(self, param, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.param = param
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
+        self.exp_avg = torch.zeros_like(param)
+        self.exp_avg_sq = torch.zeros_like(param)
+        self.step_count = torch.zeros((), dtype=torch.float32, device=param.device)
+
+    def step(self, zero_grad=False):
+        p = self.param
+        if p.grad is None:
+            return
+        g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+        with torch.cuda.device(p.device):
+            _check(load().shacira_adam_step(_ptr(p.data), _ptr(g), _ptr(self.exp_avg), _ptr(self.exp_avg_sq), p.numel(),
+                                            self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                            _ptr(self.step_count), 1 if zero_grad else 0, _stream()))

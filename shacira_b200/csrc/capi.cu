@@ -357,6 +357,21 @@ int64_t shacira_entropy_scratch_bytes(int32_t latent_dim, int32_t num_lods) {
     return ((4 * blocks * P + 255) & ~(int64_t)255) + 256;
 }
 
+int shacira_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, float* step, int32_t zero_grad,
+                      shacira_stream_t stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !step) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "adam_step: NULL argument");
+    if (n <= 0) return SHACIRA_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t blocks = (n + 1023) / 1024;
+    adam_step_kernel<<<(int)blocks, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                                 step, zero_grad, grad);
+    LAUNCHED();
+    adam_advance_kernel<<<1, 1, 0, s>>>(step);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
 int shacira_quantize_symbols(const float* latents, int64_t table_rows, int32_t latent_dim, int16_t* symbols,
                              int32_t* minmax, shacira_stream_t stream) {
     if (!latents || !minmax) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "latents/minmax is NULL");

@@ -59,3 +59,21 @@ def test_fused_mlp_rejects_other_shapes(lib):
     mlp = nn.Sequential(nn.Linear(16, 32), nn.ReLU(), nn.Linear(32, 32), nn.ReLU(), nn.Linear(32, 3)).cuda()
     with pytest.raises(lib.ShaciraError):
         grid_ops.mlp_mse_loss(torch.zeros(8, 16, device="cuda"), torch.zeros(8, 3, device="cuda"), mlp)
+
+
+def test_table_adam_matches_torch_adam(lib):
+    from shacira_b200._lib import TableAdam
+    torch.manual_seed(0)
+    for n, wd in ((374612, 0.0), (1001, 0.01)):
+        p_ref = torch.nn.Parameter(torch.randn(n, 1, device="cuda"))
+        p_our = torch.nn.Parameter(p_ref.detach().clone())
+        ref = torch.optim.Adam([p_ref], lr=2e-2, weight_decay=wd)
+        our = TableAdam(p_our, lr=2e-2, weight_decay=wd)
+        for it in range(5):
+            g = torch.randn(n, 1, device="cuda") * (10.0 ** (it - 2))
+            p_ref.grad = g.clone()
+            p_our.grad = g.clone()
+            ref.step()
+            our.step()
+        assert rel_err(p_our.detach().cpu().numpy(), p_ref.detach().cpu().numpy()) <= 1e-6
+        assert float(our.step_count) == 5.0
