@@ -4,6 +4,7 @@
 
 #include "arith_coder.inl"
 #include "capi_internal.h"
+#include "coarse_kernels.cuh"
 #include "entropy_kernels.cuh"
 #include "hashgrid_kernels.cuh"
 #include "mlp_kernels.cuh"
@@ -81,12 +82,100 @@ int launch_plain_fwd(const float* coords, int64_t n, const float* table, const L
     LAUNCHED();
     return SHACIRA_OK;
 }
+// Coarse dense levels go through shared memory (coarse_kernels.cuh) when the batch is large enough for their
+// same-address global adds to serialise; SHACIRA_COARSE_MAX_SLABS=0 turns the path off (tuning / A-B runs).
+inline int coarse_max_slabs() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SHACIRA_COARSE_MAX_SLABS");
+        v = e ? atoi(e) : 1;  // measured at the NeRF shape: whole-level jobs pay, slabbed levels do not
+        if (v < 0) v = 0;
+    }
+    return v;
+}
+inline int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}
+struct SideStream {
+    int dev = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int ensure() {
+        int d = 0;
+        CUDA_OK(cudaGetDevice(&d));
+        if (d == dev) return SHACIRA_OK;
+        CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        dev = d;
+        return SHACIRA_OK;
+    }
+};
+inline SideStream& side_stream() {
+    thread_local SideStream ss;
+    return ss;
+}
+inline int join_side_stream(cudaStream_t s) {
+    CUDA_OK(cudaStreamWaitEvent(s, side_stream().join, 0));
+    return SHACIRA_OK;
+}
+template <int D, int C, int F, bool LATENT>
+int launch_coarse_bwd(const float* coords, int64_t n, const float* g, const LevelParams& lp, const float* A,
+                      int per_level, float* gt, cudaStream_t s, uint32_t& mask, bool& pending_join) {
+    mask = 0;
+    pending_join = false;
+    if (n < 65536 || coarse_max_slabs() == 0) return SHACIRA_OK;
+    CoarseJobs jobs;
+    constexpr int NV = LATENT ? C : F;
+    const uint32_t m = plan_coarse_jobs(D, lp, NV, n, sm_count(), coarse_max_slabs(), jobs);
+    if (!m) return SHACIRA_OK;
+    const size_t smem = coarse_smem_bytes(jobs, NV);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUDA_OK(cudaFuncSetAttribute(coarse_bwd_kernel<D, C, F, LATENT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(float) * kCoarseBudgetFloats)));
+        configured = sizeof(float) * kCoarseBudgetFloats;
+    }
+    // The coarse kernel is bound by shared-memory CAS, the point-parallel kernel by L2 atomics: fork a side stream so
+    // that both run at once (one coarse CTA per SM is placed first, the other kernel fills the rest of the SM).
+    // Event fork/join composes with stream capture (the side stream joins the caller's capture).
+    static const bool fork = [] { const char* e = getenv("SHACIRA_COARSE_FORK"); return !e || atoi(e) != 0; }();
+    if (!fork) {  // A/B runs: same stream, the two kernels serialise
+        coarse_bwd_kernel<D, C, F, LATENT><<<coarse_total_ctas(jobs), kCoarseThreads, smem, s>>>(
+            coords, n, g, lp, jobs, A, per_level, gt);
+        LAUNCHED();
+        mask = m;
+        return SHACIRA_OK;
+    }
+    SideStream& ss = side_stream();
+    if (int rc = ss.ensure()) return rc;
+    CUDA_OK(cudaEventRecord(ss.fork, s));
+    CUDA_OK(cudaStreamWaitEvent(ss.stream, ss.fork, 0));
+    coarse_bwd_kernel<D, C, F, LATENT><<<coarse_total_ctas(jobs), kCoarseThreads, smem, ss.stream>>>(
+        coords, n, g, lp, jobs, A, per_level, gt);
+    LAUNCHED();
+    CUDA_OK(cudaEventRecord(ss.join, ss.stream));
+    pending_join = true;
+    mask = m;
+    return SHACIRA_OK;
+}
 template <int D, int F>
 int launch_plain_bwd(const float* coords, int64_t n, const float* g, const LevelParams& lp, float* gt,
                      cudaStream_t s) {
-    hashgrid_bwd_kernel<D, F><<<grid_for(n, kBlock), kBlock, 0, s>>>(coords, n, g, lp, gt);
+    uint32_t skip = 0;
+    bool join = false;
+    int rc = launch_coarse_bwd<D, F, F, false>(coords, n, g, lp, nullptr, 0, gt, s, skip, join);
+    if (rc) return rc;
+    hashgrid_bwd_kernel<D, F><<<grid_for(n, kBlock), kBlock, 0, s>>>(coords, n, g, lp, skip, gt);
     LAUNCHED();
-    return SHACIRA_OK;
+    return join ? join_side_stream(s) : SHACIRA_OK;
 }
 template <int D, int C, int F>
 int launch_latent_fwd(const float* coords, int64_t n, const float* lat, const LevelParams& lp, const float* A,
@@ -104,10 +193,14 @@ int launch_latent_bwd(const float* coords, int64_t n, const float* g, const floa
                       const float* A, int per_level, float* gl, float* gA, float* gS, cudaStream_t s) {
     const int nA = per_level ? lp.num_lods : 1;
     const size_t smem = sizeof(float) * (size_t)(nA * C * F + lp.num_lods * C * F + lp.num_lods * F);
-    latent_bwd_kernel<D, C, F><<<grid_for(n, kBlock), kBlock, smem, s>>>(coords, n, g, zsave, lp, A, per_level, gl,
-                                                                          gA, gS);
+    uint32_t skip = 0;
+    bool join = false;
+    int rc = launch_coarse_bwd<D, C, F, true>(coords, n, g, lp, A, per_level, gl, s, skip, join);
+    if (rc) return rc;
+    latent_bwd_kernel<D, C, F><<<grid_for(n, kBlock), kBlock, smem, s>>>(coords, n, g, zsave, lp, A, per_level, skip,
+                                                                          gl, gA, gS);
     LAUNCHED();
-    return SHACIRA_OK;
+    return join ? join_side_stream(s) : SHACIRA_OK;
 }
 
 #define DISPATCH_F(D_, F_, CALL)                                                                   \

@@ -80,7 +80,7 @@ hashgrid_fwd_kernel(const float* __restrict__ coords, int64_t n, const float* __
 template <int D, int F>
 __global__ void __launch_bounds__(kBlock)
 hashgrid_bwd_kernel(const float* __restrict__ coords, int64_t n, const float* __restrict__ grad_out,
-                    const __grid_constant__ LevelParams lp, float* __restrict__ grad_table) {
+                    const __grid_constant__ LevelParams lp, uint32_t skip_mask, float* __restrict__ grad_table) {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= n) return;
     double t[D];
@@ -91,6 +91,7 @@ hashgrid_bwd_kernel(const float* __restrict__ coords, int64_t n, const float* __
     const bool vec_ok = (F == 1) || ((L * F) % (F >= 4 ? 4 : F) == 0);
 #pragma unroll 2
     for (int l = 0; l < L; ++l) {
+        if ((skip_mask >> l) & 1u) continue;  // level accumulated in shared memory by coarse_bwd_kernel
         Corners<D> c;
         corners<D>(t, lp, l, c);
         float g[F];
@@ -238,7 +239,7 @@ template <int D, int C, int F>
 __global__ void __launch_bounds__(kBlock)
 latent_bwd_kernel(const float* __restrict__ coords, int64_t n, const float* __restrict__ grad_out,
                   const float* __restrict__ zsave, const __grid_constant__ LevelParams lp,
-                  const float* __restrict__ A, int per_level, float* __restrict__ grad_latents,
+                  const float* __restrict__ A, int per_level, uint32_t skip_mask, float* __restrict__ grad_latents,
                   float* __restrict__ grad_A, float* __restrict__ grad_shift) {
     extern __shared__ float s_mem[];  // A [nA*C*F] | gA [L*C*F] | gS [L*F]
     const int L = lp.num_lods;
@@ -262,6 +263,9 @@ latent_bwd_kernel(const float* __restrict__ coords, int64_t n, const float* __re
     const bool vec_z = (C == 1) || ((L * C) % (C >= 4 ? 4 : C) == 0);
 #pragma unroll 2
     for (int l = 0; l < L; ++l) {
+        // levels accumulated in shared memory by coarse_bwd_kernel: only the decoder gradients remain here
+        const bool scatter = !((skip_mask >> l) & 1u);
+        if (!scatter && !want_dec) continue;
         float g[F];
 #pragma unroll
         for (int j = 0; j < F; ++j) g[j] = 0.0f;
@@ -272,6 +276,8 @@ latent_bwd_kernel(const float* __restrict__ coords, int64_t n, const float* __re
 #pragma unroll
                 for (int j = 0; j < F; ++j) g[j] = __ldg(g_row + l * F + j);
             }
+        }
+        if (live && scatter) {
             Corners<D> c;
             corners<D>(t, lp, l, c);
             const int la = per_level ? l : 0;

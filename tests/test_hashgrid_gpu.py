@@ -205,3 +205,44 @@ def test_hashgrid_module(lib):
     assert grid.interpolate(coords, 0).shape == (5, 40, 2)
     out.sum().backward()
     assert grid.codebook.grad is not None and grid.size()[1] == grid.codebook.numel() * 32
+
+
+# ---- large batches: the coarse dense levels are accumulated in shared memory (coarse_kernels.cuh) ---------
+COARSE_CASES = [
+    # dim, L, bw, rmin, rmax, n, F
+    (3, 16, 19, 16, 2048, 1 << 17, 2),   # BASELINE cfg4 grid: 5 dense levels, levels 3 and 4 cut into slabs
+    (3, 8, 16, 16, 128, 1 << 16, 4),
+    (3, 4, 22, 16, 40, 70001, 1),        # every level dense, ragged n
+    (2, 16, 16, 16, 512, 1 << 17, 2),    # 2D point-parallel path: 12 dense levels, slabs along y
+    (2, 8, 19, 16, 700, 1 << 16, 2),     # dense levels with res >= 257 (zero-weight corner past the level)
+]
+
+
+@pytest.mark.parametrize("dim,L,bw,rmin,rmax,n,F", COARSE_CASES)
+def test_plain_backward_large_batch_matches_oracle(lib, dim, L, bw, rmin, rmax, n, F):
+    c = make_case(dim, L, bw, rmin, rmax, n, F, seed=dim * 1000 + F + 3, coord_kind="uniform")
+    want = oracle.backward(c["coords"], c["grad_out"], c["T"], c["first_idx"], c["resolutions"], bw, F)
+    got = lib.hashgrid_backward(_dev(c["coords"]), _dev(c["grad_out"]), c["first_idx"], c["resolutions"], bw, F,
+                                c["T"]).cpu().numpy()
+    assert rel_err(got, want) <= BWD_TOL
+    # per level too: a coarse level must not hide behind the largest gradient of the whole table
+    bounds = list(c["first_idx"]) + [c["T"]]
+    for l in range(L):
+        a, b = bounds[l], bounds[l + 1]
+        assert rel_err(got[a:b], want[a:b]) <= BWD_TOL, "level %d" % l
+
+
+def test_latent_backward_large_batch_3d_matches_oracle(lib):
+    """NeRF shape (C=1 -> F=4, shared affine decoder): grad_latents = scatter of A^T g, against the oracle."""
+    dim, L, bw, C, F, n = 3, 16, 19, 1, 4, 1 << 17
+    c = make_case(dim, L, bw, 16, 2048, n, F, seed=77, coord_kind="arbitrary")
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((1, C, F)).astype(np.float32)
+    gz = (c["grad_out"].reshape(n, L, F) @ A[0].T).reshape(n, L * C).astype(np.float32)   # [n, L*C]
+    want = oracle.backward(c["coords"], gz, c["T"], c["first_idx"], c["resolutions"], bw, C)
+    z = torch.zeros((n, L * C), device="cuda")
+    gl, gA, gS = lib.latent_backward(_dev(c["coords"]), _dev(c["grad_out"]), z, c["first_idx"], c["resolutions"], bw,
+                                     _dev(A), C, F, c["T"], True)
+    assert rel_err(gl.cpu().numpy(), want) <= BWD_TOL
+    want_gS = c["grad_out"].reshape(n, L, F).astype(np.float64).sum(0)
+    assert rel_err(gS.cpu().numpy(), want_gS) <= BWD_TOL
