@@ -8,6 +8,8 @@ wd 1e-2}, loss = mse + lambda(epoch) * bits / rows with lambda cosine 1e-3 -> 1e
 every step. SGA is OFF (it is RNG-bound; SURVEY 8d asks for SGA-off parity runs).
 
   --impl ours   shacira_b200.grids.LatentGrid (fused + tiled kernels)
+  --impl native shacira_b200.image_fit.ImageFitStep: the whole training step (grid, MLP + loss, bit-rate loss, every
+                gradient, Adam for every parameter group) as 11 native launches, no autograd
   --impl ref    the reference path restated with ITS OWN CUDA kernels (oracle/_ref): table-side
                 round/decode in torch, repeat(1,2), one kernel launch per level, torch ent_loss  -- the checker
   --graph       capture the whole training step (grid, MLP, loss, backward, Adam) in one CUDA graph
@@ -109,7 +111,70 @@ def clamped_psnr(pred, gt):
     return 20 * np.log10(255.0) - 10 * np.log10(max(mse, 1e-12))
 
 
+def fit_native(seed, steps, dev, use_graph, noise_cpu):
+    """The same fit through shacira_b200.image_fit.ImageFitStep: the whole training step as 11 native launches."""
+    from shacira_b200.grids import LatentGrid
+    from shacira_b200.image_fit import ImageFitStep
+    torch.manual_seed(seed)
+    grid = LatentGrid.from_geometric(feature_dim=1, num_lods=16, latent_dim=1, multiscale_type="cat", resolution_dim=2,
+                                     feature_std=0.1, codebook_bitwidth=16, min_grid_res=16, max_grid_res=512,
+                                     init_grid="uniform", conf_latent_decoder=dict(DEC), conf_entropy_reg=dict(ENT))
+    mlp = nn.Sequential(nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 3))
+    with torch.no_grad():
+        grid.codebook.mul_(LATENT_SCALE)
+    grid, mlp = grid.to(dev), mlp.to(dev)
+    coords, gt = make_data(seed, dev)
+    fs = ImageFitStep(grid, mlp, coords, gt, lr=1e-3, grid_lr=2e-2, ldec_lr=1e-2, prob_lr=1e-4, weight_decay=0.0,
+                      weight_decay_decoder=1e-2)
+    noise_gen = torch.Generator().manual_seed(10_000 + seed)
+
+    def host_side(it):
+        fs.set_lambda(1e-4 + 0.5 * (1e-3 - 1e-4) * (1 + math.cos(math.pi * it / steps)))
+        fs.draw_noise(noise_gen if noise_cpu else None)
+        if it + 1 in (1, 2, 5, 10):
+            fs.update_div()
+
+    graph, start_it = None, 0
+    if use_graph:
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for it in range(3):
+                host_side(it)
+                fs.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fs.step()
+        start_it = 3
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for it in range(start_it, steps):
+        host_side(it)
+        if graph is not None:
+            graph.replay()
+        else:
+            fs.step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    rgb_loss = float(fs.rgb_loss())
+    fs.close()
+    with torch.no_grad():
+        pred = mlp(grid.interpolate(coords, 0))
+        psnr = clamped_psnr(pred, gt)
+        q = torch.round(grid.codebook.detach()[:, 0]).long()
+        _, counts = torch.unique(q, return_counts=True)
+        p = counts / counts.sum()
+        latent_bits = float(torch.sum(torch.clamp(-torch.log(p + 1e-10) / np.log(2.0), 0, 1000) * counts))
+        n_other = sum(p.numel() for p in mlp.parameters()) + sum(p.numel() for p in grid.latent_dec.parameters())
+        bpp = (latent_bits + 32 * n_other) / (H * W)
+    return dict(seed=seed, psnr=psnr, bpp=bpp, latent_bits=latent_bits, ms_per_step=dt / (steps - start_it) * 1e3,
+                rgb_loss=rgb_loss)
+
+
 def fit(seed, impl, steps, dev, use_graph, noise_cpu, fused_mlp=False):
+    if impl == "native":
+        return fit_native(seed, steps, dev, use_graph, noise_cpu)
     from shacira_b200 import grid_ops
     from shacira_b200.grids import LatentGrid
     torch.manual_seed(seed)
@@ -219,7 +284,7 @@ def fit(seed, impl, steps, dev, use_graph, noise_cpu, fused_mlp=False):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--impl", default="ours", choices=["ours", "ref"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "ref", "native"])
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--images", type=int, default=1)
     ap.add_argument("--graph", action="store_true")

@@ -199,6 +199,45 @@ int shacira_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_
                       float beta2, float eps, float weight_decay, float* step, int32_t zero_grad,
                       shacira_stream_t stream);
 
+/* Same update with the gradient taken as grad + (*scale2 * scale2_mul) * grad2: the image fit adds the bit-rate
+ * gradient (lambda / rows, lambda a device scalar that changes every step) to the grid gradient without a pass of
+ * its own (wisp/trainers/image_trainer.py:298-319). grad2 / scale2 may be NULL. With advance == 0 the step counter
+ * is left to a later shacira_multi_adam_step (extra_step), saving the one-thread launch. */
+int shacira_adam_step_sum(float* param, const float* grad, const float* grad2, const float* scale2, float scale2_mul,
+                          float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, float* step, int32_t advance, shacira_stream_t stream);
+
+/* Adam over MANY small tensors in ONE single-CTA launch (the reference's trainer steps ~20 tensors of 1..256
+ * elements: decoder MLP, latent-decoder scale/shift, density-model h/b/a; wisp/trainers/base_trainer.py:206-266
+ * builds their parameter groups). Per segment the gradient is
+ *     (sum_{r < grad_rows} grad[r * grad_row_stride + i]) * grad_mul * (grad_scale ? *grad_scale : 1)
+ *                                                         / (grad_div ? grad_div[i / div_group] : 1)
+ * which covers the chain rules of this path without extra kernels: latent-decoder scale = A * div (sum of the
+ * per-level dA rows, divided by div), shift (sum of per-level rows), density parameters (lambda / rows).
+ * After the update, if A_out != NULL: A_out[c * F + f] = scale[c * F + f] / div[c] for the next step's kernels.
+ * `step` (device float) is advanced by the call, and so is `extra_step` when not NULL. At most
+ * SHACIRA_MAX_ADAM_SEGS segments. */
+#define SHACIRA_MAX_ADAM_SEGS 32
+typedef struct {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    const float* grad_scale; /* device scalar or NULL */
+    const float* grad_div;   /* device [ceil(n / div_group)] or NULL */
+    int32_t n;
+    int32_t grad_rows;
+    int32_t grad_row_stride;
+    int32_t div_group;
+    float lr;
+    float weight_decay;
+    float grad_mul;
+    float reserved;
+} shacira_adam_seg_t;
+int shacira_multi_adam_step(const shacira_adam_seg_t* segs, int32_t num_segs, float beta1, float beta2, float eps,
+                            float* step, float* extra_step, const float* scale, const float* div, float* A_out,
+                            int32_t latent_dim, int32_t feature_dim, shacira_stream_t stream);
+
 /* ---- latent bitstream (host side) ---------------------------------------------------- */
 /* Static arithmetic coder over dense symbol ranks 0..num_symbols-1 with 16-bit cumulative
  * frequencies cdf[num_symbols+1] (cdf[0] = 0, strictly increasing, cdf[num_symbols] = 65536).

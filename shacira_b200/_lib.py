@@ -26,6 +26,16 @@ _vp = ctypes.c_void_p
 _i32 = ctypes.c_int32
 _i64 = ctypes.c_int64
 
+class AdamSeg(ctypes.Structure):
+    """shacira_adam_seg_t (include/shacira_b200.h)."""
+    _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("grad_scale", _vp),
+                ("grad_div", _vp), ("n", _i32), ("grad_rows", _i32), ("grad_row_stride", _i32), ("div_group", _i32),
+                ("lr", ctypes.c_float), ("weight_decay", ctypes.c_float), ("grad_mul", ctypes.c_float),
+                ("reserved", ctypes.c_float)]
+
+
+MAX_ADAM_SEGS = 32
+
 # name -> (restype, argtypes); mirrors include/shacira_b200.h one to one.
 SIGNATURES = {
     "shacira_abi_version": (ctypes.c_int, []),
@@ -51,6 +61,8 @@ SIGNATURES = {
     "shacira_symbol_histogram": (ctypes.c_int, [_vp, _i64, _i32, _c_int32_p, _i32, _vp, _vp]),
     "shacira_mlp_mse_step": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "shacira_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _i32, _vp]),
+    "shacira_adam_step_sum": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_float, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _i32, _vp]),
+    "shacira_multi_adam_step": (ctypes.c_int, [_vp, _i32, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "shacira_ac_encode": (_i64, [_vp, _i64, _vp, _i32, _vp, _i64]),
     "shacira_ac_decode": (ctypes.c_int, [_vp, _i64, _vp, _i32, _vp, _i64]),
     "shacira_latent_step_host": (ctypes.c_int, [_i32, _vp, _i64, _vp, _i64, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),

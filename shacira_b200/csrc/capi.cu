@@ -465,6 +465,49 @@ int shacira_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_
     return SHACIRA_OK;
 }
 
+int shacira_adam_step_sum(float* param, const float* grad, const float* grad2, const float* scale2, float scale2_mul,
+                          float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, float* step, int32_t advance, shacira_stream_t stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !step)
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "adam_step_sum: NULL argument");
+    if (n <= 0) return SHACIRA_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t blocks = (n + 1023) / 1024;
+    adam_step_sum_kernel<<<(int)blocks, 256, 0, s>>>(param, grad, grad2, scale2, scale2_mul, exp_avg, exp_avg_sq, n, lr,
+                                                     beta1, beta2, eps, weight_decay, step);
+    LAUNCHED();
+    if (advance) {
+        adam_advance_kernel<<<1, 1, 0, s>>>(step);
+        LAUNCHED();
+    }
+    return SHACIRA_OK;
+}
+
+int shacira_multi_adam_step(const shacira_adam_seg_t* segs, int32_t num_segs, float beta1, float beta2, float eps,
+                            float* step, float* extra_step, const float* scale, const float* div, float* A_out,
+                            int32_t latent_dim, int32_t feature_dim, shacira_stream_t stream) {
+    if (!step || num_segs < 0 || (num_segs > 0 && !segs))
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "multi_adam_step: NULL argument");
+    if (num_segs > SHACIRA_MAX_ADAM_SEGS)
+        return fail(SHACIRA_ERR_UNSUPPORTED, "multi_adam_step: %d segments (max %d)", num_segs, SHACIRA_MAX_ADAM_SEGS);
+    if (A_out && (!scale || !div || latent_dim < 1 || feature_dim < 1))
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "multi_adam_step: A_out needs scale, div, latent_dim, feature_dim");
+    AdamSegs S;
+    memset(&S, 0, sizeof(S));
+    S.num = num_segs;
+    for (int i = 0; i < num_segs; ++i) {
+        const shacira_adam_seg_t& g = segs[i];
+        if (!g.param || !g.grad || !g.exp_avg || !g.exp_avg_sq || g.n < 0 || g.grad_rows < 1 ||
+            (g.grad_div && g.div_group < 1))
+            return fail(SHACIRA_ERR_INVALID_ARGUMENT, "multi_adam_step: bad segment %d", i);
+        S.seg[i] = g;
+    }
+    multi_adam_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(S, beta1, beta2, eps, step, extra_step, scale, div, A_out,
+                                                           latent_dim, feature_dim);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
 int shacira_quantize_symbols(const float* latents, int64_t table_rows, int32_t latent_dim, int16_t* symbols,
                              int32_t* minmax, shacira_stream_t stream) {
     if (!latents || !minmax) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "latents/minmax is NULL");

@@ -256,6 +256,92 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 }
 __global__ void adam_advance_kernel(float* step) { *step += 1.0f; }
 
+// grad = g + (*scale2 * mul2) * g2: the bit-rate gradient rides on the grid gradient (no pass of its own)
+__global__ void __launch_bounds__(256)
+adam_step_sum_kernel(float* __restrict__ p, const float* __restrict__ g, const float* __restrict__ g2,
+                     const float* __restrict__ scale2, float mul2, float* __restrict__ m, float* __restrict__ v,
+                     int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                     const float* __restrict__ step) {
+    const float t = *step + 1.0f;
+    const float bc1 = 1.0f - powf(beta1, t), bc2 = 1.0f - powf(beta2, t);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    const float s2 = g2 ? (scale2 ? *scale2 * mul2 : mul2) : 0.0f;
+    const int64_t i4 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    const bool vec = i4 + 3 < n && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                                     reinterpret_cast<uintptr_t>(g2) | reinterpret_cast<uintptr_t>(m) |
+                                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    if (vec) {
+        float4 pp = *reinterpret_cast<float4*>(p + i4), mm = *reinterpret_cast<float4*>(m + i4);
+        float4 vv = *reinterpret_cast<float4*>(v + i4);
+        float4 gg = *reinterpret_cast<const float4*>(g + i4);
+        if (g2) {
+            const float4 hh = *reinterpret_cast<const float4*>(g2 + i4);
+            gg.x = fmaf(s2, hh.x, gg.x); gg.y = fmaf(s2, hh.y, gg.y); gg.z = fmaf(s2, hh.z, gg.z); gg.w = fmaf(s2, hh.w, gg.w);
+        }
+        float* P = &pp.x; float* M = &mm.x; float* V = &vv.x; const float* G = &gg.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gk = fmaf(weight_decay, P[k], G[k]);
+            M[k] = fmaf(beta1, M[k], (1.0f - beta1) * gk);
+            V[k] = fmaf(beta2, V[k], (1.0f - beta2) * gk * gk);
+            P[k] -= step_size * M[k] / (sqrtf(V[k]) * inv_sqrt_bc2 + eps);
+        }
+        *reinterpret_cast<float4*>(p + i4) = pp;
+        *reinterpret_cast<float4*>(m + i4) = mm;
+        *reinterpret_cast<float4*>(v + i4) = vv;
+    } else {
+        for (int64_t i = i4; i < min(n, i4 + 4); ++i) {
+            const float gi = g2 ? fmaf(s2, g2[i], g[i]) : g[i];
+            const float gk = fmaf(weight_decay, p[i], gi);
+            const float mk = fmaf(beta1, m[i], (1.0f - beta1) * gk);
+            const float vk = fmaf(beta2, v[i], (1.0f - beta2) * gk * gk);
+            m[i] = mk;
+            v[i] = vk;
+            p[i] -= step_size * mk / (sqrtf(vk) * inv_sqrt_bc2 + eps);
+        }
+    }
+}
+
+// Adam over many small tensors, one CTA (see shacira_multi_adam_step in the header for the gradient formula).
+struct AdamSegs {
+    shacira_adam_seg_t seg[SHACIRA_MAX_ADAM_SEGS];
+    int32_t num;
+    int32_t pad[3];
+};
+__global__ void __launch_bounds__(256)
+multi_adam_kernel(const __grid_constant__ AdamSegs S, float beta1, float beta2, float eps, float* __restrict__ step,
+                  float* __restrict__ extra_step, const float* __restrict__ scale, const float* __restrict__ div,
+                  float* __restrict__ A_out, int C, int F) {
+    const float t = *step + 1.0f;
+    const float bc1 = 1.0f - powf(beta1, t), bc2 = 1.0f - powf(beta2, t);
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
+    for (int s = 0; s < S.num; ++s) {
+        const shacira_adam_seg_t& sg = S.seg[s];
+        const float gs = sg.grad_mul * (sg.grad_scale ? *sg.grad_scale : 1.0f);
+        const float step_size = sg.lr / bc1;
+        for (int i = threadIdx.x; i < sg.n; i += 256) {
+            float g = 0.0f;
+            for (int r = 0; r < sg.grad_rows; ++r) g += sg.grad[(size_t)r * sg.grad_row_stride + i];
+            g *= gs;
+            if (sg.grad_div) g /= sg.grad_div[i / sg.div_group];
+            const float p = sg.param[i];
+            const float gk = fmaf(sg.weight_decay, p, g);
+            const float mk = fmaf(beta1, sg.exp_avg[i], (1.0f - beta1) * gk);
+            const float vk = fmaf(beta2, sg.exp_avg_sq[i], (1.0f - beta2) * gk * gk);
+            sg.exp_avg[i] = mk;
+            sg.exp_avg_sq[i] = vk;
+            sg.param[i] = p - step_size * mk / (sqrtf(vk) * inv_sqrt_bc2 + eps);
+        }
+    }
+    __syncthreads();  // every thread has read *step; the updated scale is visible to the block
+    if (threadIdx.x == 0) {
+        *step = t;
+        if (extra_step) *extra_step += 1.0f;
+    }
+    if (A_out)
+        for (int e = threadIdx.x; e < C * F; e += 256) A_out[e] = scale[e] / div[e / F];
+}
+
 // ---- symbols and histogram ---------------------------------------------------------------
 __global__ void init_minmax_kernel(int32_t* minmax, int C) {
     const int c = threadIdx.x;

@@ -1,0 +1,215 @@
+"""One training step of the image INR fit, natively fused.
+
+Mirrors `ImageTrainer.step` (wisp/trainers/image_trainer.py:269-359) for the static-coordinate image fit:
+
+    feats = grid.interpolate(coords)            latent_grid.py:340-382   -> tiled forward kernel
+    rgb   = decoder_color(feats)                nefs/image.py:109-120,152 \\  fused MLP + MSE kernel
+    rgb_loss = ((rgb - gt) ** 2).mean()         image_trainer.py:298-300  /  (value + every gradient)
+    ent   = grid.ent_loss(it)[0]                latent_grid.py:122-136   -> fused bit-rate kernel
+    loss  = rgb_loss + lambda * ent             image_trainer.py:314-319
+    loss.backward(); optimizer.step()           :321-359, parameter groups base_trainer.py:206-266
+
+In PyTorch terms that step is ~50 kernels (autograd glue, gradient scaling passes over the table, one multi-tensor
+Adam per group). Here it is 11 launches and no autograd: the gradients each kernel produces are consumed in place --
+the bit-rate gradient joins the grid gradient inside the table's Adam kernel (`shacira_adam_step_sum`, lambda is a
+device scalar), and ONE single-CTA kernel runs Adam over all ~20 small tensors with their chain rules
+(`shacira_multi_adam_step`). The whole step is CUDA-graph capturable; `set_lambda` / `draw_noise` / `update_div`
+are the host-side schedule hooks of the trainer (image_trainer.py:131-137,284-296).
+
+The module parameters stay the single source of truth: the kernels read and update the storage of
+`grid.codebook`, `grid.latent_dec.layers[0].{scale,shift}`, `grid.prob_model.f*.{h,b,a}` and the MLP in place, so
+`grid.interpolate`, `grid.size()`, `state_dict()` etc. see the trained values at any time.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, grid_ops
+
+
+class ImageFitStep:
+    def __init__(self, grid, mlp, coords, target, lr=1e-3, grid_lr=2e-2, ldec_lr=1e-2, prob_lr=1e-4,
+                 weight_decay=0.0, weight_decay_decoder=1e-2, betas=(0.9, 0.999), eps=1e-8):
+        """`grid`: shacira_b200.grids.LatentGrid (2D, single affine decoder, STE rounding); `mlp`:
+        nn.Sequential(Linear(L*F,16), ReLU, Linear(16,16), ReLU, Linear(16,3)); coords [N,2], target [N,3].
+        Learning rates / weight decays: the reference's parameter groups (base_trainer.py:219-239; kodak.yaml:61-70)."""
+        dec = grid.latent_dec
+        if getattr(dec, "use_sga", False):
+            raise _lib.ShaciraError(_lib.ERR_UNSUPPORTED, "ImageFitStep: SGA sampling runs on the PyTorch path")
+        amap = dec.affine_map() if hasattr(dec, "affine_map") else None
+        if amap is None or amap[0].shape[0] != 1 or "dft" in dec.layers[0].ldecode_matrix:
+            raise _lib.ShaciraError(_lib.ERR_UNSUPPORTED, "ImageFitStep: needs ONE affine 'sq' latent decoder")
+        if grid.prob_model is None:
+            raise _lib.ShaciraError(_lib.ERR_UNSUPPORTED, "ImageFitStep: needs the bit-rate model (entropy_reg > 0)")
+        self.grid, self.mlp = grid, mlp
+        self.coords = _lib._f32c(coords, "coords")
+        self.target = _lib._f32c(target, "target")
+        dev = self.coords.device
+        self.dev = dev
+        self.n = self.coords.shape[0]
+        self.T, self.C = grid.codebook.shape
+        self.L = grid.num_lods
+        layer = dec.layers[0]
+        self.F = layer.scale.shape[1]
+        self.fi, _ = _lib._i32_array(grid._first_idx())
+        self.rs, _ = _lib._i32_array(grid.resolutions)
+        self.bw = int(grid.codebook_bitwidth)
+        self.betas, self.eps = betas, float(eps)
+        self.grid_lr, self.weight_decay = float(grid_lr), float(weight_decay)
+        self.lin = [mlp[0], mlp[2], mlp[4]]
+        self.IN, self.H, self.OUT = self.lin[0].in_features, self.lin[0].out_features, self.lin[2].out_features
+        if self.IN != self.L * self.F:
+            raise _lib.ShaciraError(_lib.ERR_INVALID_ARGUMENT, "MLP input width must be num_lods * feature_dim")
+        self.plan = grid_ops.plan_for(self.coords)
+        if self.plan is None:
+            raise _lib.ShaciraError(_lib.ERR_UNSUPPORTED, "ImageFitStep: coordinate set too small for the tiled kernels")
+        self.plan.users += 1   # pinned for the life of this object
+        f32 = dict(dtype=torch.float32, device=dev)
+        # density-model parameters live in ONE [4, 3, C] buffer (the kernel's layout); the module's h / b / a become
+        # views of it, so nothing is packed per step
+        pm = grid.prob_model
+        self.prob = torch.zeros((4, 3, self.C), **f32)
+        for i, f in enumerate((pm.f1, pm.f2, pm.f3, pm.f4)):
+            for k, name in enumerate(("h", "b", "a")):
+                p = getattr(f, name, None)
+                if p is None:
+                    continue
+                self.prob[i, k].copy_(p.detach().reshape(-1))
+                p.data = self.prob[i, k].view(1, self.C)
+        self.num_prob_layers = int(pm.num_layers)
+        # step buffers
+        self.A = torch.empty((1, self.C, self.F), **f32)
+        self.feats = torch.empty((self.n, self.L * self.F), **f32)
+        self.gfeat = torch.empty_like(self.feats)
+        n_par = self.H * self.IN + self.H + self.H * self.H + self.H + self.OUT * self.H + self.OUT
+        self.mlp_out = torch.zeros(2 + n_par, **f32)            # double SSE | packed MLP gradients
+        self.g_grid = torch.empty((self.T, self.C), **f32)
+        self.g_ent = torch.empty((self.T, self.C), **f32)
+        self.g_prob = torch.zeros((4, 3, self.C), **f32)
+        self.g_dec = torch.zeros((self.L * self.C * self.F + self.L * self.F,), **f32)   # dA rows | dshift rows
+        self.bits = torch.zeros((1 + self.L,), dtype=torch.float64, device=dev)
+        self.noise = torch.zeros((self.T, self.C), **f32)
+        self.lam = torch.zeros((), **f32)
+        self.ent_scratch = torch.zeros(int(_lib.load().shacira_entropy_scratch_bytes(self.C, self.L)),
+                                       dtype=torch.uint8, device=dev)
+        # Adam state
+        self.m_table, self.v_table = torch.zeros_like(grid.codebook.data), torch.zeros_like(grid.codebook.data)
+        self.step_table = torch.zeros((), **f32)
+        self.step_small = torch.zeros((), **f32)
+        self._keep = []
+        segs = []
+
+        def seg(param, grad, n, lr, wd, rows=1, stride=0, scale=None, mul=1.0, div=None, group=1):
+            m, v = torch.zeros(n, **f32), torch.zeros(n, **f32)
+            self._keep += [m, v]
+            s = _lib.AdamSeg()
+            s.param, s.grad = param.data_ptr(), grad.data_ptr()
+            s.exp_avg, s.exp_avg_sq = m.data_ptr(), v.data_ptr()
+            s.grad_scale = scale.data_ptr() if scale is not None else None
+            s.grad_div = div.data_ptr() if div is not None else None
+            s.n, s.grad_rows, s.grad_row_stride, s.div_group = n, rows, stride, group
+            s.lr, s.weight_decay, s.grad_mul = lr, wd, mul
+            segs.append(s)
+
+        packed = self.mlp_out[2:]
+        off = 0
+        for lin in self.lin:                       # decoder group: lr, weight decay 0 (base_trainer.py:222-224)
+            for p in (lin.weight, lin.bias):
+                seg(p.data, packed[off:], p.numel(), float(lr), 0.0)
+                off += p.numel()
+        CF = self.C * self.F
+        # latent_dec group (base_trainer.py:225-229): scale = A * div  =>  dscale = (sum_l dA_l) / div
+        seg(layer.scale.data, self.g_dec, CF, float(ldec_lr), float(weight_decay_decoder), rows=self.L, stride=CF,
+            div=dec.div.data, group=self.F)
+        self.has_shift = layer.shift is not None
+        if self.has_shift:
+            seg(layer.shift.data, self.g_dec[self.L * CF:], self.F, float(ldec_lr), float(weight_decay_decoder),
+                rows=self.L, stride=self.F)
+        # prob_model group: lr fixed 1e-4 (base_trainer.py:230-234); gradient = lambda / rows * d(bits)
+        used = [0] if self.num_prob_layers > 1 else []
+        if self.num_prob_layers > 2:
+            used.append(1)
+        if self.num_prob_layers > 3:
+            used.append(2)
+        used.append(3)
+        for i, f in zip(range(4), (pm.f1, pm.f2, pm.f3, pm.f4)):
+            if i not in used:
+                continue                            # never receives a gradient: torch.optim.Adam skips it too
+            for k, name in enumerate(("h", "b", "a")):
+                p = getattr(f, name, None)
+                if p is None or not p.requires_grad:
+                    continue
+                seg(self.prob[i, k], self.g_prob[i, k], self.C, float(prob_lr), float(weight_decay_decoder),
+                    scale=self.lam, mul=1.0 / self.T)
+        if len(segs) > _lib.MAX_ADAM_SEGS:
+            raise _lib.ShaciraError(_lib.ERR_UNSUPPORTED, "too many small tensors")
+        self.segs = (_lib.AdamSeg * len(segs))(*segs)
+        self.nseg = len(segs)
+        self.layer = layer
+        self.refresh_A()
+
+    # ---- host-side schedule hooks ------------------------------------------------------------
+    def refresh_A(self):
+        """A = scale / div (latent_decoders.affine_map); call after changing scale or div outside step()."""
+        with torch.no_grad():
+            self.A.copy_((self.layer.scale.data / self.grid.latent_dec.div.data.unsqueeze(1)).unsqueeze(0))
+
+    def set_lambda(self, value):
+        self.lam.fill_(float(value))
+
+    def draw_noise(self, generator=None):
+        """U(-0.5, 0.5) per latent (latent_grid.py:128); with a CPU generator the reference's stream."""
+        if generator is not None:
+            self.noise.copy_(torch.rand((self.T, self.C), generator=generator) - 0.5)
+        else:
+            self.noise.uniform_(-0.5, 0.5)
+
+    def update_div(self):
+        """norm='max' (image_trainer.py:284-296): div = max(|min|, |max|) per latent channel."""
+        with torch.no_grad():
+            w = self.grid.codebook.data
+            self.grid.latent_dec.div.data.copy_(torch.max(torch.abs(w.min(dim=0)[0]), torch.abs(w.max(dim=0)[0])))
+        self.refresh_A()
+
+    # ---- the step --------------------------------------------------------------------------------
+    def step(self):
+        lib, P, chk = _lib.load(), _lib._ptr, _lib._check
+        g, dec = self.grid, self.grid.latent_dec
+        lat = g.codebook.data
+        shift = self.layer.shift.data if self.has_shift else None
+        lin = self.lin
+        with torch.cuda.device(self.dev):
+            st = _lib._stream()
+            chk(lib.shacira_latent_forward_planned(self.plan.handle, P(lat), self.fi, self.rs, self.L, self.bw, self.C,
+                                                   self.F, 1, P(self.A), P(shift), 0, P(self.feats), st))
+            chk(lib.shacira_mlp_mse_step(P(self.feats), P(self.target), self.n, self.IN, self.H, self.OUT,
+                                         P(lin[0].weight.data), P(lin[0].bias.data), P(lin[1].weight.data),
+                                         P(lin[1].bias.data), P(lin[2].weight.data), P(lin[2].bias.data),
+                                         P(self.gfeat), None, P(self.mlp_out), st))
+            chk(lib.shacira_entropy_bits(P(lat), P(self.noise), self.T, self.C, P(self.prob), self.num_prob_layers,
+                                         self.fi, self.L, P(self.bits), P(self.g_ent), P(self.g_prob),
+                                         P(self.ent_scratch), self.ent_scratch.numel(), st))
+            self.g_dec.zero_()
+            CF = self.C * self.F
+            chk(lib.shacira_latent_backward_planned(self.plan.handle, P(self.gfeat), P(lat), self.fi, self.rs, self.L,
+                                                    self.bw, self.C, self.F, 1, P(self.A), 0, self.T, 1, P(self.g_grid),
+                                                    P(self.g_dec), P(self.g_dec[self.L * CF:]), st))
+            chk(lib.shacira_adam_step_sum(P(lat), P(self.g_grid), P(self.g_ent), P(self.lam), 1.0 / self.T,
+                                          P(self.m_table), P(self.v_table), self.T * self.C, self.grid_lr,
+                                          self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                          P(self.step_table), 0, st))
+            chk(lib.shacira_multi_adam_step(ctypes.cast(self.segs, ctypes.c_void_p), self.nseg, self.betas[0],
+                                            self.betas[1], self.eps, P(self.step_small), P(self.step_table),
+                                            P(self.layer.scale.data), P(dec.div.data), P(self.A), self.C, self.F, st))
+
+    # ---- results of the last step (device tensors; reading them synchronises) -------------------
+    def rgb_loss(self):
+        return (self.mlp_out[:2].view(torch.float64)[0] / (self.n * self.OUT)).to(torch.float32)
+
+    def total_bits(self):
+        return self.bits[0].to(torch.float32)
+
+    def close(self):
+        if self.plan is not None:
+            self.plan.users = max(0, self.plan.users - 1)
+            self.plan = None

@@ -38,3 +38,93 @@ def test_whole_step_cuda_graph_matches_eager(lib):
     eager = fit_image.fit(1, "ours", 300, dev, use_graph=False, noise_cpu=False)
     graph = fit_image.fit(1, "ours", 300, dev, use_graph=True, noise_cpu=False)
     assert abs(eager["psnr"] - graph["psnr"]) <= 0.3 and abs(eager["bpp"] - graph["bpp"]) <= 0.03 * eager["bpp"]
+
+
+def test_native_fit_step_matches_autograd_step(lib):
+    """ImageFitStep (11 native launches, no autograd) against the same step through autograd + torch.optim.Adam:
+    same initial state, same noise and lambda; parameters after a few steps agree to float reordering."""
+    import copy
+    import fit_image
+    from shacira_b200.grids import LatentGrid
+    from shacira_b200.image_fit import ImageFitStep
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    grid = LatentGrid.from_geometric(feature_dim=1, num_lods=16, latent_dim=1, multiscale_type="cat", resolution_dim=2,
+                                     feature_std=0.1, codebook_bitwidth=16, min_grid_res=16, max_grid_res=512,
+                                     init_grid="uniform", conf_latent_decoder=dict(fit_image.DEC),
+                                     conf_entropy_reg=dict(fit_image.ENT))
+    mlp = torch.nn.Sequential(torch.nn.Linear(16, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(),
+                              torch.nn.Linear(16, 3))
+    with torch.no_grad():
+        grid.codebook.mul_(fit_image.LATENT_SCALE)
+        grid.latent_dec.layers[0].shift.normal_(0, 0.05)
+    grid, mlp = grid.to(dev), mlp.to(dev)
+    grid2, mlp2 = copy.deepcopy(grid), copy.deepcopy(mlp)
+    coords, gt = fit_image.make_data(3, dev)
+    T = grid.codebook.shape[0]
+    opt = torch.optim.Adam([dict(params=list(mlp.parameters()), lr=1e-3, weight_decay=0.0),
+                            dict(params=[grid.codebook], lr=2e-2, weight_decay=0.0),
+                            dict(params=[p for p in grid.latent_dec.parameters() if p.requires_grad], lr=1e-2,
+                                 weight_decay=1e-2),
+                            dict(params=list(grid.prob_model.parameters()), lr=1e-4, weight_decay=1e-2)], eps=1e-8)
+    fs = ImageFitStep(grid2, mlp2, coords, gt)
+    f2_h_init = grid2.prob_model.f2.h.data.clone()
+    gen = torch.Generator().manual_seed(5)
+    losses = []
+    for it in range(6):
+        lam = 1e-3 - 1e-4 * it
+        noise = (torch.rand((T, 1), generator=gen) - 0.5).to(dev)
+        # autograd arm
+        opt.zero_grad()
+        grid.noise, grid.noise_freq = noise, 2
+        rgb = ((mlp(grid.interpolate(coords, 0)) - gt) ** 2).mean()
+        avg_bits, bits = grid.ent_loss(1)
+        (rgb + lam * avg_bits).backward()
+        opt.step()
+        # native arm
+        fs.set_lambda(lam)
+        fs.noise.copy_(noise)
+        fs.step()
+        losses.append((float(rgb.detach()), float(fs.rgb_loss()), float(bits.detach()), float(fs.total_bits())))
+        if it == 1:   # the norm='max' rescale of the trainer
+            with torch.no_grad():
+                w = grid.codebook
+                grid.latent_dec.div.data.copy_(torch.max(torch.abs(w.min(dim=0)[0]), torch.abs(w.max(dim=0)[0])))
+            fs.update_div()
+    for a, b, c, d in losses:
+        assert abs(a - b) <= 2e-4 * abs(a) and abs(c - d) <= 1e-5 * abs(c), losses
+
+    def close(x, y, tol):
+        return float((x - y).abs().max()) <= tol * max(float(y.abs().max()), 1e-12)
+
+    # Adam normalises the gradient, so early steps move every latent by ~lr whatever its gradient: entries whose
+    # gradient is float-reordering noise around 0 can differ by a full step; compare robustly (99.9 % within 1e-3)
+    d = (grid2.codebook.data - grid.codebook.data).abs()
+    assert float((d <= 1e-3 * float(grid.codebook.data.abs().max())).float().mean()) >= 0.999
+    for p2, p1 in zip(mlp2.parameters(), mlp.parameters()):
+        assert close(p2.data, p1.data, 2e-3)
+    assert close(grid2.latent_dec.layers[0].scale.data, grid.latent_dec.layers[0].scale.data, 2e-3)
+    assert close(grid2.latent_dec.layers[0].shift.data, grid.latent_dec.layers[0].shift.data, 2e-3)
+    for f2, f1 in zip((grid2.prob_model.f1, grid2.prob_model.f4), (grid.prob_model.f1, grid.prob_model.f4)):
+        assert close(f2.h.data, f1.h.data, 2e-3) and close(f2.b.data, f1.b.data, 2e-3)
+    # unused density layers are never touched: in the reference they never receive a gradient and torch.optim.Adam
+    # skips them (bit_estimator.py:58-65 only calls f1 and f4 for num_prob_layers = 2)
+    assert torch.equal(grid2.prob_model.f2.h.data, f2_h_init)
+    fs.close()
+
+
+def test_native_fit_reaches_reference_quality(lib):
+    """The natively fused step, captured in a CUDA graph, against the reference's own kernels: PSNR / bpp gate."""
+    from oracle import build_ref
+    build_ref.build()
+    if build_ref.load() is None:
+        pytest.skip("oracle/_ref/wisp_ref_ops.so not present")
+    import fit_image
+    dev = torch.device("cuda", 0)
+    steps = 400
+    ours = fit_image.fit(0, "native", steps, dev, use_graph=False, noise_cpu=True)
+    ref = fit_image.fit(0, "ref", steps, dev, use_graph=False, noise_cpu=True)
+    print("native", ours, "ref", ref)
+    assert ours["psnr"] > 20.0
+    assert abs(ours["psnr"] - ref["psnr"]) <= PSNR_TOL_DB
+    assert abs(ours["bpp"] - ref["bpp"]) <= BPP_TOL * ref["bpp"]
