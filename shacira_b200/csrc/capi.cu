@@ -223,6 +223,66 @@ int launch_latent_bwd(const float* coords, int64_t n, const float* g, const floa
 }  // namespace
 
 namespace {
+// IN = 16: weights as constant-bank operands (mlp16_mse_step_kernel). The six tensors are copied device-to-device
+// into the constant bank on the caller's stream (one copy when they are packed back to back, as ImageFitStep keeps
+// them); the copies are stream ordered and capturable.
+int launch_mlp16(const float* x, const float* gt, int64_t n, const float* W1, const float* b1, const float* W2,
+                 const float* b2, const float* W3, const float* b3, float* gx, float* pred, void* out, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        CUDA_OK(cudaFuncSetAttribute(mlp16_mse_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(Mlp16Smem)));
+        configured = true;
+    }
+    const float* src[6] = {W1, b1, W2, b2, W3, b3};
+    const size_t cnt[6] = {256, 16, 256, 16, 48, 3};
+    bool packed = true;
+    for (int k = 0; k + 1 < 6; ++k) packed &= (src[k] + cnt[k] == src[k + 1]);
+    if (packed) {
+        CUDA_OK(cudaMemcpyToSymbolAsync(shacira_c_mlp, W1, sizeof(float) * kMlpConstFloats, 0, cudaMemcpyDeviceToDevice, s));
+    } else {
+        size_t off = 0;
+        for (int k = 0; k < 6; ++k) {
+            CUDA_OK(cudaMemcpyToSymbolAsync(shacira_c_mlp, src[k], sizeof(float) * cnt[k], sizeof(float) * off,
+                                            cudaMemcpyDeviceToDevice, s));
+            off += cnt[k];
+        }
+    }
+    const size_t out_bytes = 8 + sizeof(float) * kMlpConstFloats;
+    CUDA_OK(cudaMemsetAsync(out, 0, out_bytes, s));
+    int64_t warps = (n + 31) / 32;
+    int64_t blocks = (warps + kMlpWarps - 1) / kMlpWarps;
+    const int64_t cap = (int64_t)sm_count() * 2;  // persistent: 2 CTAs per SM fit the shared memory
+    if (blocks > cap) blocks = cap;
+    const float scale = (float)(2.0 / ((double)n * 3.0));
+    mlp16_mse_step_kernel<<<(int)blocks, kMlpThreads, sizeof(Mlp16Smem), s>>>(x, gt, n, scale, gx, pred, (double*)out,
+                                                                              (float*)((char*)out + 8));
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
+// IN = 16 on the tensor cores (mlp16_tc_step_kernel: mma.sync TF32 with 3xTF32 compensation)
+int launch_mlp_tc(const float* x, const float* gt, int64_t n, const float* W1, const float* b1, const float* W2,
+                  const float* b2, const float* W3, const float* b3, float* gx, float* pred, void* out, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        CUDA_OK(cudaFuncSetAttribute(mlp16_tc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(MlpTcSmem)));
+        configured = true;
+    }
+    const size_t out_bytes = 8 + sizeof(float) * kMlpConstFloats;
+    CUDA_OK(cudaMemsetAsync(out, 0, out_bytes, s));
+    int64_t warps = (n + 31) / 32;
+    int64_t blocks = (warps + kTcWarps - 1) / kTcWarps;
+    const int64_t cap = (int64_t)sm_count() * 2;  // persistent: 2 CTAs per SM fit the shared memory
+    if (blocks > cap) blocks = cap;
+    const float scale = (float)(2.0 / ((double)n * 3.0));
+    mlp16_tc_step_kernel<<<(int)blocks, kTcThreads, sizeof(MlpTcSmem), s>>>(x, gt, n, W1, b1, W2, b2, W3, b3, scale, gx,
+                                                                            pred, (double*)out, (float*)((char*)out + 8));
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
 template <int IN>
 int launch_mlp(const float* x, const float* gt, int64_t n, const float* W1, const float* b1, const float* W2,
                const float* b2, const float* W3, const float* b3, float* gx, float* pred, void* out, cudaStream_t s) {
@@ -561,7 +621,16 @@ int shacira_mlp_mse_step(const float* features, const float* target, int64_t n, 
         return fail(SHACIRA_ERR_UNSUPPORTED, "mlp_mse_step: hidden %d / out %d (compiled: 16 / 3)", hidden_dim, out_dim);
     cudaStream_t s = (cudaStream_t)stream;
     switch (in_dim) {
-        case 16: return launch_mlp<16>(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
+        case 16: {
+            // SHACIRA_MLP_IMPL = tc (default) | const (FFMA, weights in the constant bank) | smem (FFMA, shared memory)
+            static const int impl = [] {
+                const char* e = getenv("SHACIRA_MLP_IMPL");
+                return !e ? 0 : (!strcmp(e, "const") ? 1 : (!strcmp(e, "smem") ? 2 : 0));
+            }();
+            if (impl == 2) return launch_mlp<16>(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
+            if (impl == 1) return launch_mlp16(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
+            return launch_mlp_tc(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
+        }
         case 24: return launch_mlp<24>(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
         case 32: return launch_mlp<32>(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
         default: return fail(SHACIRA_ERR_UNSUPPORTED, "mlp_mse_step: in_dim %d not in {16,24,32}", in_dim);

@@ -15,7 +15,15 @@
 // memory, each lane accumulating an 8-wide slice in registers across ALL its warp's points (persistent CTAs),
 // then reduced over the block in shared memory and added to global memory once per CTA and value.
 #pragma once
+#include <utility>
+
 #include "common.cuh"
+
+// Decoder-MLP weights of the IN = 16 fast path, packed W1 | b1 | W2 | b2 | W3 | b3. C linkage: the kernel names the
+// symbol in inline PTX (see cweight below).
+extern "C" {
+__constant__ float shacira_c_mlp[16 * 16 + 16 + 16 * 16 + 16 + 3 * 16 + 3 + 1];
+}
 
 namespace shacira {
 
@@ -257,6 +265,631 @@ mlp_mse_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, i
     for (int e = tid; e < OUT * H; e += kMlpThreads) red_add(gW3 + e, S.gW3[e]);
     if (tid < H) { red_add(gb1 + tid, S.gb1[tid]); red_add(gb2 + tid, S.gb2[tid]); }
     if (tid < OUT) red_add(gb3 + tid, S.gb3[tid]);
+    if (tid == 0) atomicAdd(loss_sum, S.loss);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// IN = 16 fast path (the image decoder: 16 levels x 1 feature).
+//
+// The kernel above feeds every FMA of the forward / backward products with a weight broadcast from shared memory
+// (one LDS.128 per 4 FMAs): measured on B200 it is bound by the shared-memory pipe, 82 us at the Kodak shape against
+// an 18 us FP32 floor. Here the 595 weights live in CONSTANT memory (copied device-to-device before the launch), so
+// the products are plain `FFMA R, R, c[bank][imm], R` with no load at all, and the weight-gradient stage splits each
+// warp into two half-warps that walk the even / odd points of the warp's 32: every lane owns a 4 x 4 block of dW1
+// and dW2 (16 FMAs per two 16-byte shared loads instead of 8 per three). Activations are staged unpadded with an XOR
+// swizzle of the 16-byte chunks (conflict-free both for the per-lane row stores and the half-warp block loads).
+// One MLP step may be in flight per device at a time (the constant bank is shared by all streams).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMlpConstFloats = 16 * 16 + 16 + 16 * 16 + 16 + 3 * 16 + 3;  // W1 | b1 | W2 | b2 | W3 | b3 (packed order)
+
+// Weight OFF as an FFMA constant-bank operand (`FFMA R, R, c[3][imm], R`: no load instruction at all). Two things
+// defeat that if the products are written inline in the persistent point loop (both measured with cuobjdump): the
+// 595 loads are loop invariant, so ptxas hoists them into registers and spills 2 KB per thread; and a weight used by
+// the forward AND the backward product becomes one load with two uses, i.e. a register again. Hence the forward and
+// the backward live in two __noinline__ functions: no loop to hoist out of, one use per weight and function.
+template <int OFF>
+__device__ __forceinline__ float cweight() {
+    float w;
+    asm("ld.const.f32 %0, [shacira_c_mlp+%1];" : "=f"(w) : "n"(OFF * 4));
+    return w;
+}
+template <int... Is, class Fn>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, Fn&& f) {
+    (f(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, class Fn>
+__device__ __forceinline__ void static_for(Fn&& f) {
+    static_for_impl(std::make_integer_sequence<int, N>{}, f);
+}
+
+struct Mlp16Smem {
+    // per warp: 32 points x 16 floats each, chunk-swizzled; dy padded to 4
+    float x[kMlpWarps][32][16], h1[kMlpWarps][32][16], h2[kMlpWarps][32][16];
+    float d1[kMlpWarps][32][16], d2[kMlpWarps][32][16], dy[kMlpWarps][32][4];
+    uint2 mask[kMlpWarps][32];  // ReLU masks of layers 1 and 2, forward -> backward
+    float g[kMlpConstFloats + 1];  // block reduction of the gradient slices (packed order)
+    double loss;
+};
+
+// physical 16-byte chunk of logical chunk c in row p: the row's parity picks the bank half (row stride 64 B), the
+// rotation by (p >> 1) spreads a quarter-warp's stores over all 32 banks
+__device__ __forceinline__ int swz16(int p, int c) { return c ^ ((p >> 1) & 3); }
+
+namespace mlp16 {
+constexpr int IN = 16, H = 16, OUT = 3;
+constexpr int oW1 = 0, ob1 = oW1 + H * IN, oW2 = ob1 + H, ob2 = oW2 + H * H, oW3 = ob2 + H, ob3 = oW3 + OUT * H;
+}  // namespace mlp16
+
+// Forward of one point per lane: stages x, h1, h2, dy and the ReLU masks of the lane's row; returns its squared error.
+__device__ __noinline__ float mlp16_forward(const float* __restrict__ x, const float* __restrict__ gt, int64_t p,
+                                            int live, float grad_scale, float* __restrict__ pred, Mlp16Smem* Sp,
+                                            int warp, int lane) {
+    using namespace mlp16;
+    Mlp16Smem& S = *Sp;
+    float4* sx = reinterpret_cast<float4*>(&S.x[warp][0][0]);
+    float4* sh1 = reinterpret_cast<float4*>(&S.h1[warp][0][0]);
+    float4* sh2 = reinterpret_cast<float4*>(&S.h2[warp][0][0]);
+    float v[16], h[16], tgt[OUT] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = 0.0f;
+    if (live) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(x + p * IN) + q);
+            v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+        }
+#pragma unroll
+        for (int k = 0; k < OUT; ++k) tgt[k] = __ldg(gt + p * OUT + k);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sx[lane * 4 + swz16(lane, q)] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    unsigned m1 = 0u, m2 = 0u;
+    static_for<H>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        float acc = cweight<ob1 + i>();
+        static_for<IN>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            acc = fmaf(v[m], cweight<oW1 + i * IN + m>(), acc);
+        });
+        h[i] = fmaxf(acc, 0.0f);
+        m1 |= (acc > 0.0f ? 1u : 0u) << i;
+    });
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sh1[lane * 4 + swz16(lane, q)] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    static_for<H>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        float acc = cweight<ob2 + j>();
+        static_for<H>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            acc = fmaf(h[i], cweight<oW2 + j * H + i>(), acc);
+        });
+        v[j] = fmaxf(acc, 0.0f);   // v now holds h2
+        m2 |= (acc > 0.0f ? 1u : 0u) << j;
+    });
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sh2[lane * 4 + swz16(lane, q)] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    float dy[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float loss = 0.0f;
+    static_for<OUT>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        float acc = cweight<ob3 + k>();
+        static_for<H>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            acc = fmaf(v[j], cweight<oW3 + k * H + j>(), acc);
+        });
+        if (live) {
+            const float e = acc - tgt[k];
+            loss = fmaf(e, e, loss);
+            dy[k] = e * grad_scale;
+            if (pred) pred[p * OUT + k] = acc;
+        }
+    });
+    reinterpret_cast<float4*>(&S.dy[warp][0][0])[lane] = make_float4(dy[0], dy[1], dy[2], dy[3]);
+    S.mask[warp][lane] = make_uint2(m1, m2);
+    return loss;
+}
+
+// Backward of the lane's point: d2, d1 (staged) and the feature gradient row.
+__device__ __noinline__ void mlp16_backward(int64_t p, int live, float* __restrict__ gx, Mlp16Smem* Sp, int warp,
+                                            int lane) {
+    using namespace mlp16;
+    Mlp16Smem& S = *Sp;
+    float4* sd1 = reinterpret_cast<float4*>(&S.d1[warp][0][0]);
+    float4* sd2 = reinterpret_cast<float4*>(&S.d2[warp][0][0]);
+    const float4 dy4 = reinterpret_cast<const float4*>(&S.dy[warp][0][0])[lane];
+    const uint2 mk = S.mask[warp][lane];
+    const float dy[3] = {dy4.x, dy4.y, dy4.z};
+    float h[16], v[16];
+    static_for<H>([&](auto J) {   // d2 -> h[]
+        constexpr int j = decltype(J)::value;
+        float acc = dy[0] * cweight<oW3 + j>();
+        acc = fmaf(dy[1], cweight<oW3 + H + j>(), acc);
+        acc = fmaf(dy[2], cweight<oW3 + 2 * H + j>(), acc);
+        h[j] = ((mk.y >> j) & 1u) ? acc : 0.0f;
+    });
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sd2[lane * 4 + swz16(lane, q)] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    static_for<H>([&](auto I) {   // d1 -> v[]
+        constexpr int i = decltype(I)::value;
+        float acc = 0.0f;
+        static_for<H>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            acc = fmaf(h[j], cweight<oW2 + j * H + i>(), acc);
+        });
+        v[i] = ((mk.x >> i) & 1u) ? acc : 0.0f;
+    });
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sd1[lane * 4 + swz16(lane, q)] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    if (live) {
+        float o[IN];
+        static_for<IN>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            float acc = 0.0f;
+            static_for<H>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                acc = fmaf(v[i], cweight<oW1 + i * IN + m>(), acc);
+            });
+            o[m] = acc;
+        });
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            reinterpret_cast<float4*>(gx + p * IN)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    }
+}
+
+__global__ void __launch_bounds__(kMlpThreads, 2)
+mlp16_mse_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, int64_t n, float grad_scale,
+                      float* __restrict__ gx, float* __restrict__ pred, double* __restrict__ loss_sum,
+                      float* __restrict__ grad_params) {
+    using namespace mlp16;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    Mlp16Smem& S = *reinterpret_cast<Mlp16Smem*>(s_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < kMlpConstFloats + 1; e += kMlpThreads) S.g[e] = 0.0f;
+    if (tid == 0) S.loss = 0.0;
+    __syncthreads();
+    // weight-gradient ownership: half = lane >> 4 walks points of that parity; r = lane & 15 -> block (ib, jb)
+    const int half = lane >> 4, r = lane & 15, ib = r >> 2, jb = r & 3;
+    float aW1[4][4], aW2[4][4], aW3[4], ab1[4], ab2[4], ab3 = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        aW3[a] = 0.0f; ab1[a] = 0.0f; ab2[a] = 0.0f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { aW1[a][b] = 0.0f; aW2[a][b] = 0.0f; }
+    }
+    float my_loss = 0.0f;
+    float4* sx = reinterpret_cast<float4*>(&S.x[warp][0][0]);
+    float4* sh1 = reinterpret_cast<float4*>(&S.h1[warp][0][0]);
+    float4* sh2 = reinterpret_cast<float4*>(&S.h2[warp][0][0]);
+    float4* sd1 = reinterpret_cast<float4*>(&S.d1[warp][0][0]);
+    float4* sd2 = reinterpret_cast<float4*>(&S.d2[warp][0][0]);
+
+    const int64_t warps_total = (int64_t)gridDim.x * kMlpWarps;
+    for (int64_t base = ((int64_t)blockIdx.x * kMlpWarps + warp) * 32; base < n; base += warps_total * 32) {
+        const int64_t p = base + lane;
+        const int live = p < n;
+        __syncwarp();  // the previous iteration's weight-gradient reads of the staging rows are done
+        my_loss += mlp16_forward(x, gt, p, live, grad_scale, pred, &S, warp, lane);
+        mlp16_backward(p, live, gx, &S, warp, lane);
+        __syncwarp();
+        // ---- weight gradients: this half-warp walks the points of its parity ----
+#pragma unroll 4
+        for (int t = 0; t < 16; ++t) {
+            const int q = 2 * t + half;
+            const float4 d1v = sd1[q * 4 + swz16(q, ib)];   // d1[q][4 ib ..]
+            const float4 xv = sx[q * 4 + swz16(q, jb)];     // x[q][4 jb ..]
+            const float4 d2v = sd2[q * 4 + swz16(q, ib)];
+            const float4 h1v = sh1[q * 4 + swz16(q, jb)];
+            const float4 h2v = sh2[q * 4 + swz16(q, jb)];
+            const float dyk = S.dy[warp][q][ib];            // ib doubles as the output index k (3 is the zero pad)
+            const float a1[4] = {d1v.x, d1v.y, d1v.z, d1v.w}, bx[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float a2[4] = {d2v.x, d2v.y, d2v.z, d2v.w}, bh[4] = {h1v.x, h1v.y, h1v.z, h1v.w};
+            const float b3v[4] = {h2v.x, h2v.y, h2v.z, h2v.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    aW1[a][b] = fmaf(a1[a], bx[b], aW1[a][b]);
+                    aW2[a][b] = fmaf(a2[a], bh[b], aW2[a][b]);
+                }
+                ab1[a] += a1[a];      // only the jb == 0 lanes' copies are used
+                ab2[a] += a2[a];
+                aW3[a] = fmaf(dyk, b3v[a], aW3[a]);
+            }
+            ab3 += dyk;
+        }
+    }
+    // ---- block reduction in shared memory, then one global add per CTA and value ----
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            atomicAdd(&S.g[oW1 + (4 * ib + a) * IN + 4 * jb + b], aW1[a][b]);
+            atomicAdd(&S.g[oW2 + (4 * ib + a) * H + 4 * jb + b], aW2[a][b]);
+        }
+        if (ib < OUT) atomicAdd(&S.g[oW3 + ib * H + 4 * jb + a], aW3[a]);
+        if (jb == 0) {
+            atomicAdd(&S.g[ob1 + 4 * ib + a], ab1[a]);
+            atomicAdd(&S.g[ob2 + 4 * ib + a], ab2[a]);
+        }
+    }
+    if (jb == 0 && ib < OUT) atomicAdd(&S.g[ob3 + ib], ab3);
+    const float wl = warp_sum(my_loss);
+    if (lane == 0) atomicAdd(&S.loss, (double)wl);
+    __syncthreads();
+    for (int e = tid; e < kMlpConstFloats; e += kMlpThreads) red_add(grad_params + e, S.g[e]);
+    if (tid == 0) atomicAdd(loss_sum, S.loss);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// IN = 16 on the tensor cores: mma.sync m16n8k8 TF32 with 3xTF32 error compensation.
+//
+// Every product of the step is a small dense contraction -- forward [32 points x 16] x [16 x 16], backward the same
+// with the transposed weights, weight gradients [16 x 32 points] x [32 points x 16] -- so one warp runs its 32 points
+// as two m16 tiles through `mma.sync`. Operands are split a = hi + lo in TF32 and each product is issued three
+// times (lo*hi + hi*lo + hi*hi, the 2^-22 lo*lo term dropped): fp32-grade results (the tests hold this kernel to the
+// same 1e-5 / 1e-4 gates as the FP32 SIMT kernels) at a third of the instruction count of the FFMA formulations
+// (measured: those are issue-bound, 3700 instructions per 32 points).
+//
+// Layout trick: the accumulator fragment of one layer (lane (g, t) holds rows g, g+8, columns 2t, 2t+1 of each
+// 8-column tile) is fed straight back as the A fragment of the next product by PERMUTING THE K INDEX -- logical
+// k = t is column 2t, logical k = t+4 is column 2t+1 -- and the weight fragments are built with the same permutation
+// once per CTA (shared memory, one LDS.128 per fragment: {b0.hi, b1.hi, b0.lo, b1.lo}). No shuffles between layers.
+// Weight gradients need the point index as K: the activations are staged per warp in shared memory ([point][24],
+// conflict-free for both the fragment-layout stores and the transposed fragment loads).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTcWarps = 6;
+constexpr int kTcThreads = kTcWarps * 32;
+constexpr int kTcStride = 24;   // floats per staged point row
+
+struct MlpTcSmem {
+    uint4 wf[20][32];                       // weight fragments (see the enum in the kernel)
+    float b1[16], b2[16], b3[4];
+    float x[kTcWarps][32][kTcStride], h1[kTcWarps][32][kTcStride], h2[kTcWarps][32][kTcStride];
+    float d1[kTcWarps][32][kTcStride], d2[kTcWarps][32][kTcStride];
+    float dy[kTcWarps][32][8];
+    float g[kMlpConstFloats + 1];           // block reduction of the gradients (packed order)
+    double loss;
+};
+
+// v = hi + lo with hi, lo TF32 (10 explicit mantissa bits). Round-to-nearest on the magnitude by integer add + mask:
+// `cvt.rna.tf32.f32` compiles to a ~5-instruction sequence on sm_100a (cuobjdump) and the step needs ~250 splits per
+// 32 points. The tensor core ignores the low 13 bits of a TF32 operand, so lo only needs the rounding add.
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi)) + 0x1000u;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += (ahi + alo) * (bhi + blo), small terms first
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], uint32_t bh0,
+                                     uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+    mma_tf32(c, alo, bh0, bh1);
+    mma_tf32(c, ahi, bl0, bl1);
+    mma_tf32(c, ahi, bh0, bh1);
+}
+// accumulator-layout tile (c0 c1 | c2 c3 = rows g | g+8, columns 2t, 2t+1) -> A fragment under the K permutation
+__device__ __forceinline__ void tile_to_a(const float (&c)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+    split_tf32(c[0], hi[0], lo[0]);
+    split_tf32(c[2], hi[1], lo[1]);
+    split_tf32(c[1], hi[2], lo[2]);
+    split_tf32(c[3], hi[3], lo[3]);
+}
+
+// out[mt][nt] (+)= in[mt][ks] x W-fragments; KS k-steps, NT n-tiles; fragment f(ks, nt) = wf[base + ks * NT + nt]
+template <int KS, int NT>
+__device__ __forceinline__ void tc_layer(const uint4 (*wf)[32], int base, int lane, const float (&in)[2][2][4],
+                                         float (&out)[2][2][4]) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        uint4 f[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) f[nt] = wf[base + ks * NT + nt][lane];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            uint32_t ahi[4], alo[4];
+            tile_to_a(in[mt][ks], ahi, alo);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma3(out[mt][nt], ahi, alo, f[nt].x, f[nt].y, f[nt].z, f[nt].w);
+        }
+    }
+}
+
+// stage a [32 points x 16] activation held in accumulator layout as rows of kTcStride floats
+__device__ __forceinline__ void tc_stage(float (*rows)[kTcStride], int g, int t, const float (&a)[2][2][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            *reinterpret_cast<float2*>(&rows[16 * mt + g][8 * nt + 2 * t]) = make_float2(a[mt][nt][0], a[mt][nt][1]);
+            *reinterpret_cast<float2*>(&rows[16 * mt + g + 8][8 * nt + 2 * t]) = make_float2(a[mt][nt][2], a[mt][nt][3]);
+        }
+}
+
+// acc[nt] += A^T B over the warp's 32 points: A = rowsA[p][16] (M index = column of A), B = rowsB[p][8 * NT]
+template <int NT, int SB>
+__device__ __forceinline__ void tc_wgrad(const float (*rowsA)[kTcStride], const float (*rowsB)[SB], int g, int t,
+                                         float (&acc)[NT][4]) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const int p0 = 8 * ks + t, p1 = p0 + 4;
+        uint32_t ahi[4], alo[4];
+        split_tf32(rowsA[p0][g], ahi[0], alo[0]);
+        split_tf32(rowsA[p0][g + 8], ahi[1], alo[1]);
+        split_tf32(rowsA[p1][g], ahi[2], alo[2]);
+        split_tf32(rowsA[p1][g + 8], ahi[3], alo[3]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(rowsB[p0][8 * nt + g], bh0, bl0);
+            split_tf32(rowsB[p1][8 * nt + g], bh1, bl1);
+            mma3(acc[nt], ahi, alo, bh0, bh1, bl0, bl1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 2)
+mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, int64_t n,
+                     const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
+                     const float* __restrict__ b2, const float* __restrict__ W3, const float* __restrict__ b3,
+                     float grad_scale, float* __restrict__ gx, float* __restrict__ pred, double* __restrict__ loss_sum,
+                     float* __restrict__ grad_params) {
+    constexpr int H = 16, OUT = 3;
+    constexpr int oW1 = 0, ob1 = oW1 + 256, oW2 = ob1 + H, ob2 = oW2 + 256, oW3 = ob2 + H, ob3 = oW3 + OUT * H;
+    // weight-fragment table: forward L1 (ks, nt) 0..3, L2 4..7, L3 (ks) 8..9; backward d2 (nt) 10..11, d1 (ks, nt)
+    // 12..15, feature gradient (ks, nt) 16..19
+    enum { F_L1 = 0, F_L2 = 4, F_L3 = 8, B_D2 = 10, B_D1 = 12, B_GX = 16 };
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    MlpTcSmem& S = *reinterpret_cast<MlpTcSmem*>(s_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    for (int e = tid; e < 20 * 32; e += kTcThreads) {
+        const int f = e >> 5, fl = e & 31, fg = fl >> 2, ft = fl & 3;
+        float w0 = 0.0f, w1 = 0.0f;
+        if (f < F_L3) {                      // y = W a : B[k = in][n = out]
+            const float* W = f < F_L2 ? W1 : W2;
+            const int q = f & 3, ks = q >> 1, nt = q & 1;
+            w0 = W[(8 * nt + fg) * 16 + 8 * ks + 2 * ft];
+            w1 = W[(8 * nt + fg) * 16 + 8 * ks + 2 * ft + 1];
+        } else if (f < B_D2) {               // W3: outputs padded to 8
+            const int ks = f - F_L3;
+            if (fg < OUT) { w0 = W3[fg * 16 + 8 * ks + 2 * ft]; w1 = W3[fg * 16 + 8 * ks + 2 * ft + 1]; }
+        } else if (f < B_D1) {               // d2 = dy W3 : B[k = out][n = j]
+            const int nt = f - B_D2;
+            if (2 * ft < OUT) w0 = W3[(2 * ft) * 16 + 8 * nt + fg];
+            if (2 * ft + 1 < OUT) w1 = W3[(2 * ft + 1) * 16 + 8 * nt + fg];
+        } else {                             // d_in = d_out W : B[k = out row][n = in column]
+            const float* W = f < B_GX ? W2 : W1;
+            const int q = (f - B_D1) & 3, ks = q >> 1, nt = q & 1;
+            w0 = W[(8 * ks + 2 * ft) * 16 + 8 * nt + fg];
+            w1 = W[(8 * ks + 2 * ft + 1) * 16 + 8 * nt + fg];
+        }
+        uint4 v;
+        split_tf32(w0, v.x, v.z);
+        split_tf32(w1, v.y, v.w);
+        S.wf[f][fl] = v;
+    }
+    for (int e = tid; e < kMlpConstFloats + 1; e += kTcThreads) S.g[e] = 0.0f;
+    if (tid < H) { S.b1[tid] = b1[tid]; S.b2[tid] = b2[tid]; }
+    if (tid < 4) S.b3[tid] = tid < OUT ? b3[tid] : 0.0f;
+    if (tid == 0) S.loss = 0.0;
+    __syncthreads();
+
+    float accW1[2][4], accW2[2][4], accW3[1][4], accb1[2][2], accb2[2][2], accb3[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { accW1[a][b] = 0.0f; accW2[a][b] = 0.0f; }
+        accb1[a][0] = accb1[a][1] = accb2[a][0] = accb2[a][1] = 0.0f;
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) accW3[0][b] = 0.0f;
+    float my_loss = 0.0f;
+    float (*sx)[kTcStride] = S.x[warp];
+    float (*sh1)[kTcStride] = S.h1[warp];
+    float (*sh2)[kTcStride] = S.h2[warp];
+    float (*sd1)[kTcStride] = S.d1[warp];
+    float (*sd2)[kTcStride] = S.d2[warp];
+    float (*sdy)[8] = S.dy[warp];
+
+    const int64_t warps_total = (int64_t)gridDim.x * kTcWarps;
+    float X[2][2][4];
+    auto load_x = [&](int64_t b) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int64_t row = b + 16 * mt + g + 8 * hh;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    float2 v = make_float2(0.0f, 0.0f);
+                    if (row < n) v = __ldg(reinterpret_cast<const float2*>(x + row * 16 + 8 * ks + 2 * t));
+                    X[mt][ks][2 * hh] = v.x;
+                    X[mt][ks][2 * hh + 1] = v.y;
+                }
+            }
+    };
+    load_x(((int64_t)blockIdx.x * kTcWarps + warp) * 32);
+    for (int64_t base = ((int64_t)blockIdx.x * kTcWarps + warp) * 32; base < n; base += warps_total * 32) {
+        // rows of this lane: base + 16 mt + g + 8 h. X was loaded by the previous iteration (software pipeline);
+        // the targets of this iteration are requested now, long before the loss needs them
+        float T[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int col = 2 * t + (r & 1);
+                const int64_t row = base + 16 * mt + g + 8 * (r >> 1);
+                T[mt][r] = (col < OUT && row < n) ? __ldg(gt + row * OUT + col) : 0.0f;
+            }
+        __syncwarp();  // the previous iteration's weight-gradient reads of the staging rows are done
+        tc_stage(sx, g, t, X);
+        // ---- forward ----
+        float h1[2][2][4], h2[2][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const float2 bb = *reinterpret_cast<const float2*>(&S.b1[8 * nt + 2 * t]);
+                h1[mt][nt][0] = h1[mt][nt][2] = bb.x;
+                h1[mt][nt][1] = h1[mt][nt][3] = bb.y;
+            }
+        tc_layer<2, 2>(S.wf, F_L1, lane, X, h1);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const float2 bb = *reinterpret_cast<const float2*>(&S.b2[8 * nt + 2 * t]);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) h1[mt][nt][r] = fmaxf(h1[mt][nt][r], 0.0f);
+                h2[mt][nt][0] = h2[mt][nt][2] = bb.x;
+                h2[mt][nt][1] = h2[mt][nt][3] = bb.y;
+            }
+        tc_stage(sh1, g, t, h1);
+        tc_layer<2, 2>(S.wf, F_L2, lane, h1, h2);
+        float Y[2][2][4];   // [mt][0] used (8 padded outputs); the second tile is a dummy of the generic helper
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) h2[mt][nt][r] = fmaxf(h2[mt][nt][r], 0.0f);
+            }
+        tc_stage(sh2, g, t, h2);
+        {
+            const float2 bb = *reinterpret_cast<const float2*>(&S.b3[(2 * t) & 3]);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                Y[mt][0][0] = Y[mt][0][2] = (t < 2) ? bb.x : 0.0f;
+                Y[mt][0][1] = Y[mt][0][3] = (t < 2) ? bb.y : 0.0f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) Y[mt][1][r] = 0.0f;
+            }
+        }
+        {   // 16 -> 3 (padded to one 8-column tile): K = 16 in two k-steps, fragments F_L3 + ks
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const uint4 f = S.wf[F_L3 + ks][lane];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    uint32_t ahi[4], alo[4];
+                    tile_to_a(h2[mt][ks], ahi, alo);
+                    mma3(Y[mt][0], ahi, alo, f.x, f.y, f.z, f.w);
+                }
+            }
+        }
+        // ---- loss and its gradient (columns 2t, 2t+1 < 3 are real) ----
+        float DY[2][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int col = 2 * t + (r & 1);
+                const int64_t row = base + 16 * mt + g + 8 * (r >> 1);
+                float d = 0.0f;
+                if (col < OUT && row < n) {
+                    const float y = Y[mt][0][r];
+                    const float e = y - T[mt][r];
+                    my_loss = fmaf(e, e, my_loss);
+                    d = e * grad_scale;
+                    if (pred) pred[row * OUT + col] = y;
+                }
+                DY[mt][0][r] = d;
+                DY[mt][1][r] = 0.0f;
+            }
+            *reinterpret_cast<float2*>(&sdy[16 * mt + g][2 * t]) = make_float2(DY[mt][0][0], DY[mt][0][1]);
+            *reinterpret_cast<float2*>(&sdy[16 * mt + g + 8][2 * t]) = make_float2(DY[mt][0][2], DY[mt][0][3]);
+            accb3[0] += DY[mt][0][0] + DY[mt][0][2];
+            accb3[1] += DY[mt][0][1] + DY[mt][0][3];
+        }
+        // ---- backward to the features ----
+        float D[2][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) D[mt][nt][r] = 0.0f;
+        tc_layer<1, 2>(S.wf, B_D2, lane, DY, D);                  // d2 = dy W3   (K = 8 padded outputs)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) D[mt][nt][r] = h2[mt][nt][r] > 0.0f ? D[mt][nt][r] : 0.0f;
+                accb2[nt][0] += D[mt][nt][0] + D[mt][nt][2];
+                accb2[nt][1] += D[mt][nt][1] + D[mt][nt][3];
+            }
+        tc_stage(sd2, g, t, D);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) h2[mt][nt][r] = 0.0f;   // h2 is dead: reuse as d1
+        tc_layer<2, 2>(S.wf, B_D1, lane, D, h2);                  // d1 = d2 W2
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    h2[mt][nt][r] = h1[mt][nt][r] > 0.0f ? h2[mt][nt][r] : 0.0f;
+                    D[mt][nt][r] = 0.0f;
+                }
+                accb1[nt][0] += h2[mt][nt][0] + h2[mt][nt][2];
+                accb1[nt][1] += h2[mt][nt][1] + h2[mt][nt][3];
+            }
+        tc_stage(sd1, g, t, h2);
+        tc_layer<2, 2>(S.wf, B_GX, lane, h2, D);                  // gx = d1 W1
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int64_t row = base + 16 * mt + g + 8 * hh;
+                if (row < n) {
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+                        *reinterpret_cast<float2*>(gx + row * 16 + 8 * nt + 2 * t) =
+                            make_float2(D[mt][nt][2 * hh], D[mt][nt][2 * hh + 1]);
+                }
+            }
+        load_x(base + warps_total * 32);   // next iteration's features: in flight behind the weight-gradient stage
+        __syncwarp();
+        // ---- weight gradients: K = the warp's 32 points, operands from the staged rows ----
+        tc_wgrad<2, kTcStride>(sd1, sx, g, t, accW1);    // dW1[i][m] = sum_p d1[p][i] x[p][m]
+        tc_wgrad<2, kTcStride>(sd2, sh1, g, t, accW2);   // dW2[j][i] = sum_p d2[p][j] h1[p][i]
+        tc_wgrad<1, 8>(sh2, sdy, g, t, accW3);           // dW3^T[j][k] = sum_p h2[p][j] dy[p][k]
+    }
+    // ---- block reduction in shared memory, then one global add per CTA and value ----
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = g + 8 * (r >> 1), col = 8 * nt + 2 * t + (r & 1);
+            atomicAdd(&S.g[oW1 + row * 16 + col], accW1[nt][r]);
+            atomicAdd(&S.g[oW2 + row * 16 + col], accW2[nt][r]);
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            atomicAdd(&S.g[ob1 + 8 * nt + 2 * t + e], accb1[nt][e]);
+            atomicAdd(&S.g[ob2 + 8 * nt + 2 * t + e], accb2[nt][e]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int j = g + 8 * (r >> 1), k = 2 * t + (r & 1);
+        if (k < OUT) atomicAdd(&S.g[oW3 + k * 16 + j], accW3[0][r]);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+        if (2 * t + e < OUT) atomicAdd(&S.g[ob3 + 2 * t + e], accb3[e]);
+    const float wl = warp_sum(my_loss);
+    if (lane == 0) atomicAdd(&S.loss, (double)wl);
+    __syncthreads();
+    for (int e = tid; e < kMlpConstFloats; e += kTcThreads) red_add(grad_params + e, S.g[e]);
     if (tid == 0) atomicAdd(loss_sum, S.loss);
 }
 

@@ -35,7 +35,13 @@ def test_fused_mlp_mse_matches_torch(lib, n, in_dim, ref_dtype):
         (3.0 * loss).backward()
         assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
         assert rel_err(pred.cpu().numpy(), pred_ref.detach().cpu().numpy()) <= 1e-5
-        assert rel_err(x.grad.cpu().numpy(), want["x"].cpu().numpy()) <= 1e-4
+        # Feature gradients go through two ReLU masks: a pre-activation within rounding distance of zero flips its
+        # mask and changes that ONE row by O(1) -- in any fp32-grade implementation (torch's own fp32 Linear shows 13 %
+        # on such rows, see above). Hold every row to 1e-4 except a handful of mask-flip rows (<= 1 in 10 000), and
+        # hold the typical row to 1e-5; the weight gradients (sums over all rows) are held to 1e-4 as everywhere.
+        err = (x.grad.double() - want["x"]).abs().amax(dim=1) / want["x"].abs().max()
+        assert int((err > 1e-4).sum()) <= n // 10000, int((err > 1e-4).sum())
+        assert float(err.quantile(0.999)) <= 1e-5
         for k, p in mlp.named_parameters():
             assert rel_err(p.grad.cpu().numpy(), want[k].cpu().numpy()) <= 1e-4, k
         return
