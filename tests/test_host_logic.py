@@ -174,3 +174,49 @@ def test_odd_feature_dim_raises_like_reference(lib):
     from shacira_b200 import grid_ops
     with pytest.raises(Exception, match="multiple of 2"):
         grid_ops.hashgrid2d(torch.zeros(4, 2), [17], 10, 0, torch.zeros(289, 1), None, torch.zeros(1, dtype=torch.int32))
+
+
+def test_codec_container_round_trip_and_size_accounting(lib):
+    """the fitted model as a real byte stream. Decoding restores round(latents) and every decoder /
+    MLP parameter exactly; the file is the reference's BPP formula (image_trainer.py:162-168) plus the histogram and
+    header the formula leaves out."""
+    import torch.nn as nn
+    from shacira_b200 import codec
+    from shacira_b200.grids import LatentGrid
+    torch.manual_seed(11)
+    dec = dict(ldecode_enabled=True, ldecode_type="single", use_sga=False, diff_sampling=True, use_shift=True,
+               ldecode_matrix="sq", latent_dim=2, norm="max", norm_every=10, ldec_std=0.1, decay_period=0.9,
+               temperature=0.1)
+    ent = dict(num_prob_layers=2, entropy_reg=1e-3, entropy_reg_end=1e-4, entropy_reg_sched="cosine", noise_freq=1)
+    mk = lambda: LatentGrid.from_geometric(feature_dim=4, num_lods=8, latent_dim=2, multiscale_type="cat",
+                                           resolution_dim=2, feature_std=0.1, codebook_bitwidth=12, min_grid_res=16,
+                                           max_grid_res=128, init_grid="uniform", conf_latent_decoder=dict(dec),
+                                           conf_entropy_reg=dict(ent))
+    grid = mk()
+    mlp = nn.Sequential(nn.Linear(32, 16), nn.ReLU(), nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 3))
+    with torch.no_grad():
+        grid.codebook.copy_(torch.randn_like(grid.codebook) * torch.tensor([3.0, 9.0]))
+        grid.latent_dec.div.copy_(torch.tensor([2.5, 7.0]))
+    blob = codec.encode_model(grid, mlp, extra_meta={"image": "synthetic"})
+    state = codec.decode_model(blob)
+    assert torch.equal(state["latents"], torch.round(grid.codebook.detach()).long())
+    assert state["header"]["meta"] == {"image": "synthetic"} and state["header"]["num_lods"] == 8
+    grid2, mlp2 = mk(), nn.Sequential(nn.Linear(32, 16), nn.ReLU(), nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 3))
+    codec.load_into(state, grid2, mlp2)
+    assert torch.equal(grid2.codebook.detach(), torch.round(grid.codebook.detach()))
+    for (k1, v1), (k2, v2) in zip(grid.latent_dec.state_dict().items(), grid2.latent_dec.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    for v1, v2 in zip(mlp.state_dict().values(), mlp2.state_dict().values()):
+        assert torch.equal(v1, v2)
+    # the decoder path only ever sees round(w): the decoded table decodes to the same features
+    assert torch.equal(grid2.latent_dec(grid2.codebook), grid.latent_dec(grid.codebook))
+    rep = codec.size_report(grid, mlp, blob, pixels=768 * 512)
+    assert rep["file_bytes"] == len(blob)
+    assert rep["latent_entropy_bits"] <= rep["latent_stream_bits"] <= rep["latent_entropy_bits"] * 1.01 + 128
+    # file = formula + (histogram, header, framing), and nothing else
+    assert 0 < rep["uncounted_by_reference_bits"] <= rep["histogram_bits"] + 8 * 2048
+    # corruption is detected, not silently decoded
+    with pytest.raises(ValueError):
+        codec.decode_model(b"XXXX" + blob[4:])
+    with pytest.raises(ValueError):
+        codec.decode_model(blob + b"\0")
