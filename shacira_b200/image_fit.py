@@ -97,6 +97,9 @@ class ImageFitStep:
         self.step_table = torch.zeros((), **f32)
         self.step_small = torch.zeros((), **f32)
         self._keep = []
+        # the bit-rate kernel depends on nothing but the table: it runs on a forked stream beside the grid / MLP
+        # kernels (it is latency bound: 17 us alone) and joins before the optimizer kernels
+        self.side = torch.cuda.Stream(device=dev)
         segs = []
 
         def seg(param, grad, n, lr, wd, rows=1, stride=0, scale=None, mul=1.0, div=None, group=1):
@@ -180,20 +183,24 @@ class ImageFitStep:
         lin = self.lin
         with torch.cuda.device(self.dev):
             st = _lib._stream()
+            cur = torch.cuda.current_stream(self.dev)
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                chk(lib.shacira_entropy_bits(P(lat), P(self.noise), self.T, self.C, P(self.prob), self.num_prob_layers,
+                                             self.fi, self.L, P(self.bits), P(self.g_ent), P(self.g_prob),
+                                             P(self.ent_scratch), self.ent_scratch.numel(), _lib._stream()))
             chk(lib.shacira_latent_forward_planned(self.plan.handle, P(lat), self.fi, self.rs, self.L, self.bw, self.C,
                                                    self.F, 1, P(self.A), P(shift), 0, P(self.feats), st))
             chk(lib.shacira_mlp_mse_step(P(self.feats), P(self.target), self.n, self.IN, self.H, self.OUT,
                                          P(lin[0].weight.data), P(lin[0].bias.data), P(lin[1].weight.data),
                                          P(lin[1].bias.data), P(lin[2].weight.data), P(lin[2].bias.data),
                                          P(self.gfeat), None, P(self.mlp_out), st))
-            chk(lib.shacira_entropy_bits(P(lat), P(self.noise), self.T, self.C, P(self.prob), self.num_prob_layers,
-                                         self.fi, self.L, P(self.bits), P(self.g_ent), P(self.g_prob),
-                                         P(self.ent_scratch), self.ent_scratch.numel(), st))
             self.g_dec.zero_()
             CF = self.C * self.F
             chk(lib.shacira_latent_backward_planned(self.plan.handle, P(self.gfeat), P(lat), self.fi, self.rs, self.L,
                                                     self.bw, self.C, self.F, 1, P(self.A), 0, self.T, 1, P(self.g_grid),
                                                     P(self.g_dec), P(self.g_dec[self.L * CF:]), st))
+            cur.wait_stream(self.side)
             chk(lib.shacira_adam_step_sum(P(lat), P(self.g_grid), P(self.g_ent), P(self.lam), 1.0 / self.T,
                                           P(self.m_table), P(self.v_table), self.T * self.C, self.grid_lr,
                                           self.betas[0], self.betas[1], self.eps, self.weight_decay,
