@@ -214,7 +214,9 @@ int shacira_adam_step_sum(float* param, const float* grad, const float* grad2, c
  *                                                         / (grad_div ? grad_div[i / div_group] : 1)
  * which covers the chain rules of this path without extra kernels: latent-decoder scale = A * div (sum of the
  * per-level dA rows, divided by div), shift (sum of per-level rows), density parameters (lambda / rows).
- * After the update, if A_out != NULL: A_out[c * F + f] = scale[c * F + f] / div[c] for the next step's kernels.
+ * After the update, if A_out != NULL: A_out[c * F + f] = scale[c * F + f] / div[c] for the next step's kernels
+ * (`scale` must then be the `param` of one of the segments). One launch, one CTA per segment; one call may be in
+ * flight per device at a time.
  * `step` (device float) is advanced by the call, and so is `extra_step` when not NULL. At most
  * SHACIRA_MAX_ADAM_SEGS segments. */
 #define SHACIRA_MAX_ADAM_SEGS 32
@@ -232,7 +234,7 @@ typedef struct {
     float lr;
     float weight_decay;
     float grad_mul;
-    float reserved;
+    float zero_grad; /* != 0: clear the gradient rows after use (they are accumulated into by the next step) */
 } shacira_adam_seg_t;
 int shacira_multi_adam_step(const shacira_adam_seg_t* segs, int32_t num_segs, float beta1, float beta2, float eps,
                             float* step, float* extra_step, const float* scale, const float* div, float* A_out,

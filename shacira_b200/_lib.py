@@ -31,7 +31,7 @@ class AdamSeg(ctypes.Structure):
     _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("grad_scale", _vp),
                 ("grad_div", _vp), ("n", _i32), ("grad_rows", _i32), ("grad_row_stride", _i32), ("div_group", _i32),
                 ("lr", ctypes.c_float), ("weight_decay", ctypes.c_float), ("grad_mul", ctypes.c_float),
-                ("reserved", ctypes.c_float)]
+                ("zero_grad", ctypes.c_float)]
 
 
 MAX_ADAM_SEGS = 32

@@ -562,8 +562,14 @@ int shacira_multi_adam_step(const shacira_adam_seg_t* segs, int32_t num_segs, fl
             return fail(SHACIRA_ERR_INVALID_ARGUMENT, "multi_adam_step: bad segment %d", i);
         S.seg[i] = g;
     }
-    multi_adam_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(S, beta1, beta2, eps, step, extra_step, scale, div, A_out,
-                                                           latent_dim, feature_dim);
+    if (num_segs == 0) return SHACIRA_OK;
+    if (A_out) {
+        bool owner = false;
+        for (int i = 0; i < num_segs; ++i) owner |= (segs[i].param == scale);
+        if (!owner) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "multi_adam_step: A_out needs `scale` among the segments");
+    }
+    multi_adam_kernel<<<num_segs, 128, 0, (cudaStream_t)stream>>>(S, beta1, beta2, eps, step, extra_step, scale, div,
+                                                                  A_out, latent_dim, feature_dim);
     LAUNCHED();
     return SHACIRA_OK;
 }

@@ -308,38 +308,47 @@ struct AdamSegs {
     int32_t num;
     int32_t pad[3];
 };
-__global__ void __launch_bounds__(256)
+// One CTA per segment (a single CTA walking ~20 tiny tensors pays ~1 us of load latency per tensor: 19 us measured).
+// The last CTA to finish (ticket) advances the step counters -- every CTA has read them by then -- and leaves the
+// ticket at 0 for the next launch. One multi-tensor Adam step may be in flight per device at a time.
+__device__ unsigned g_multi_adam_ticket = 0u;
+__global__ void __launch_bounds__(128)
 multi_adam_kernel(const __grid_constant__ AdamSegs S, float beta1, float beta2, float eps, float* __restrict__ step,
                   float* __restrict__ extra_step, const float* __restrict__ scale, const float* __restrict__ div,
                   float* __restrict__ A_out, int C, int F) {
     const float t = *step + 1.0f;
     const float bc1 = 1.0f - powf(beta1, t), bc2 = 1.0f - powf(beta2, t);
     const float inv_sqrt_bc2 = rsqrtf(bc2);
-    for (int s = 0; s < S.num; ++s) {
-        const shacira_adam_seg_t& sg = S.seg[s];
-        const float gs = sg.grad_mul * (sg.grad_scale ? *sg.grad_scale : 1.0f);
-        const float step_size = sg.lr / bc1;
-        for (int i = threadIdx.x; i < sg.n; i += 256) {
-            float g = 0.0f;
-            for (int r = 0; r < sg.grad_rows; ++r) g += sg.grad[(size_t)r * sg.grad_row_stride + i];
-            g *= gs;
-            if (sg.grad_div) g /= sg.grad_div[i / sg.div_group];
-            const float p = sg.param[i];
-            const float gk = fmaf(sg.weight_decay, p, g);
-            const float mk = fmaf(beta1, sg.exp_avg[i], (1.0f - beta1) * gk);
-            const float vk = fmaf(beta2, sg.exp_avg_sq[i], (1.0f - beta2) * gk * gk);
-            sg.exp_avg[i] = mk;
-            sg.exp_avg_sq[i] = vk;
-            sg.param[i] = p - step_size * mk / (sqrtf(vk) * inv_sqrt_bc2 + eps);
+    const shacira_adam_seg_t& sg = S.seg[blockIdx.x];
+    const float gs = sg.grad_mul * (sg.grad_scale ? *sg.grad_scale : 1.0f);
+    const float step_size = sg.lr / bc1;
+    for (int i = threadIdx.x; i < sg.n; i += 128) {
+        float g = 0.0f;
+        for (int r = 0; r < sg.grad_rows; ++r) g += sg.grad[(size_t)r * sg.grad_row_stride + i];
+        if (sg.zero_grad != 0.0f)
+            for (int r = 0; r < sg.grad_rows; ++r) const_cast<float*>(sg.grad)[(size_t)r * sg.grad_row_stride + i] = 0.0f;
+        g *= gs;
+        if (sg.grad_div) g /= sg.grad_div[i / sg.div_group];
+        const float p = sg.param[i];
+        const float gk = fmaf(sg.weight_decay, p, g);
+        const float mk = fmaf(beta1, sg.exp_avg[i], (1.0f - beta1) * gk);
+        const float vk = fmaf(beta2, sg.exp_avg_sq[i], (1.0f - beta2) * gk * gk);
+        sg.exp_avg[i] = mk;
+        sg.exp_avg_sq[i] = vk;
+        sg.param[i] = p - step_size * mk / (sqrtf(vk) * inv_sqrt_bc2 + eps);
+    }
+    __syncthreads();  // the block's updated values are visible to the block
+    // the CTA that owns the latent decoder's scale refreshes A = scale / div for the next step's kernels
+    if (A_out && sg.param == scale)
+        for (int e = threadIdx.x; e < C * F; e += 128) A_out[e] = scale[e] / div[e / F];
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&g_multi_adam_ticket, 1u) == gridDim.x - 1) {
+            *step = t;
+            if (extra_step) *extra_step += 1.0f;
+            g_multi_adam_ticket = 0u;
         }
     }
-    __syncthreads();  // every thread has read *step; the updated scale is visible to the block
-    if (threadIdx.x == 0) {
-        *step = t;
-        if (extra_step) *extra_step += 1.0f;
-    }
-    if (A_out)
-        for (int e = threadIdx.x; e < C * F; e += 256) A_out[e] = scale[e] / div[e / F];
 }
 
 // ---- symbols and histogram ---------------------------------------------------------------

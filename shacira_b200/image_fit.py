@@ -102,7 +102,7 @@ class ImageFitStep:
         self.side = torch.cuda.Stream(device=dev)
         segs = []
 
-        def seg(param, grad, n, lr, wd, rows=1, stride=0, scale=None, mul=1.0, div=None, group=1):
+        def seg(param, grad, n, lr, wd, rows=1, stride=0, scale=None, mul=1.0, div=None, group=1, zero=False):
             m, v = torch.zeros(n, **f32), torch.zeros(n, **f32)
             self._keep += [m, v]
             s = _lib.AdamSeg()
@@ -111,7 +111,7 @@ class ImageFitStep:
             s.grad_scale = scale.data_ptr() if scale is not None else None
             s.grad_div = div.data_ptr() if div is not None else None
             s.n, s.grad_rows, s.grad_row_stride, s.div_group = n, rows, stride, group
-            s.lr, s.weight_decay, s.grad_mul = lr, wd, mul
+            s.lr, s.weight_decay, s.grad_mul, s.zero_grad = lr, wd, mul, 1.0 if zero else 0.0
             segs.append(s)
 
         packed = self.mlp_out[2:]
@@ -123,11 +123,11 @@ class ImageFitStep:
         CF = self.C * self.F
         # latent_dec group (base_trainer.py:225-229): scale = A * div  =>  dscale = (sum_l dA_l) / div
         seg(layer.scale.data, self.g_dec, CF, float(ldec_lr), float(weight_decay_decoder), rows=self.L, stride=CF,
-            div=dec.div.data, group=self.F)
+            div=dec.div.data, group=self.F, zero=True)
         self.has_shift = layer.shift is not None
         if self.has_shift:
             seg(layer.shift.data, self.g_dec[self.L * CF:], self.F, float(ldec_lr), float(weight_decay_decoder),
-                rows=self.L, stride=self.F)
+                rows=self.L, stride=self.F, zero=True)
         # prob_model group: lr fixed 1e-4 (base_trainer.py:230-234); gradient = lambda / rows * d(bits)
         used = [0] if self.num_prob_layers > 1 else []
         if self.num_prob_layers > 2:
@@ -195,7 +195,8 @@ class ImageFitStep:
                                          P(lin[0].weight.data), P(lin[0].bias.data), P(lin[1].weight.data),
                                          P(lin[1].bias.data), P(lin[2].weight.data), P(lin[2].bias.data),
                                          P(self.gfeat), None, P(self.mlp_out), st))
-            self.g_dec.zero_()
+            if not self.has_shift:
+                self.g_dec[self.L * self.C * self.F:].zero_()   # no segment consumes (and clears) the shift rows
             CF = self.C * self.F
             chk(lib.shacira_latent_backward_planned(self.plan.handle, P(self.gfeat), P(lat), self.fi, self.rs, self.L,
                                                     self.bw, self.C, self.F, 1, P(self.A), 0, self.T, 1, P(self.g_grid),
