@@ -170,6 +170,7 @@ def cpu_step(wl, s, want_entropy=False):
 
 def run_cpu(wl, steps, warmup):
     import oracle
+    oracle.use_all_cores()   # torchrun exports OMP_NUM_THREADS=1; the CPU arm gets every host core
     n = wl["sets"][0]["coords"].shape[0]
     for i in range(warmup):
         cpu_step(wl, wl["sets"][i % ROTATE])

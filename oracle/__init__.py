@@ -37,6 +37,8 @@ def lib():
         L.oracle_hashgrid_backward.restype = i64
         L.oracle_hashgrid_backward.argtypes = [ctypes.c_int, vp, i64, vp, i64, vp, vp, i32, i32, i32, vp]
         L.oracle_num_threads.restype = ctypes.c_int
+        L.oracle_set_num_threads.restype = None
+        L.oracle_set_num_threads.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
 
@@ -51,6 +53,19 @@ def _i32(a):
 
 def num_threads():
     return int(lib().oracle_num_threads())
+
+
+def use_all_cores():
+    """All host cores for the timed CPU arm (torchrun sets OMP_NUM_THREADS=1 for its ranks). Returns the count."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oracle_set_num_threads(n)
+    try:
+        import torch
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    return num_threads()
 
 
 def level_layout(resolutions, bitwidth, dim):

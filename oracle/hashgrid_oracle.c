@@ -243,6 +243,15 @@ int64_t oracle_hashgrid_backward(int dim, const float* coords, int64_t n, const 
     return redirected;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the timed reference arm asks for all host cores explicitly. */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
