@@ -44,6 +44,14 @@ def main():
                                                         bench.BITWIDTH, 1, 1, 1, p(A), 0, T, 1, p(s["gl"]),
                                                         p(gA) if dec else None, p(gS) if dec else None, st))
 
+    for s_ in sets:
+        s_["gmax"] = s_["grad_out"].abs().amax(dim=0).contiguous()
+
+    def bwd_bounded(s, st):
+        _lib._check(lib.shacira_latent_backward_planned_bounded(s["plan"].handle, p(s["grad_out"]), p(lat), fi, rs, L,
+                                                                bench.BITWIDTH, 1, 1, 1, p(A), 0, T, 1, p(s["gl"]),
+                                                                p(gA), p(gS), p(s["gmax"]), st))
+
     def fwd_pp(s, st):
         _lib._check(lib.shacira_latent_forward(2, p(s["coords"]), n, p(lat), fi, rs, L, bench.BITWIDTH, 1, 1, 1, p(A),
                                                p(shift), 0, p(s["feats"]), p(s["z"]), st))
@@ -76,7 +84,7 @@ def main():
 
     out = {}
     only_ent = bool(os.environ.get("ONLY_ENT"))
-    for name, fn in ((("entropy_fwd_bwd", ent),) if only_ent else (("entropy_fwd_bwd", ent), ("mlp_mse_step", mlpk), ("fwd_tiled", fwd), ("bwd_tiled_dec", bwd), ("bwd_tiled_nodec", lambda s, st: bwd(s, st, False)),
+    for name, fn in ((("entropy_fwd_bwd", ent),) if only_ent else (("entropy_fwd_bwd", ent), ("mlp_mse_step", mlpk), ("fwd_tiled", fwd), ("bwd_tiled_dec", bwd), ("bwd_tiled_nodec", lambda s, st: bwd(s, st, False)), ("bwd_tiled_dec_bounded", bwd_bounded),
                      ("fwd_pointparallel", fwd_pp), ("bwd_pointparallel", bwd_pp),
                      ("step_tiled", lambda s, st: (fwd(s, st), bwd(s, st))))):
         stream = torch.cuda.Stream()

@@ -146,6 +146,17 @@ int shacira_latent_backward_planned(const shacira_plan_t* plan, const float* gra
                                     int32_t round_flag, const float* A, int32_t per_level, int64_t table_rows,
                                     int32_t zero_first, float* grad_latents, float* grad_A, float* grad_shift,
                                     shacira_stream_t stream);
+/* The same with `level_max` (device, [num_lods * feature_dim], may be NULL): upper bounds of |grad_output| per
+ * column, e.g. reduced by the kernel that produced the rows (shacira_mlp_mse_step_bounded). The tiled backward
+ * accumulates in fixed point and otherwise finds the bound itself with an extra pass over every tile's gradient rows;
+ * with the bound that second read of grad_output is skipped. The fixed-point step is then 2^-19 of the GLOBAL
+ * per-level bound instead of the tile's own maximum. A bound that is too small is an error of the caller (sums wrap). */
+int shacira_latent_backward_planned_bounded(const shacira_plan_t* plan, const float* grad_output,
+                                            const float* latents, const int32_t* first_idx, const int32_t* resolutions,
+                                            int32_t num_lods, int32_t codebook_bitwidth, int32_t latent_dim,
+                                            int32_t feature_dim, int32_t round_flag, const float* A, int32_t per_level,
+                                            int64_t table_rows, int32_t zero_first, float* grad_latents, float* grad_A,
+                                            float* grad_shift, const float* level_max, shacira_stream_t stream);
 
 /* ---- factorized-density bit-rate estimate -------------------------------------------- */
 /* LatentGrid.ent_loss (latent_grid.py:122-136) + BitEstimator/Bitparm
@@ -190,6 +201,13 @@ int shacira_mlp_mse_step(const float* features, const float* target, int64_t n, 
                          int32_t out_dim, const float* W1, const float* b1, const float* W2, const float* b2,
                          const float* W3, const float* b3, float* grad_features, float* pred, void* out,
                          shacira_stream_t stream);
+
+/* The same, also reducing max |grad_features[:, j]| per input column j into grad_feature_absmax (device,
+ * [in_dim], written by the call) for shacira_latent_backward_planned_bounded. in_dim = 16 only. */
+int shacira_mlp_mse_step_bounded(const float* features, const float* target, int64_t n, int32_t in_dim,
+                                 int32_t hidden_dim, int32_t out_dim, const float* W1, const float* b1, const float* W2,
+                                 const float* b2, const float* W3, const float* b3, float* grad_features, float* pred,
+                                 void* out, float* grad_feature_absmax, shacira_stream_t stream);
 
 /* ---- fused Adam over the latent table ------------------------ */
 /* torch.optim.Adam semantics (L2 weight decay added to the gradient, bias correction, eps outside the sqrt) for

@@ -55,11 +55,13 @@ SIGNATURES = {
     "shacira_plan_debug": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     "shacira_latent_forward_planned": (ctypes.c_int, [_vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "shacira_latent_backward_planned": (ctypes.c_int, [_vp, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "shacira_latent_backward_planned_bounded": (ctypes.c_int, [_vp, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "shacira_entropy_bits": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _c_int32_p, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "shacira_entropy_scratch_bytes": (_i64, [_i32, _i32]),
     "shacira_quantize_symbols": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "shacira_symbol_histogram": (ctypes.c_int, [_vp, _i64, _i32, _c_int32_p, _i32, _vp, _vp]),
     "shacira_mlp_mse_step": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "shacira_mlp_mse_step_bounded": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "shacira_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _i32, _vp]),
     "shacira_adam_step_sum": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_float, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _i32, _vp]),
     "shacira_multi_adam_step": (ctypes.c_int, [_vp, _i32, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
@@ -346,7 +348,8 @@ def latent_forward_planned(plan, latents, first_idx, resolutions, bitwidth, A, s
 
 
 def latent_backward_planned(plan, grad_output, latents, first_idx, resolutions, bitwidth, A, latent_dim, feature_dim,
-                            table_rows, round_flag, want_decoder_grads):
+                            table_rows, round_flag, want_decoder_grads, level_max=None):
+    """`level_max` [L * F] (optional): upper bounds of |grad_output| per column; skips the kernel's own max pass."""
     lib = load()
     grad_output = _f32c(grad_output, "grad_output")
     A = _f32c(A, "A")
@@ -361,9 +364,10 @@ def latent_backward_planned(plan, grad_output, latents, first_idx, resolutions, 
         gA = torch.zeros((L, latent_dim, feature_dim), dtype=torch.float32, device=dev)
         gS = torch.zeros((L, feature_dim), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _check(lib.shacira_latent_backward_planned(plan.handle, _ptr(grad_output), _ptr(latents), fi, rs, L, bitwidth,
-                                                   latent_dim, feature_dim, 1 if round_flag else 0, _ptr(A), per_level,
-                                                   table_rows, 1, _ptr(gl), _ptr(gA), _ptr(gS), _stream()))
+        _check(lib.shacira_latent_backward_planned_bounded(
+            plan.handle, _ptr(grad_output), _ptr(latents), fi, rs, L, bitwidth, latent_dim, feature_dim,
+            1 if round_flag else 0, _ptr(A), per_level, table_rows, 1, _ptr(gl), _ptr(gA), _ptr(gS),
+            _ptr(_f32c(level_max, "level_max") if level_max is not None else None), _stream()))
     return gl, gA, gS
 
 
@@ -407,8 +411,9 @@ def entropy_bits(latents, noise, params, num_layers, first_idx=None, want_grads=
     return bits, gl, gp
 
 
-def mlp_mse_step(features, target, W1, b1, W2, b2, W3, b3, want_pred=False):
-    """Fused decoder MLP + MSE: returns (loss scalar tensor, grad_features, pred | None, grads dict)."""
+def mlp_mse_step(features, target, W1, b1, W2, b2, W3, b3, want_pred=False, absmax_out=None):
+    """Fused decoder MLP + MSE: returns (loss scalar tensor, grad_features, pred | None, grads dict).
+    `absmax_out` [in_dim] float32 (optional, in_dim = 16): receives max |grad_features| per column."""
     lib = load()
     features, target = _f32c(features, "features"), _f32c(target, "target")
     ws = [_f32c(t, "weights") for t in (W1, b1, W2, b2, W3, b3)]
@@ -420,8 +425,8 @@ def mlp_mse_step(features, target, W1, b1, W2, b2, W3, b3, want_pred=False):
     n_par = H * IN + H + H * H + H + OUT * H + OUT
     out = torch.empty(2 + n_par, dtype=torch.float32, device=dev)  # 8-byte loss + packed gradients
     with torch.cuda.device(dev):
-        _check(lib.shacira_mlp_mse_step(_ptr(features), _ptr(target), n, IN, H, OUT, *[_ptr(w) for w in ws], _ptr(gx),
-                                        _ptr(pred), _ptr(out), _stream()))
+        _check(lib.shacira_mlp_mse_step_bounded(_ptr(features), _ptr(target), n, IN, H, OUT, *[_ptr(w) for w in ws],
+                                                _ptr(gx), _ptr(pred), _ptr(out), _ptr(absmax_out), _stream()))
     sse = out[:2].view(torch.float64)[0]
     loss = (sse / (n * OUT)).to(torch.float32)
     return loss, gx, pred, out[2:]  # packed gradients: W1 | b1 | W2 | b2 | W3 | b3

@@ -263,7 +263,8 @@ int launch_mlp16(const float* x, const float* gt, int64_t n, const float* W1, co
 
 // IN = 16 on the tensor cores (mlp16_tc_step_kernel: mma.sync TF32 with 3xTF32 compensation)
 int launch_mlp_tc(const float* x, const float* gt, int64_t n, const float* W1, const float* b1, const float* W2,
-                  const float* b2, const float* W3, const float* b3, float* gx, float* pred, void* out, cudaStream_t s) {
+                  const float* b2, const float* W3, const float* b3, float* gx, float* pred, void* out, float* absmax,
+                  cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         CUDA_OK(cudaFuncSetAttribute(mlp16_tc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -272,13 +273,15 @@ int launch_mlp_tc(const float* x, const float* gt, int64_t n, const float* W1, c
     }
     const size_t out_bytes = 8 + sizeof(float) * kMlpConstFloats;
     CUDA_OK(cudaMemsetAsync(out, 0, out_bytes, s));
+    if (absmax) CUDA_OK(cudaMemsetAsync(absmax, 0, sizeof(float) * 16, s));
     int64_t warps = (n + 31) / 32;
     int64_t blocks = (warps + kTcWarps - 1) / kTcWarps;
     const int64_t cap = (int64_t)sm_count() * 2;  // persistent: 2 CTAs per SM fit the shared memory
     if (blocks > cap) blocks = cap;
     const float scale = (float)(2.0 / ((double)n * 3.0));
     mlp16_tc_step_kernel<<<(int)blocks, kTcThreads, sizeof(MlpTcSmem), s>>>(x, gt, n, W1, b1, W2, b2, W3, b3, scale, gx,
-                                                                            pred, (double*)out, (float*)((char*)out + 8));
+                                                                            pred, (double*)out, (float*)((char*)out + 8),
+                                                                            (unsigned*)absmax);
     LAUNCHED();
     return SHACIRA_OK;
 }
@@ -616,10 +619,10 @@ int shacira_symbol_histogram(const float* latents, int64_t table_rows, int32_t l
 }
 
 // ---- fused decoder MLP + MSE ------------------------------------------------------------
-int shacira_mlp_mse_step(const float* features, const float* target, int64_t n, int32_t in_dim, int32_t hidden_dim,
-                         int32_t out_dim, const float* W1, const float* b1, const float* W2, const float* b2,
-                         const float* W3, const float* b3, float* grad_features, float* pred, void* out,
-                         shacira_stream_t stream) {
+int shacira_mlp_mse_step_bounded(const float* features, const float* target, int64_t n, int32_t in_dim,
+                                 int32_t hidden_dim, int32_t out_dim, const float* W1, const float* b1, const float* W2,
+                                 const float* b2, const float* W3, const float* b3, float* grad_features, float* pred,
+                                 void* out, float* grad_feature_absmax, shacira_stream_t stream) {
     if (!features || !target || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !grad_features || !out)
         return fail(SHACIRA_ERR_INVALID_ARGUMENT, "mlp_mse_step: NULL argument");
     if (n <= 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "mlp_mse_step: n must be positive");
@@ -633,14 +636,27 @@ int shacira_mlp_mse_step(const float* features, const float* target, int64_t n, 
                 const char* e = getenv("SHACIRA_MLP_IMPL");
                 return !e ? 0 : (!strcmp(e, "const") ? 1 : (!strcmp(e, "smem") ? 2 : 0));
             }();
+            if (grad_feature_absmax && impl != 0)
+                return fail(SHACIRA_ERR_UNSUPPORTED, "mlp_mse_step_bounded: only the tensor-core kernel reduces the bound");
             if (impl == 2) return launch_mlp<16>(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
             if (impl == 1) return launch_mlp16(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
-            return launch_mlp_tc(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
+            return launch_mlp_tc(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out,
+                                 grad_feature_absmax, s);
         }
-        case 24: return launch_mlp<24>(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
-        case 32: return launch_mlp<32>(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
+        case 24: if (grad_feature_absmax) return fail(SHACIRA_ERR_UNSUPPORTED, "mlp_mse_step_bounded: in_dim 16 only");
+                 return launch_mlp<24>(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
+        case 32: if (grad_feature_absmax) return fail(SHACIRA_ERR_UNSUPPORTED, "mlp_mse_step_bounded: in_dim 16 only");
+                 return launch_mlp<32>(features, target, n, W1, b1, W2, b2, W3, b3, grad_features, pred, out, s);
         default: return fail(SHACIRA_ERR_UNSUPPORTED, "mlp_mse_step: in_dim %d not in {16,24,32}", in_dim);
     }
+}
+
+int shacira_mlp_mse_step(const float* features, const float* target, int64_t n, int32_t in_dim, int32_t hidden_dim,
+                         int32_t out_dim, const float* W1, const float* b1, const float* W2, const float* b2,
+                         const float* W3, const float* b3, float* grad_features, float* pred, void* out,
+                         shacira_stream_t stream) {
+    return shacira_mlp_mse_step_bounded(features, target, n, in_dim, hidden_dim, out_dim, W1, b1, W2, b2, W3, b3,
+                                        grad_features, pred, out, nullptr, stream);
 }
 
 // ---- latent bitstream (host) ---------------------------------------------------------------

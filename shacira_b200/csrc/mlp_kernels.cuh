@@ -549,6 +549,7 @@ struct MlpTcSmem {
     float d1[kTcWarps][32][kTcStride], d2[kTcWarps][32][kTcStride];
     float dy[kTcWarps][32][8];
     float g[kMlpConstFloats + 1];           // block reduction of the gradients (packed order)
+    unsigned cmax[16];                      // max |feature gradient| per input column (bit patterns)
     double loss;
 };
 
@@ -636,7 +637,7 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
                      const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                      const float* __restrict__ b2, const float* __restrict__ W3, const float* __restrict__ b3,
                      float grad_scale, float* __restrict__ gx, float* __restrict__ pred, double* __restrict__ loss_sum,
-                     float* __restrict__ grad_params) {
+                     float* __restrict__ grad_params, unsigned* __restrict__ gx_absmax) {
     constexpr int H = 16, OUT = 3;
     constexpr int oW1 = 0, ob1 = oW1 + 256, oW2 = ob1 + H, ob2 = oW2 + 256, oW3 = ob2 + H, ob3 = oW3 + OUT * H;
     // weight-fragment table: forward L1 (ks, nt) 0..3, L2 4..7, L3 (ks) 8..9; backward d2 (nt) 10..11, d1 (ks, nt)
@@ -675,6 +676,7 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
     if (tid < H) { S.b1[tid] = b1[tid]; S.b2[tid] = b2[tid]; }
     if (tid < 4) S.b3[tid] = tid < OUT ? b3[tid] : 0.0f;
     if (tid == 0) S.loss = 0.0;
+    if (tid < 16) S.cmax[tid] = 0u;
     __syncthreads();
 
     float accW1[2][4], accW2[2][4], accW3[1][4], accb1[2][2], accb2[2][2], accb3[2] = {0.0f, 0.0f};
@@ -687,6 +689,7 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
 #pragma unroll
     for (int b = 0; b < 4; ++b) accW3[0][b] = 0.0f;
     float my_loss = 0.0f;
+    float cmax[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};   // max |gx| of this lane's columns 8 nt + 2 t + e
     float (*sx)[kTcStride] = S.x[warp];
     float (*sh1)[kTcStride] = S.h1[warp];
     float (*sh2)[kTcStride] = S.h2[warp];
@@ -851,9 +854,12 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
                 const int64_t row = base + 16 * mt + g + 8 * hh;
                 if (row < n) {
 #pragma unroll
-                    for (int nt = 0; nt < 2; ++nt)
+                    for (int nt = 0; nt < 2; ++nt) {
                         *reinterpret_cast<float2*>(gx + row * 16 + 8 * nt + 2 * t) =
                             make_float2(D[mt][nt][2 * hh], D[mt][nt][2 * hh + 1]);
+                        cmax[nt][0] = fmaxf(cmax[nt][0], fabsf(D[mt][nt][2 * hh]));
+                        cmax[nt][1] = fmaxf(cmax[nt][1], fabsf(D[mt][nt][2 * hh + 1]));
+                    }
                 }
             }
         load_x(base + warps_total * 32);   // next iteration's features: in flight behind the weight-gradient stage
@@ -886,10 +892,23 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
 #pragma unroll
     for (int e = 0; e < 2; ++e)
         if (2 * t + e < OUT) atomicAdd(&S.g[ob3 + 2 * t + e], accb3[e]);
+    if (gx_absmax) {   // non-negative floats order like their bit patterns
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                unsigned m = __float_as_uint(cmax[nt][e]);
+                m = max(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                m = max(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                m = max(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                if (g == 0) atomicMax(&S.cmax[8 * nt + 2 * t + e], m);
+            }
+    }
     const float wl = warp_sum(my_loss);
     if (lane == 0) atomicAdd(&S.loss, (double)wl);
     __syncthreads();
     for (int e = tid; e < kMlpConstFloats; e += kTcThreads) red_add(grad_params + e, S.g[e]);
+    if (gx_absmax && tid < 16) atomicMax(gx_absmax + tid, S.cmax[tid]);
     if (tid == 0) atomicAdd(loss_sum, S.loss);
 }
 

@@ -118,7 +118,7 @@ int launch_fwd(shacira_plan* p, const float* lat, const LevelParams& lp, const f
 
 template <int D, int C, int F>
 int launch_bwd(shacira_plan* p, const float* g, const float* lat, const LevelParams& lp, const float* A,
-               int per_level, int round_flag, float* gl, float* gA, float* gS, cudaStream_t s) {
+               int per_level, int round_flag, float* gl, float* gA, float* gS, const float* level_max, cudaStream_t s) {
     const int nA = per_level ? lp.num_lods : 1;
     const bool dec = gA != nullptr || gS != nullptr;
     // shared memory: fixed-point accumulators (kRepBudget ints of lane-replicated copies shared by the CA
@@ -138,10 +138,10 @@ int launch_bwd(shacira_plan* p, const float* g, const float* lat, const LevelPar
     smem = smem_pad(smem);
     if (dec)
         latent_bwd_tiled_kernel<D, C, F, true><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), g, lat, lp, A, per_level,
-                                                                                      round_flag, gl, gA, gS, cap, cap_acc);
+                                                                                      round_flag, gl, gA, gS, cap, cap_acc, level_max);
     else
         latent_bwd_tiled_kernel<D, C, F, false><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), g, lat, lp, A, per_level,
-                                                                                       round_flag, gl, gA, gS, cap, cap_acc);
+                                                                                       round_flag, gl, gA, gS, cap, cap_acc, level_max);
     LAUNCHED();
     return SHACIRA_OK;
 }
@@ -319,12 +319,12 @@ int shacira_latent_forward_planned(const shacira_plan_t* plan, const float* late
                   (launch_fwd<3, kC, kF>(const_cast<shacira_plan*>(plan), latents, lp, A, shift, per_level, round_flag, feats, s)))
 }
 
-int shacira_latent_backward_planned(const shacira_plan_t* plan, const float* grad_output, const float* latents,
+int shacira_latent_backward_planned_bounded(const shacira_plan_t* plan, const float* grad_output, const float* latents,
                                     const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
                                     int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim,
                                     int32_t round_flag, const float* A, int32_t per_level, int64_t table_rows,
                                     int32_t zero_first, float* grad_latents, float* grad_A, float* grad_shift,
-                                    shacira_stream_t stream) {
+                                    const float* level_max, shacira_stream_t stream) {
     if (!plan) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan is NULL");
     LevelParams lp;
     int rc = build_levels(plan->dim, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
@@ -340,11 +340,24 @@ int shacira_latent_backward_planned(const shacira_plan_t* plan, const float* gra
     if (plan->dim == 2) {
         T_DISPATCH_CF(latent_dim, feature_dim,
                       (launch_bwd<2, kC, kF>(const_cast<shacira_plan*>(plan), grad_output, latents, lp, A, per_level, round_flag, grad_latents,
-                                             grad_A, grad_shift, s)))
+                                             grad_A, grad_shift, level_max, s)))
     }
     T_DISPATCH_CF(latent_dim, feature_dim,
                   (launch_bwd<3, kC, kF>(const_cast<shacira_plan*>(plan), grad_output, latents, lp, A, per_level, round_flag, grad_latents, grad_A,
-                                         grad_shift, s)))
+                                         grad_shift, level_max, s)))
+}
+
+
+int shacira_latent_backward_planned(const shacira_plan_t* plan, const float* grad_output, const float* latents,
+                                    const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                                    int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim,
+                                    int32_t round_flag, const float* A, int32_t per_level, int64_t table_rows,
+                                    int32_t zero_first, float* grad_latents, float* grad_A, float* grad_shift,
+                                    shacira_stream_t stream) {
+    return shacira_latent_backward_planned_bounded(plan, grad_output, latents, first_idx, resolutions, num_lods,
+                                                   codebook_bitwidth, latent_dim, feature_dim, round_flag, A, per_level,
+                                                   table_rows, zero_first, grad_latents, grad_A, grad_shift, nullptr,
+                                                   stream);
 }
 
 }  // extern "C"

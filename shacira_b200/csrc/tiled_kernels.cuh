@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(kTileThreads, (C * F <= 4) ? SHACIRA_MIN_CTAS 
 latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, const float* __restrict__ latents,
                         const __grid_constant__ LevelParams lp, const float* __restrict__ A, int per_level,
                         int round_flag, float* __restrict__ grad_latents, float* __restrict__ grad_A,
-                        float* __restrict__ grad_shift, int cap, int cap_acc) {
+                        float* __restrict__ grad_shift, int cap, int cap_acc, const float* __restrict__ level_max) {
     constexpr bool SG = DEC && (F <= C);
     constexpr bool ZP = DEC && !SG;          // per-point z recomputation
     constexpr int CA = SG ? F : C;           // accumulator channels
@@ -695,6 +695,30 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
         }
         if (threadIdx.x < SHACIRA_MAX_LEVELS) s_gmax[threadIdx.x] = 0u;
         __syncthreads();
+        if (level_max) {
+            // The caller knows an upper bound of |grad_output| per level (e.g. the kernel that produced the rows
+            // reduced it on the way): the fixed-point scales come from it and the pass over the tile's gradient rows
+            // (a second read of every row) is skipped. The bound of the accumulated quantity is |g| itself in
+            // scatter-g mode, else |A^T g| <= max|g| * max_c sum_f |A[c][f]|.
+            if (threadIdx.x < L) {
+                float m = __ldg(level_max + threadIdx.x * F);
+#pragma unroll
+                for (int jf = 1; jf < F; ++jf) m = fmaxf(m, __ldg(level_max + threadIdx.x * F + jf));
+                if (!SG) {
+                    const int la = per_level ? threadIdx.x : 0;
+                    float amax = 0.0f;
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) {
+                        float sum = 0.0f;
+#pragma unroll
+                        for (int jf = 0; jf < F; ++jf) sum += fabsf(s_A[(la * C + ch) * F + jf]);
+                        amax = fmaxf(amax, sum);
+                    }
+                    m *= amax;
+                }
+                s_gmax[threadIdx.x] = __float_as_uint(m);
+            }
+        } else
         // pass 1: per-level maxima of what will be accumulated (they fix the fixed-point scales).
         // Points outer, whole gradient row (all levels) in flight per point: one round trip to memory per
         // group of KP1 points instead of one per level chunk. Per-level running maxima live in shared memory

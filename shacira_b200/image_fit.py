@@ -21,6 +21,7 @@ The module parameters stay the single source of truth: the kernels read and upda
 `grid.interpolate`, `grid.size()`, `state_dict()` etc. see the trained values at any time.
 """
 import ctypes
+import os
 
 import torch
 
@@ -81,6 +82,8 @@ class ImageFitStep:
         self.A = torch.empty((1, self.C, self.F), **f32)
         self.feats = torch.empty((self.n, self.L * self.F), **f32)
         self.gfeat = torch.empty_like(self.feats)
+        self.gfeat_max = torch.zeros((self.L * self.F,), **f32)   # max |feature gradient| per column (MLP kernel)
+        self.use_bound = self.IN == 16 and os.environ.get("SHACIRA_MLP_IMPL", "tc") == "tc"   # the tensor-core kernel
         n_par = self.H * self.IN + self.H + self.H * self.H + self.H + self.OUT * self.H + self.OUT
         self.mlp_out = torch.zeros(2 + n_par, **f32)            # double SSE | packed MLP gradients
         self.g_grid = torch.empty((self.T, self.C), **f32)
@@ -191,16 +194,20 @@ class ImageFitStep:
                                              P(self.ent_scratch), self.ent_scratch.numel(), _lib._stream()))
             chk(lib.shacira_latent_forward_planned(self.plan.handle, P(lat), self.fi, self.rs, self.L, self.bw, self.C,
                                                    self.F, 1, P(self.A), P(shift), 0, P(self.feats), st))
-            chk(lib.shacira_mlp_mse_step(P(self.feats), P(self.target), self.n, self.IN, self.H, self.OUT,
-                                         P(lin[0].weight.data), P(lin[0].bias.data), P(lin[1].weight.data),
-                                         P(lin[1].bias.data), P(lin[2].weight.data), P(lin[2].bias.data),
-                                         P(self.gfeat), None, P(self.mlp_out), st))
+            # the MLP kernel reduces max |feature gradient| per column on the way; the tiled backward takes its
+            # fixed-point scales from that bound and skips its own pass over the gradient rows
+            bound = P(self.gfeat_max) if self.use_bound else None
+            chk(lib.shacira_mlp_mse_step_bounded(P(self.feats), P(self.target), self.n, self.IN, self.H, self.OUT,
+                                                 P(lin[0].weight.data), P(lin[0].bias.data), P(lin[1].weight.data),
+                                                 P(lin[1].bias.data), P(lin[2].weight.data), P(lin[2].bias.data),
+                                                 P(self.gfeat), None, P(self.mlp_out), bound, st))
             if not self.has_shift:
                 self.g_dec[self.L * self.C * self.F:].zero_()   # no segment consumes (and clears) the shift rows
             CF = self.C * self.F
-            chk(lib.shacira_latent_backward_planned(self.plan.handle, P(self.gfeat), P(lat), self.fi, self.rs, self.L,
-                                                    self.bw, self.C, self.F, 1, P(self.A), 0, self.T, 1, P(self.g_grid),
-                                                    P(self.g_dec), P(self.g_dec[self.L * CF:]), st))
+            chk(lib.shacira_latent_backward_planned_bounded(self.plan.handle, P(self.gfeat), P(lat), self.fi, self.rs,
+                                                            self.L, self.bw, self.C, self.F, 1, P(self.A), 0, self.T, 1,
+                                                            P(self.g_grid), P(self.g_dec), P(self.g_dec[self.L * CF:]),
+                                                            bound, st))
             cur.wait_stream(self.side)
             chk(lib.shacira_adam_step_sum(P(lat), P(self.g_grid), P(self.g_ent), P(self.lam), 1.0 / self.T,
                                           P(self.m_table), P(self.v_table), self.T * self.C, self.grid_lr,

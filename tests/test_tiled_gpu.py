@@ -249,3 +249,39 @@ def test_plan_cache_recycles_allocations_for_changing_coordinates(lib, monkeypat
     grid_ops.latent_hashgrid(pending[0][0], lat, A, S, c["first"], c["res"], 12, True).sum().backward()
     assert rel_err(g_first.cpu().numpy(), lat.grad.cpu().numpy()) <= 1e-6
     grid_ops.clear_plans()
+
+
+@pytest.mark.parametrize("C,F,dec", [(1, 1, True), (1, 1, False), (2, 4, True), (4, 2, False)])
+def test_bounded_backward_matches_self_scaled(lib, C, F, dec):
+    """shacira_latent_backward_planned_bounded: with the caller's per-column bound of |grad_output| the kernel skips
+    its own max pass; the result agrees with the oracle to the same tolerance, also when the bound is loose."""
+    c = _case(2, 16, 16, 16, 512, 100000, C, F, seed=91 + C + F, kind="uniform")
+    coords, lat, A, g = _dev(c["coords"]), _dev(c["lat"]), _dev(c["A"]), _dev(c["g"])
+    # uneven magnitudes across levels and space, like real upstream gradients
+    g = g * torch.logspace(-3, 2, g.shape[1], device="cuda") * (0.1 + coords[:, :1].abs())
+    c["g"] = g.cpu().numpy()
+    plan = lib.Plan(coords)
+    _, want_gl, want_gA, want_gS = _oracle_fwd_bwd(c)
+    for slack in (1.0, 7.3):
+        bound = g.abs().amax(dim=0) * slack
+        gl, gA, gS = lib.latent_backward_planned(plan, g, lat if dec else None, c["first"], c["res"], 16, A, C, F, c["T"],
+                                                 True, dec, level_max=bound)
+        bounds = list(c["first"]) + [c["T"]]
+        for l in range(16):   # per level: the coarse levels must not hide behind the largest gradient
+            a, b = bounds[l], bounds[l + 1]
+            assert rel_err(gl[a:b].cpu().numpy(), want_gl[a:b]) <= BWD_TOL, (l, slack)
+        if dec:
+            _check_decoder_grads(c, gA, gS, want_gA, want_gS)
+    plan.close()
+
+
+def test_mlp_step_reports_feature_gradient_bound(lib):
+    torch.manual_seed(5)
+    n = 50000
+    mlp = torch.nn.Sequential(torch.nn.Linear(16, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(),
+                              torch.nn.Linear(16, 3)).cuda()
+    x, gt = torch.randn(n, 16, device="cuda"), torch.rand(n, 3, device="cuda")
+    bound = torch.full((16,), -1.0, device="cuda")
+    ws = [mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias, mlp[4].weight, mlp[4].bias]
+    _, gx, _, _ = lib.mlp_mse_step(x, gt, *[w.detach() for w in ws], absmax_out=bound)
+    assert torch.equal(bound, gx.abs().amax(dim=0))
