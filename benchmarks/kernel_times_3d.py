@@ -77,6 +77,23 @@ def main():
                                                                       BW, F, T, 1, P(gl), st))
             out[name] = {"fwd_us": timed(fwd), "bwd_us": timed(bwd)}
         del sets
+    # packed exponential integration: 4096 rays x 128 samples, RGB
+    R, per = 4096, S // 4096
+    feats3 = torch.rand((S, 3), device=dev)
+    tau = torch.rand((S,), device=dev) ** 3
+    starts = (torch.arange(R + 1, device=dev, dtype=torch.int32) * per).contiguous()
+    w = torch.empty((S,), device=dev)
+    ray = torch.empty((R, 3), device=dev)
+    alpha = torch.empty((R,), device=dev)
+    g_ray = torch.randn((R, 3), device=dev)
+    g_w = torch.randn((S,), device=dev)
+    g_f = torch.empty((S, 3), device=dev)
+    g_t = torch.empty((S,), device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ifwd = lambda i: _lib._check(lib.shacira_integrate_forward(P(feats3), P(tau), P(starts), R, 3, P(w), P(ray), P(alpha), st))
+    ibwd = lambda i: _lib._check(lib.shacira_integrate_backward(P(feats3), P(tau), P(w), P(starts), R, 3, P(g_ray), P(g_w),
+                                                                P(g_f), P(g_t), st))
+    out["integrate_rgb"] = {"rays": R, "samples": S, "fwd_us": timed(ifwd), "bwd_us": timed(ibwd)}
     print(json.dumps(out), flush=True)
 
 

@@ -258,6 +258,23 @@ int shacira_multi_adam_step(const shacira_adam_seg_t* segs, int32_t num_segs, fl
                             float* step, float* extra_step, const float* scale, const float* div, float* A_out,
                             int32_t latent_dim, int32_t feature_dim, shacira_stream_t stream);
 
+/* ---- packed exponential integration along rays ----------------- */
+/* What the reference's tracer calls right after the grid and its decoders
+ * (wisp/tracers/packed_rf_tracer.py:136-153: spc_render.exponential_integration(color, tau, boundary, exclusive=True)
+ * and spc_render.sum_reduce(transmittance, boundary); kaolin 0.13.0, absent -- published algorithm restated, parity
+ * with kaolin unpinned). Samples are packed ray after ray: ray r owns [ray_start[r], ray_start[r+1]) (device int32,
+ * num_rays + 1 entries; the shim derives them from the reference's boolean `boundary`).
+ *   weights[i]   = exp(-sum_{j<i in ray} tau[j]) * (1 - exp(-tau[i]))
+ *   ray_feats[r] = sum_i weights[i] * feats[i, :]      ray_alpha[r] = sum_i weights[i]   (may be NULL)
+ * backward: grad_feats (may be NULL) and grad_tau from grad_ray_feats and, optionally, a gradient reaching the
+ * per-sample weights directly (grad_weights: alpha and depth terms). num_feats in {1, 3, 4, 8}. */
+int shacira_integrate_forward(const float* feats, const float* tau, const int32_t* ray_start, int32_t num_rays,
+                              int32_t num_feats, float* weights, float* ray_feats, float* ray_alpha,
+                              shacira_stream_t stream);
+int shacira_integrate_backward(const float* feats, const float* tau, const float* weights, const int32_t* ray_start,
+                               int32_t num_rays, int32_t num_feats, const float* grad_ray_feats,
+                               const float* grad_weights, float* grad_feats, float* grad_tau, shacira_stream_t stream);
+
 /* ---- latent bitstream (host side) ---------------------------------------------------- */
 /* Static arithmetic coder over dense symbol ranks 0..num_symbols-1 with 16-bit cumulative
  * frequencies cdf[num_symbols+1] (cdf[0] = 0, strictly increasing, cdf[num_symbols] = 65536).

@@ -8,6 +8,7 @@
 #include "entropy_kernels.cuh"
 #include "hashgrid_kernels.cuh"
 #include "mlp_kernels.cuh"
+#include "render_kernels.cuh"
 
 using namespace shacira;
 
@@ -657,6 +658,47 @@ int shacira_mlp_mse_step(const float* features, const float* target, int64_t n, 
                          shacira_stream_t stream) {
     return shacira_mlp_mse_step_bounded(features, target, n, in_dim, hidden_dim, out_dim, W1, b1, W2, b2, W3, b3,
                                         grad_features, pred, out, nullptr, stream);
+}
+
+// ---- packed exponential integration ---------------------------------------------------
+#define DISPATCH_NF(NF_, CALL)                                                                     \
+    switch (NF_) {                                                                                 \
+        case 1: { constexpr int kNF = 1; CALL; break; }                                            \
+        case 3: { constexpr int kNF = 3; CALL; break; }                                            \
+        case 4: { constexpr int kNF = 4; CALL; break; }                                            \
+        case 8: { constexpr int kNF = 8; CALL; break; }                                            \
+        default: return fail(SHACIRA_ERR_UNSUPPORTED, "num_feats %d not in {1,3,4,8}", (int)NF_);  \
+    }
+
+int shacira_integrate_forward(const float* feats, const float* tau, const int32_t* ray_start, int32_t num_rays,
+                              int32_t num_feats, float* weights, float* ray_feats, float* ray_alpha,
+                              shacira_stream_t stream) {
+    if (num_rays < 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "num_rays is negative");
+    if (num_rays == 0) return SHACIRA_OK;
+    if (!feats || !tau || !ray_start || !weights || !ray_feats)
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "integrate_forward: NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = (num_rays + kRenderWarps - 1) / kRenderWarps;
+    DISPATCH_NF(num_feats, (integrate_fwd_kernel<kNF><<<blocks, kRenderWarps * 32, 0, s>>>(
+                               feats, tau, ray_start, num_rays, weights, ray_feats, ray_alpha)))
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
+int shacira_integrate_backward(const float* feats, const float* tau, const float* weights, const int32_t* ray_start,
+                               int32_t num_rays, int32_t num_feats, const float* grad_ray_feats,
+                               const float* grad_weights, float* grad_feats, float* grad_tau, shacira_stream_t stream) {
+    if (num_rays < 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "num_rays is negative");
+    if (num_rays == 0) return SHACIRA_OK;
+    if (!feats || !tau || !weights || !ray_start || !grad_ray_feats || !grad_tau)
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "integrate_backward: NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = (num_rays + kRenderWarps - 1) / kRenderWarps;
+    DISPATCH_NF(num_feats, (integrate_bwd_kernel<kNF><<<blocks, kRenderWarps * 32, 0, s>>>(
+                               feats, tau, weights, ray_start, num_rays, grad_ray_feats, grad_weights, grad_feats,
+                               grad_tau)))
+    LAUNCHED();
+    return SHACIRA_OK;
 }
 
 // ---- latent bitstream (host) ---------------------------------------------------------------

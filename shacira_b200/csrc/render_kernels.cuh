@@ -1,0 +1,122 @@
+// render_kernels.cuh -- packed exponential integration along rays (the step AFTER the 3D grid
+// and its decoders in the NeRF path).
+//
+// Reference call site: wisp/tracers/packed_rf_tracer.py:136-153
+//     tau = density * deltas
+//     ray_colors, transmittance = spc_render.exponential_integration(color, tau, boundary, exclusive=True)
+//     alpha = spc_render.sum_reduce(transmittance, boundary)            (+ depth = sum_reduce(depths * transmittance))
+// `spc_render` is kaolin.render.spc (kaolin==0.13.0, README.md:35): an absent third-party dependency. Its published
+// algorithm, restated: samples are PACKED ray after ray (`boundary[i]` marks the first sample of a ray);
+//     T_i = exp(-sum_{j<i, same ray} tau_j)          (exclusive cumsum)
+//     w_i = T_i * (1 - exp(-tau_i))                  ("transmittance" returned per sample)
+//     ray_feats_r = sum_{i in r} w_i * feats_i       (sum_reduce)
+// Parity with kaolin itself is UNPINNED (package absent); the oracle (oracle/render_oracle.py) restates the same
+// formulas in float64 and the gradients are checked against autograd of that restatement.
+//
+// One warp per ray: 32 samples per step, prefix sums by warp shuffles with a running carry. Forward: one pass.
+// Backward: d w_k / d tau_i = -w_k for k > i and T_{i+1} for k = i, so
+//     grad_tau_i = G_i * T_{i+1} - sum_{k>i} G_k w_k,   G_i = <grad_ray_feats_r, feats_i> + grad_w_i
+// i.e. one forward sweep (T_{i+1}, parked in the output) and one reverse sweep (suffix sums).
+#pragma once
+#include "common.cuh"
+
+namespace shacira {
+
+constexpr int kRenderWarps = 8;
+
+__device__ __forceinline__ float warp_incl_scan(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+
+// ray_start[r] .. ray_start[r+1]: samples of ray r. feats [S, NF]; tau [S]; out: weights [S], ray_feats [R, NF],
+// ray_alpha [R] (= sum of the weights; may be NULL).
+template <int NF>
+__global__ void __launch_bounds__(kRenderWarps * 32)
+integrate_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ tau, const int32_t* __restrict__ ray_start,
+                     int32_t num_rays, float* __restrict__ weights, float* __restrict__ ray_feats,
+                     float* __restrict__ ray_alpha) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kRenderWarps + (threadIdx.x >> 5);
+    if (r >= num_rays) return;
+    const int s0 = ray_start[r], s1 = ray_start[r + 1];
+    float carry = 0.0f, acc[NF], asum = 0.0f;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc[f] = 0.0f;
+    for (int base = s0; base < s1; base += 32) {
+        const int i = base + lane;
+        const float t = (i < s1) ? __ldg(tau + i) : 0.0f;
+        const float incl = warp_incl_scan(t, lane);
+        const float T = expf(-(carry + incl - t));
+        const float w = T * (1.0f - expf(-t));
+        if (i < s1) {
+            weights[i] = w;
+            asum += w;
+#pragma unroll
+            for (int f = 0; f < NF; ++f) acc[f] = fmaf(w, __ldg(feats + (int64_t)i * NF + f), acc[f]);
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const float v = warp_sum(acc[f]);
+        if (lane == 0) ray_feats[(int64_t)r * NF + f] = v;
+    }
+    const float a = warp_sum(asum);
+    if (lane == 0 && ray_alpha) ray_alpha[r] = a;
+}
+
+// grad_ray_feats [R, NF]; grad_weights [S] or NULL (gradient reaching the per-sample weights directly: alpha, depth);
+// weights [S] from the forward. out: grad_feats [S, NF] (may be NULL), grad_tau [S].
+template <int NF>
+__global__ void __launch_bounds__(kRenderWarps * 32)
+integrate_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ tau, const float* __restrict__ weights,
+                     const int32_t* __restrict__ ray_start, int32_t num_rays, const float* __restrict__ grad_ray_feats,
+                     const float* __restrict__ grad_weights, float* __restrict__ grad_feats,
+                     float* __restrict__ grad_tau) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kRenderWarps + (threadIdx.x >> 5);
+    if (r >= num_rays) return;
+    const int s0 = ray_start[r], s1 = ray_start[r + 1];
+    float gr[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) gr[f] = __ldg(grad_ray_feats + (int64_t)r * NF + f);
+    // forward sweep: T_{i+1} = exp(-inclusive cumsum), parked in grad_tau
+    float carry = 0.0f;
+    for (int base = s0; base < s1; base += 32) {
+        const int i = base + lane;
+        const float t = (i < s1) ? __ldg(tau + i) : 0.0f;
+        const float incl = warp_incl_scan(t, lane);
+        if (i < s1) grad_tau[i] = expf(-(carry + incl));
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    // reverse sweep: suffix sums of G_k w_k
+    float tail = 0.0f;  // sum over the chunks behind this one
+    const int nchunks = (s1 - s0 + 31) >> 5;
+    for (int c = nchunks - 1; c >= 0; --c) {
+        const int i = s0 + 32 * c + lane;
+        float G = 0.0f, w = 0.0f;
+        if (i < s1) {
+            w = weights[i];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                G = fmaf(gr[f], __ldg(feats + (int64_t)i * NF + f), G);
+                if (grad_feats) grad_feats[(int64_t)i * NF + f] = w * gr[f];
+            }
+            if (grad_weights) G += __ldg(grad_weights + i);
+        }
+        const float gw = G * w;
+        const float incl = warp_incl_scan(gw, lane);
+        const float total = __shfl_sync(0xffffffffu, incl, 31);
+        const float after = tail + (total - incl);  // sum_{k > i} G_k w_k
+        if (i < s1) grad_tau[i] = G * grad_tau[i] - after;
+        tail += total;
+    }
+}
+
+}  // namespace shacira

@@ -1,0 +1,80 @@
+"""Packed ray integration: the `kaolin.render.spc` calls of the reference's tracer, on the B200 kernels
+(SURVEY section 8 row f-3).
+
+`wisp/tracers/packed_rf_tracer.py:136-153` does, right after the 3D grid and its decoders:
+
+    tau = density * deltas
+    ray_colors, transmittance = spc_render.exponential_integration(color, tau, boundary, exclusive=True)
+    alpha = spc_render.sum_reduce(transmittance, boundary)
+    ray_depth = spc_render.sum_reduce(depths * transmittance, boundary)
+
+Same names and argument meaning here (`boundary`: bool [S], True at the first sample of every packed ray). kaolin
+(0.13.0) is an absent dependency: its published algorithm is restated, parity with the package itself is unpinned
+(oracle/render_oracle.py is the float64 restatement the tests check against). No CPU fallback.
+"""
+import torch
+
+from . import _lib
+
+
+def ray_starts(boundary):
+    """int32 [R + 1]: first sample of every ray, then the sample count (kaolin's pack boundaries as offsets)."""
+    if boundary.dtype != torch.bool:
+        boundary = boundary != 0
+    S = boundary.shape[0]
+    starts = torch.nonzero(boundary, as_tuple=False).squeeze(1).to(torch.int32)
+    return torch.cat((starts, torch.tensor([S], dtype=torch.int32, device=boundary.device)))
+
+
+class _ExponentialIntegration(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, tau, starts, tau_2d):
+        lib = _lib.load()
+        feats, tau = _lib._f32c(feats, "feats"), _lib._f32c(tau.reshape(-1), "tau")
+        S, NF = feats.shape
+        R = starts.numel() - 1
+        weights = torch.empty((S,), dtype=torch.float32, device=feats.device)
+        ray_feats = torch.empty((R, NF), dtype=torch.float32, device=feats.device)
+        with torch.cuda.device(feats.device):
+            _lib._check(lib.shacira_integrate_forward(_lib._ptr(feats), _lib._ptr(tau), _lib._ptr(starts), R, NF,
+                                                      _lib._ptr(weights), _lib._ptr(ray_feats), None, _lib._stream()))
+        ctx.save_for_backward(feats, tau, weights, starts)
+        ctx.tau_2d = tau_2d
+        return ray_feats, weights.unsqueeze(1)
+
+    @staticmethod
+    def backward(ctx, g_ray, g_w):
+        feats, tau, weights, starts = ctx.saved_tensors
+        lib = _lib.load()
+        S, NF = feats.shape
+        R = starts.numel() - 1
+        g_ray = _lib._f32c(g_ray, "grad_ray_feats")
+        g_w = _lib._f32c(g_w.reshape(-1), "grad_weights") if g_w is not None else None
+        g_feats = torch.empty_like(feats) if ctx.needs_input_grad[0] else None
+        g_tau = torch.empty_like(tau)
+        with torch.cuda.device(feats.device):
+            _lib._check(lib.shacira_integrate_backward(_lib._ptr(feats), _lib._ptr(tau), _lib._ptr(weights),
+                                                       _lib._ptr(starts), R, NF, _lib._ptr(g_ray), _lib._ptr(g_w),
+                                                       _lib._ptr(g_feats), _lib._ptr(g_tau), _lib._stream()))
+        return g_feats, (g_tau.unsqueeze(1) if ctx.tau_2d else g_tau), None, None
+
+
+def exponential_integration(feats, tau, boundary, exclusive=True, starts=None):
+    """(ray_feats [R, NF], transmittance weights [S, 1]) -- spc_render.exponential_integration. Pass `starts`
+    (ray_starts(boundary)) to reuse the offsets across calls; exclusive=False is not used by the reference."""
+    if not exclusive:
+        raise _lib.ShaciraError(_lib.ERR_UNSUPPORTED, "exponential_integration: exclusive=False is not implemented")
+    if starts is None:
+        starts = ray_starts(boundary)
+    return _ExponentialIntegration.apply(feats, tau, starts, tau.dim() == 2)
+
+
+def sum_reduce(feats, boundary, starts=None):
+    """Per-ray sums of packed per-sample values [S, F] -> [R, F] (spc_render.sum_reduce)."""
+    if starts is None:
+        starts = ray_starts(boundary)
+    seg = torch.zeros(feats.shape[0], dtype=torch.int64, device=feats.device)
+    seg[starts[1:-1].long()] = 1
+    seg = torch.cumsum(seg, 0)
+    out = torch.zeros((starts.numel() - 1, feats.shape[1]), dtype=feats.dtype, device=feats.device)
+    return out.index_add_(0, seg, feats)

@@ -183,3 +183,24 @@ def _regen(dim, L, bw, res, n, F, seed, name):
     table = rng.standard_normal((T, F)).astype(np.float32)
     gout = rng.standard_normal((n, L * F)).astype(np.float32)
     return table, gout
+
+
+def test_render_oracle_closed_forms():
+    """oracle/render_oracle.py (restated kaolin exponential integration, parity with kaolin unpinned): closed forms.
+    A ray of equal samples tau: w_i = e^{-i tau}(1 - e^{-tau}), alpha = 1 - e^{-n tau}; rays are independent."""
+    import numpy as np
+    from oracle import render_oracle as ro
+    n, tau = 9, 0.37
+    feats = np.ones((2 * n, 2))
+    feats[:, 1] = np.arange(2 * n)
+    taus = np.full(2 * n, tau)
+    boundary = np.zeros(2 * n, dtype=bool)
+    boundary[[0, n]] = True
+    ray, w = ro.exponential_integration(feats, taus, boundary)
+    want_w = np.exp(-tau * np.arange(n)) * (1 - np.exp(-tau))
+    assert np.allclose(w[:n], want_w, rtol=1e-12) and np.allclose(w[n:], want_w, rtol=1e-12)
+    assert np.allclose(ray[:, 0], 1 - np.exp(-n * tau), rtol=1e-12)
+    assert np.allclose(ray[1, 1] - ray[0, 1], n * (1 - np.exp(-n * tau)), rtol=1e-12)
+    import torch
+    r2, w2 = ro.exponential_integration_torch(torch.from_numpy(feats), torch.from_numpy(taus), torch.from_numpy(boundary))
+    assert np.allclose(r2.numpy(), ray) and np.allclose(w2.numpy(), w)

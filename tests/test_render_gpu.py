@@ -1,0 +1,64 @@
+"""Packed exponential integration against the float64 restatement of the published kaolin algorithm
+(oracle/render_oracle.py; kaolin itself is absent: parity with the package is unpinned)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _packed_case(num_rays, max_len, nf, seed, min_len=1):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(min_len, max_len + 1, size=num_rays)
+    S = int(lens.sum())
+    boundary = np.zeros(S, dtype=bool)
+    boundary[np.concatenate(([0], np.cumsum(lens)[:-1]))] = True
+    feats = rng.random((S, nf)).astype(np.float32)
+    tau = (rng.random(S) ** 3 * 4.0).astype(np.float32)     # mostly thin samples, a few opaque ones
+    return feats, tau, boundary
+
+
+@pytest.mark.parametrize("num_rays,max_len,nf", [(1, 1, 3), (7, 31, 3), (64, 128, 3), (300, 200, 4), (50, 33, 1),
+                                                 (4096, 128, 3), (20, 1000, 8)])
+def test_integration_forward_and_backward(lib, num_rays, max_len, nf):
+    from oracle import render_oracle as ro
+    from shacira_b200 import render
+    feats, tau, boundary = _packed_case(num_rays, max_len, nf, seed=num_rays + nf)
+    f = torch.from_numpy(feats).cuda().requires_grad_(True)
+    t = torch.from_numpy(tau).cuda().unsqueeze(1).requires_grad_(True)
+    b = torch.from_numpy(boundary).cuda()
+    ray, w = render.exponential_integration(f, t, b, exclusive=True)
+    alpha = render.sum_reduce(w, b)
+    want_ray, want_w = ro.exponential_integration(feats, tau, boundary)
+    assert ray.shape == (num_rays, nf) and w.shape == (tau.shape[0], 1)
+    assert rel_err(ray.detach().cpu().numpy(), want_ray) <= 1e-5
+    assert rel_err(w.detach().cpu().numpy().reshape(-1), want_w) <= 1e-5
+    starts = list(np.nonzero(boundary)[0]) + [tau.shape[0]]
+    want_alpha = np.array([want_w[starts[r]:starts[r + 1]].sum() for r in range(num_rays)])
+    assert rel_err(alpha.detach().cpu().numpy().reshape(-1), want_alpha) <= 1e-5
+    # gradients: a loss that uses the ray colours, alpha and a depth-like weighted sum, as the tracer does
+    torch.manual_seed(0)
+    g_ray = torch.randn(num_rays, nf, device="cuda")
+    depth = torch.rand(tau.shape[0], 1, device="cuda")
+    loss = (ray * g_ray).sum() + (alpha ** 2).sum() + render.sum_reduce(depth * w, b).sum()
+    loss.backward()
+    f64 = torch.from_numpy(feats).double().requires_grad_(True)
+    t64 = torch.from_numpy(tau).double().requires_grad_(True)
+    ray64, w64 = ro.exponential_integration_torch(f64, t64, torch.from_numpy(boundary))
+    seg = torch.from_numpy(np.repeat(np.arange(num_rays), np.diff(starts)))
+    alpha64 = torch.zeros(num_rays, dtype=torch.float64).index_add_(0, seg, w64)
+    loss64 = (ray64 * g_ray.cpu().double()).sum() + (alpha64 ** 2).sum() + (depth.cpu().double().reshape(-1) * w64).sum()
+    loss64.backward()
+    assert rel_err(f.grad.cpu().numpy(), f64.grad.numpy()) <= 1e-4
+    assert rel_err(t.grad.cpu().numpy().reshape(-1), t64.grad.numpy()) <= 1e-4
+
+
+def test_integration_rejects_cpu_tensors_and_odd_widths(lib):
+    from shacira_b200 import render
+    b = torch.tensor([True, False, False])
+    with pytest.raises(lib.ShaciraError):
+        render.exponential_integration(torch.zeros(3, 3), torch.zeros(3, 1), b)
+    with pytest.raises(lib.ShaciraError):
+        render.exponential_integration(torch.zeros(3, 5).cuda(), torch.zeros(3, 1).cuda(), b.cuda())
