@@ -439,15 +439,21 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
             import fit_image
             fr = fit_image.fit(rank, "native", 400, dev, use_graph=True, noise_cpu=False)
-            tf = torch.tensor([fr["ms_per_step"]], device=dev, dtype=torch.float64)
+            # throughput form (BASELINE cfg3: 24 independent images over the GPUs): three fits in flight per GPU,
+            # one stream + one CUDA graph each -- independent INRs overlap each other's latency
+            group = fit_image.fit_native_many([3 * rank, 3 * rank + 1, 3 * rank + 2], 400, dev, True, False)
+            tf = torch.tensor([fr["ms_per_step"], group[0]["ms_per_step"]], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-            kodak_fit = {"ms_per_step": float(tf.item()), "steps_measured": 400, "steps_per_fit": 60000,
-                         "fits_per_hour": world * 3600.0 / (60000 * float(tf.item()) * 1e-3),
+            single_ms, group_ms = float(tf[0].item()), float(tf[1].item())
+            kodak_fit = {"ms_per_step": single_ms, "steps_measured": 400, "steps_per_fit": 60000,
+                         "fits_per_hour_one_fit_per_gpu": world * 3600.0 / (60000 * single_ms * 1e-3),
+                         "concurrent_fits_per_gpu": 3, "ms_per_step_per_fit_concurrent": group_ms,
+                         "fits_per_hour": world * 3600.0 / (60000 * group_ms * 1e-3),
                          "psnr_after_400_steps": fr["psnr"], "bpp_after_400_steps": fr["bpp"],
-                         "step": "shacira_b200.image_fit.ImageFitStep: grid fwd/bwd + fused decoder MLP/MSE + "
+                         "step": "shacira_b200.image_fit.ImageFitStep: grid fwd/bwd + tensor-core decoder MLP/MSE + "
                                  "bit-rate loss + Adam of every parameter group as 11 native launches in one CUDA "
-                                 "graph; one independent image per GPU"}
+                                 "graph; independent images, no collective; fits_per_hour = 3 images in flight per GPU"}
         except Exception as e:  # the headline metric must not depend on the extra measurement
             kodak_fit = {"unavailable": repr(e)[:200]}
 

@@ -111,8 +111,7 @@ def clamped_psnr(pred, gt):
     return 20 * np.log10(255.0) - 10 * np.log10(max(mse, 1e-12))
 
 
-def fit_native(seed, steps, dev, use_graph, noise_cpu):
-    """The same fit through shacira_b200.image_fit.ImageFitStep: the whole training step as 11 native launches."""
+def _native_setup(seed, dev):
     from shacira_b200.grids import LatentGrid
     from shacira_b200.image_fit import ImageFitStep
     torch.manual_seed(seed)
@@ -126,37 +125,10 @@ def fit_native(seed, steps, dev, use_graph, noise_cpu):
     coords, gt = make_data(seed, dev)
     fs = ImageFitStep(grid, mlp, coords, gt, lr=1e-3, grid_lr=2e-2, ldec_lr=1e-2, prob_lr=1e-4, weight_decay=0.0,
                       weight_decay_decoder=1e-2)
-    noise_gen = torch.Generator().manual_seed(10_000 + seed)
+    return grid, mlp, coords, gt, fs
 
-    def host_side(it):
-        fs.set_lambda(1e-4 + 0.5 * (1e-3 - 1e-4) * (1 + math.cos(math.pi * it / steps)))
-        fs.draw_noise(noise_gen if noise_cpu else None)
-        if it + 1 in (1, 2, 5, 10):
-            fs.update_div()
 
-    graph, start_it = None, 0
-    if use_graph:
-        side = torch.cuda.Stream()
-        with torch.cuda.stream(side):
-            for it in range(3):
-                host_side(it)
-                fs.step()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            fs.step()
-        start_it = 3
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for it in range(start_it, steps):
-        host_side(it)
-        if graph is not None:
-            graph.replay()
-        else:
-            fs.step()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+def _native_metrics(seed, grid, mlp, coords, gt, fs, ms_per_step):
     rgb_loss = float(fs.rgb_loss())
     fs.close()
     with torch.no_grad():
@@ -168,8 +140,57 @@ def fit_native(seed, steps, dev, use_graph, noise_cpu):
         latent_bits = float(torch.sum(torch.clamp(-torch.log(p + 1e-10) / np.log(2.0), 0, 1000) * counts))
         n_other = sum(p.numel() for p in mlp.parameters()) + sum(p.numel() for p in grid.latent_dec.parameters())
         bpp = (latent_bits + 32 * n_other) / (H * W)
-    return dict(seed=seed, psnr=psnr, bpp=bpp, latent_bits=latent_bits, ms_per_step=dt / (steps - start_it) * 1e3,
-                rgb_loss=rgb_loss)
+    return dict(seed=seed, psnr=psnr, bpp=bpp, latent_bits=latent_bits, ms_per_step=ms_per_step, rgb_loss=rgb_loss)
+
+
+def fit_native_many(seeds, steps, dev, use_graph, noise_cpu):
+    """Fit len(seeds) independent images AT ONCE on one GPU through shacira_b200.image_fit.ImageFitStep (the whole
+    training step as 11 native launches), one stream and one CUDA graph per image. Independent INRs share nothing, and
+    every kernel of the step alone leaves most of the SMs' issue slots idle (ncu: 35-50 % busy), so two or three fits in
+    flight overlap each other's latency. `ms_per_step` is wall time per step of the whole group divided by the group
+    size, i.e. the throughput figure that fits/hour is made of."""
+    fits = [_native_setup(s, dev) for s in seeds]
+    gens = [torch.Generator().manual_seed(10_000 + s) for s in seeds]
+    streams = [torch.cuda.Stream(device=dev) for _ in seeds]
+
+    def host_side(k, it):
+        fs = fits[k][4]
+        fs.set_lambda(1e-4 + 0.5 * (1e-3 - 1e-4) * (1 + math.cos(math.pi * it / steps)))
+        fs.draw_noise(gens[k] if noise_cpu else None)
+        if it + 1 in (1, 2, 5, 10):
+            fs.update_div()
+
+    graphs, start_it = [None] * len(seeds), 0
+    if use_graph:
+        for k in range(len(seeds)):
+            with torch.cuda.stream(streams[k]):
+                for it in range(3):
+                    host_side(k, it)
+                    fits[k][4].step()
+        torch.cuda.synchronize()
+        for k in range(len(seeds)):
+            graphs[k] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graphs[k], stream=streams[k]):
+                fits[k][4].step()
+        start_it = 3
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for it in range(start_it, steps):
+        for k in range(len(seeds)):
+            with torch.cuda.stream(streams[k]):
+                host_side(k, it)
+                if graphs[k] is not None:
+                    graphs[k].replay()
+                else:
+                    fits[k][4].step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    ms = dt / (steps - start_it) * 1e3 / len(seeds)
+    return [_native_metrics(s, *f, ms) for s, f in zip(seeds, fits)]
+
+
+def fit_native(seed, steps, dev, use_graph, noise_cpu):
+    return fit_native_many([seed], steps, dev, use_graph, noise_cpu)[0]
 
 
 def fit(seed, impl, steps, dev, use_graph, noise_cpu, fused_mlp=False):
@@ -290,6 +311,7 @@ def main():
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--noise-cpu", action="store_true", help="draw the entropy noise with the CPU generator (parity runs)")
     ap.add_argument("--fused-mlp", action="store_true", help="fused decoder MLP + MSE kernel (SURVEY 8 f-1) and fused Adam")
+    ap.add_argument("--concurrent", type=int, default=1, help="--impl native: independent images fitted at once per GPU")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -302,7 +324,12 @@ def main():
     mine = dp.shard_units(args.images, rank, world)      # independent images: round-robin, no collective
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    results = [fit(s, args.impl, args.steps, dev, args.graph, args.noise_cpu, args.fused_mlp) for s in mine]
+    if args.impl == "native" and args.concurrent > 1:
+        results = []
+        for i in range(0, len(mine), args.concurrent):
+            results += fit_native_many(mine[i:i + args.concurrent], args.steps, dev, args.graph, args.noise_cpu)
+    else:
+        results = [fit(s, args.impl, args.steps, dev, args.graph, args.noise_cpu, args.fused_mlp) for s in mine]
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     allres = dp.gather_results(dict(rank=rank, wall=wall, fits=results))
@@ -311,7 +338,7 @@ def main():
         fits = [f for r in allres for f in r["fits"]]
         ms = float(np.mean([f["ms_per_step"] for f in fits]))
         print(json.dumps({"workload": "Kodak-shape image INR fit (BASELINE cfg2/cfg3)", "impl": args.impl,
-                          "n_gpus": world, "images": args.images, "steps_per_fit": args.steps, "cuda_graph": args.graph, "fused_mlp": args.fused_mlp,
+                          "n_gpus": world, "images": args.images, "steps_per_fit": args.steps, "concurrent_per_gpu": args.concurrent, "cuda_graph": args.graph, "fused_mlp": args.fused_mlp,
                           "ms_per_step": ms, "psnr": [round(f["psnr"], 3) for f in fits], "bpp": [round(f["bpp"], 4) for f in fits],
                           "wall_s": wall,
                           "fits_per_hour_at_60000_steps": world * 3600.0 / (60000 * ms * 1e-3) if fits else None}), flush=True)

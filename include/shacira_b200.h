@@ -233,8 +233,9 @@ int shacira_adam_step_sum(float* param, const float* grad, const float* grad2, c
  * which covers the chain rules of this path without extra kernels: latent-decoder scale = A * div (sum of the
  * per-level dA rows, divided by div), shift (sum of per-level rows), density parameters (lambda / rows).
  * After the update, if A_out != NULL: A_out[c * F + f] = scale[c * F + f] / div[c] for the next step's kernels
- * (`scale` must then be the `param` of one of the segments). One launch, one CTA per segment; one call may be in
- * flight per device at a time.
+ * (`scale` must then be the `param` of one of the segments). One launch, one CTA per segment; `ticket` is a device
+ * uint32 the caller zero-initialises once per optimizer (the kernel leaves it at 0), so that independent optimizers
+ * may run concurrently on different streams.
  * `step` (device float) is advanced by the call, and so is `extra_step` when not NULL. At most
  * SHACIRA_MAX_ADAM_SEGS segments. */
 #define SHACIRA_MAX_ADAM_SEGS 32
@@ -256,7 +257,7 @@ typedef struct {
 } shacira_adam_seg_t;
 int shacira_multi_adam_step(const shacira_adam_seg_t* segs, int32_t num_segs, float beta1, float beta2, float eps,
                             float* step, float* extra_step, const float* scale, const float* div, float* A_out,
-                            int32_t latent_dim, int32_t feature_dim, shacira_stream_t stream);
+                            int32_t latent_dim, int32_t feature_dim, uint32_t* ticket, shacira_stream_t stream);
 
 /* ---- packed exponential integration along rays ----------------- */
 /* What the reference's tracer calls right after the grid and its decoders

@@ -549,8 +549,8 @@ int shacira_adam_step_sum(float* param, const float* grad, const float* grad2, c
 
 int shacira_multi_adam_step(const shacira_adam_seg_t* segs, int32_t num_segs, float beta1, float beta2, float eps,
                             float* step, float* extra_step, const float* scale, const float* div, float* A_out,
-                            int32_t latent_dim, int32_t feature_dim, shacira_stream_t stream) {
-    if (!step || num_segs < 0 || (num_segs > 0 && !segs))
+                            int32_t latent_dim, int32_t feature_dim, uint32_t* ticket, shacira_stream_t stream) {
+    if (!step || !ticket || num_segs < 0 || (num_segs > 0 && !segs))
         return fail(SHACIRA_ERR_INVALID_ARGUMENT, "multi_adam_step: NULL argument");
     if (num_segs > SHACIRA_MAX_ADAM_SEGS)
         return fail(SHACIRA_ERR_UNSUPPORTED, "multi_adam_step: %d segments (max %d)", num_segs, SHACIRA_MAX_ADAM_SEGS);
@@ -573,7 +573,7 @@ int shacira_multi_adam_step(const shacira_adam_seg_t* segs, int32_t num_segs, fl
         if (!owner) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "multi_adam_step: A_out needs `scale` among the segments");
     }
     multi_adam_kernel<<<num_segs, 128, 0, (cudaStream_t)stream>>>(S, beta1, beta2, eps, step, extra_step, scale, div,
-                                                                  A_out, latent_dim, feature_dim);
+                                                                  A_out, latent_dim, feature_dim, ticket);
     LAUNCHED();
     return SHACIRA_OK;
 }

@@ -310,12 +310,11 @@ struct AdamSegs {
 };
 // One CTA per segment (a single CTA walking ~20 tiny tensors pays ~1 us of load latency per tensor: 19 us measured).
 // The last CTA to finish (ticket) advances the step counters -- every CTA has read them by then -- and leaves the
-// ticket at 0 for the next launch. One multi-tensor Adam step may be in flight per device at a time.
-__device__ unsigned g_multi_adam_ticket = 0u;
+// caller's ticket at 0 for the next launch.
 __global__ void __launch_bounds__(128)
 multi_adam_kernel(const __grid_constant__ AdamSegs S, float beta1, float beta2, float eps, float* __restrict__ step,
                   float* __restrict__ extra_step, const float* __restrict__ scale, const float* __restrict__ div,
-                  float* __restrict__ A_out, int C, int F) {
+                  float* __restrict__ A_out, int C, int F, unsigned* __restrict__ ticket) {
     const float t = *step + 1.0f;
     const float bc1 = 1.0f - powf(beta1, t), bc2 = 1.0f - powf(beta2, t);
     const float inv_sqrt_bc2 = rsqrtf(bc2);
@@ -343,10 +342,10 @@ multi_adam_kernel(const __grid_constant__ AdamSegs S, float beta1, float beta2, 
         for (int e = threadIdx.x; e < C * F; e += 128) A_out[e] = scale[e] / div[e / F];
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(&g_multi_adam_ticket, 1u) == gridDim.x - 1) {
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
             *step = t;
             if (extra_step) *extra_step += 1.0f;
-            g_multi_adam_ticket = 0u;
+            *ticket = 0u;
         }
     }
 }

@@ -99,6 +99,7 @@ class ImageFitStep:
         self.m_table, self.v_table = torch.zeros_like(grid.codebook.data), torch.zeros_like(grid.codebook.data)
         self.step_table = torch.zeros((), **f32)
         self.step_small = torch.zeros((), **f32)
+        self.adam_ticket = torch.zeros((), dtype=torch.int32, device=dev)   # arrival counter of the per-tensor CTAs
         self._keep = []
         # the bit-rate kernel depends on nothing but the table: it runs on a forked stream beside the grid / MLP
         # kernels (it is latency bound: 17 us alone) and joins before the optimizer kernels
@@ -215,7 +216,8 @@ class ImageFitStep:
                                           P(self.step_table), 0, st))
             chk(lib.shacira_multi_adam_step(ctypes.cast(self.segs, ctypes.c_void_p), self.nseg, self.betas[0],
                                             self.betas[1], self.eps, P(self.step_small), P(self.step_table),
-                                            P(self.layer.scale.data), P(dec.div.data), P(self.A), self.C, self.F, st))
+                                            P(self.layer.scale.data), P(dec.div.data), P(self.A), self.C, self.F,
+                                            P(self.adam_ticket), st))
 
     # ---- results of the last step (device tensors; reading them synchronises) -------------------
     def rgb_loss(self):
