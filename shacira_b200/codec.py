@@ -20,8 +20,8 @@ The per-channel histogram IS the coding model: decoder and encoder rebuild the i
 reference's formula leaves out -- the histogram itself and the header -- is reported separately by `size_report`.
 Decoding restores round(latent) exactly; that is all the decoder path reads (straight-through rounding, the
 `ŵ = round(w)` of basic_latent_decoder.py:182-198), so the decoded model renders bit-identically to the fitted one.
-Entropy coding is host-side byte work (csrc/arith_coder.inl through the C ABI); the latents' histogram comes from the
-GPU kernels when the table lives on the GPU.
+Entropy coding is host-side byte work (csrc/arith_coder.inl through the C ABI), and so is its coding model: the
+histogram is taken on the host from the very symbols that are coded.
 """
 import json
 import struct
@@ -36,15 +36,11 @@ VERSION = 1
 
 
 def _channel_stats(grid):
-    """Per channel (sorted unique rounded values, counts) as int64 CPU tensors."""
-    w = grid.codebook.detach()
-    if w.is_cuda:
-        return [(u.cpu(), c.cpu()) for u, c in grid.symbol_statistics()]
-    out = []
-    for c in range(w.shape[1]):
-        u, n = torch.unique(torch.round(w[:, c]).long(), return_counts=True)
-        out.append((u, n))
-    return out
+    """Per channel (sorted unique rounded values, counts) as int64 CPU tensors. The symbols have to reach the host
+    for the coder anyway, so the coding model is always built there, from the same bytes that get coded (one path,
+    whatever device the table lives on)."""
+    q = torch.round(grid.codebook.detach()).to(torch.int64).cpu()
+    return [torch.unique(q[:, c], return_counts=True) for c in range(q.shape[1])]
 
 
 def _f32_bytes(t):

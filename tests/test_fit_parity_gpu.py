@@ -128,3 +128,32 @@ def test_native_fit_reaches_reference_quality(lib):
     assert ours["psnr"] > 20.0
     assert abs(ours["psnr"] - ref["psnr"]) <= PSNR_TOL_DB
     assert abs(ours["bpp"] - ref["bpp"]) <= BPP_TOL * ref["bpp"]
+
+
+def test_fitted_model_survives_the_codec_bit_exactly(lib):
+    """SURVEY 8 f-2 end to end: fit, write the byte stream, decode it into a freshly constructed grid + MLP: the
+    rendered image is bit-identical and the file is the reference's BPP formula plus histogram and header."""
+    import math
+    import fit_image
+    from shacira_b200 import codec
+    dev = torch.device("cuda", 0)
+    grid, mlp, coords, gt, fs = fit_image._native_setup(2, dev)
+    for it in range(150):
+        fs.set_lambda(1e-4 + 0.5 * (1e-3 - 1e-4) * (1 + math.cos(math.pi * it / 150)))
+        fs.draw_noise()
+        if it + 1 in (1, 2, 5, 10):
+            fs.update_div()
+        fs.step()
+    fs.close()
+    with torch.no_grad():
+        pred = mlp(grid.interpolate(coords, 0))
+    blob = codec.encode_model(grid, mlp)
+    grid2, mlp2, _, _, fs2 = fit_image._native_setup(7, dev)     # different seed: every value must come from the file
+    fs2.close()
+    codec.load_into(codec.decode_model(blob), grid2, mlp2)
+    with torch.no_grad():
+        pred2 = mlp2(grid2.interpolate(coords, 0))
+    assert torch.equal(pred, pred2)
+    rep = codec.size_report(grid, mlp, blob, pixels=fit_image.H * fit_image.W)
+    assert rep["reference_formula_bpp"] <= rep["file_bpp"] <= rep["reference_formula_bpp"] + 0.05
+    assert abs(rep["reference_formula_bpp"] - rep["empirical_entropy_bpp"]) <= 0.01 * rep["empirical_entropy_bpp"]
