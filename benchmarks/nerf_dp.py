@@ -50,11 +50,9 @@ def main():
     feats = torch.empty((S, L * F), device=dev)
     z = torch.empty((S, L * C), device=dev)
     glat = torch.nn.Parameter(torch.zeros((T, C), device=dev))
-    glat.grad = torch.zeros_like(glat)
     gA = torch.nn.Parameter(torch.zeros((L, C, F), device=dev))
-    gA.grad = torch.zeros_like(gA)
     gS = torch.nn.Parameter(torch.zeros((L, F), device=dev))
-    gS.grad = torch.zeros_like(gS)
+    arena = dp.GradArena([glat, gA, gS])     # one flat gradient buffer: the exchange step is ONE all-reduce
     lib = _lib.load()
     fi, _ = _lib._i32_array(first)
     rs, _ = _lib._i32_array(res)
@@ -69,7 +67,7 @@ def main():
         gS.grad.zero_()
         _lib._check(lib.shacira_latent_backward(3, P(s["coords"]), S, P(s["g"]), P(z), fi, rs, L, BW, C, F, P(A), 0, T, 1,
                                                 P(glat.grad), P(gA.grad), P(gS.grad), st))
-        return dp.allreduce_grads([glat, gA, gS])
+        return arena.allreduce()
 
     for i in range(warmup):
         ncoll = step(i)

@@ -36,6 +36,15 @@ def _worker(rank, world, port, out):
     table.grad = torch.full_like(table, float(rank + 1))
     dp.allreduce_grads([table], average=True)
     ok &= bool((table.grad == 1.5).all())
+    # GradArena: every gradient a view of one flat buffer, the exchange step is ONE collective
+    a, b2 = torch.nn.Parameter(torch.zeros(1000, 2)), torch.nn.Parameter(torch.zeros(3, 5))
+    arena = dp.GradArena([a, b2])
+    a.grad.fill_(float(rank + 1))
+    b2.grad.fill_(float(10 + rank))
+    ok &= arena.allreduce() == 1 and bool((a.grad == 3.0).all()) and bool((b2.grad == 21.0).all())
+    ok &= a.grad.data_ptr() == arena.flat.data_ptr() and arena.flat.numel() == 2015
+    arena.zero_()
+    ok &= not bool(a.grad.any()) and not bool(b2.grad.any())
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
