@@ -276,6 +276,18 @@ int shacira_integrate_backward(const float* feats, const float* tau, const float
                                int32_t num_rays, int32_t num_feats, const float* grad_ray_feats,
                                const float* grad_weights, float* grad_feats, float* grad_tau, shacira_stream_t stream);
 
+/* Samples inside the intersected cells: everything OctreeAS._raymarch_voxel does after the ray/cell intersection
+ * (wisp/accelstructs/octree_as.py:195-228; sample_from_depth_intervals / expand_pack_boundary,
+ * wisp/ops/spc/sampling.py:35-71) in one pass. Nuggets are packed ray after ray: ridx[m] (int32) and
+ * depth[m] = {entry, exit}; num_samples per nugget; jitter[m, k] in [0, 1) is the reference's rand_like draw,
+ * injected. Outputs for e = m * num_samples + k: ridx_out (int64, may be NULL), samples [., 3], depth_samples,
+ * deltas, boundary (uint8, 1 at the first sample of every ray). depth_samples / deltas / boundary are bit-exact
+ * with the reference's own functions (tests/golden/sampling_ref.npz). */
+int shacira_voxel_samples(const float* origins, const float* dirs, const int32_t* ridx, const float* depth,
+                          const float* jitter, int64_t num_nuggets, int32_t num_samples, int64_t* ridx_out,
+                          float* samples, float* depth_samples, float* deltas, uint8_t* boundary,
+                          shacira_stream_t stream);
+
 /* ---- latent bitstream (host side) ---------------------------------------------------- */
 /* Static arithmetic coder over dense symbol ranks 0..num_symbols-1 with 16-bit cumulative
  * frequencies cdf[num_symbols+1] (cdf[0] = 0, strictly increasing, cdf[num_symbols] = 65536).

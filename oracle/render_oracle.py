@@ -37,3 +37,32 @@ def exponential_integration_torch(feats, tau, boundary):
         ws.append(w)
         outs.append((w.unsqueeze(1) * feats[starts[r]:starts[r + 1]]).sum(0))
     return torch.stack(outs), torch.cat(ws)
+
+
+def voxel_samples(origins, dirs, ridx, depth, jitter):
+    """float32 numpy restatement of OctreeAS._raymarch_voxel AFTER the kaolin raytrace
+    (wisp/accelstructs/octree_as.py:195-228) with the reference's in-repo helpers
+    (wisp/ops/spc/sampling.py:35-71) and the jitter injected:
+        steps = (arange(K) + jitter) * (1 / K);  d = entry + (exit - entry) * steps           sampling.py:50-53
+        deltas = d.diff(prepend=entry)                                                        octree_as.py:202
+        samples = origins[ridx] + dirs[ridx] * d                                              octree_as.py:205-206
+        boundary = expand_pack_boundary(mark_first_hit(ridx), K)                              octree_as.py:210-211
+    Pinned against the reference's own sampling.py through tests/golden/sampling_ref.npz.
+    Returns (ridx_out [M*K] int64, samples [M*K,3], depth_samples [M*K], deltas [M*K], boundary [M*K] bool)."""
+    depth = np.asarray(depth, dtype=np.float32)
+    jitter = np.asarray(jitter, dtype=np.float32)
+    M, K = jitter.shape
+    steps = np.arange(K, dtype=np.float32)[None].repeat(M, 0)
+    steps = steps + jitter
+    steps = steps * np.float32(1.0 / K)
+    d = depth[:, 0:1] + (depth[:, 1:2] - depth[:, 0:1]) * steps
+    deltas = np.diff(d, axis=1, prepend=depth[:, 0:1])
+    ridx = np.asarray(ridx).astype(np.int64)
+    o = np.asarray(origins, dtype=np.float32)[ridx][:, None]
+    dr = np.asarray(dirs, dtype=np.float32)[ridx][:, None]
+    samples = o + dr * d[..., None]
+    first = np.ones(M, dtype=bool)
+    first[1:] = ridx[1:] != ridx[:-1]
+    boundary = np.zeros(M * K, dtype=bool)
+    boundary[np.nonzero(first)[0] * K] = True
+    return (np.repeat(ridx, K), samples.reshape(M * K, 3), d.reshape(-1), deltas.reshape(-1).astype(np.float32), boundary)

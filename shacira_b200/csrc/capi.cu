@@ -701,6 +701,25 @@ int shacira_integrate_backward(const float* feats, const float* tau, const float
     return SHACIRA_OK;
 }
 
+int shacira_voxel_samples(const float* origins, const float* dirs, const int32_t* ridx, const float* depth,
+                          const float* jitter, int64_t num_nuggets, int32_t num_samples, int64_t* ridx_out,
+                          float* samples, float* depth_samples, float* deltas, uint8_t* boundary,
+                          shacira_stream_t stream) {
+    if (num_nuggets < 0 || num_samples < 1) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "voxel_samples: bad sizes");
+    if (num_nuggets == 0) return SHACIRA_OK;
+    if (!origins || !dirs || !ridx || !depth || !jitter || !samples || !depth_samples || !deltas || !boundary)
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "voxel_samples: NULL argument");
+    const int64_t total = num_nuggets * num_samples;
+    if (total > ((int64_t)1 << 38)) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "voxel_samples: too many samples");
+    // 1.0 / num_samples as torch multiplies by it: a double scalar narrowed to float32 (sampling.py:52)
+    const float inv_k = (float)(1.0 / (double)num_samples);
+    voxel_samples_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        origins, dirs, ridx, depth, jitter, num_nuggets, num_samples, inv_k, ridx_out, samples, depth_samples, deltas,
+        boundary);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
 // ---- latent bitstream (host) ---------------------------------------------------------------
 int64_t shacira_ac_encode(const int16_t* symbols, int64_t n, const uint32_t* cdf, int32_t num_symbols, uint8_t* out,
                           int64_t out_capacity) {

@@ -120,3 +120,38 @@ integrate_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ 
 }
 
 }  // namespace shacira
+
+namespace shacira {
+
+// Samples inside the intersected cells (the reference's "voxel" raymarch after the ray/cell intersection):
+// OctreeAS._raymarch_voxel, wisp/accelstructs/octree_as.py:195-228, with sample_from_depth_intervals and
+// expand_pack_boundary of wisp/ops/spc/sampling.py:35-71 -- ~10 PyTorch launches and four [M, K] temporaries there,
+// one pass here. Nugget m = (ray ridx[m], entry/exit depth[m]); K samples each, jitter[m, k] in [0, 1) injected:
+//   d = entry + (exit - entry) * ((k + jitter) * (1 / K))      separately rounded mul and add, as torch evaluates it
+//   delta = d_k - d_{k-1} (d_{-1} = entry);  sample = origin + dir * d;  boundary = first sample of a ray's first nugget
+__global__ void __launch_bounds__(256)
+voxel_samples_kernel(const float* __restrict__ origins, const float* __restrict__ dirs, const int32_t* __restrict__ ridx,
+                     const float* __restrict__ depth, const float* __restrict__ jitter, int64_t num_nuggets, int K,
+                     float inv_k, int64_t* __restrict__ ridx_out, float* __restrict__ samples,
+                     float* __restrict__ depth_samples, float* __restrict__ deltas, uint8_t* __restrict__ boundary) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= num_nuggets * K) return;
+    const int64_t m = e / K;
+    const int k = (int)(e - m * K);
+    const float d0 = __ldg(depth + 2 * m), d1 = __ldg(depth + 2 * m + 1);
+    const float span = __fsub_rn(d1, d0);
+    const float st = __fmul_rn(__fadd_rn((float)k, __ldg(jitter + e)), inv_k);
+    const float d = __fadd_rn(d0, __fmul_rn(span, st));
+    float prev = d0;
+    if (k > 0) prev = __fadd_rn(d0, __fmul_rn(span, __fmul_rn(__fadd_rn((float)(k - 1), __ldg(jitter + e - 1)), inv_k)));
+    const int32_t r = __ldg(ridx + m);
+    depth_samples[e] = d;
+    deltas[e] = __fsub_rn(d, prev);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        samples[e * 3 + a] = fmaf(__ldg(dirs + (int64_t)r * 3 + a), d, __ldg(origins + (int64_t)r * 3 + a));
+    if (ridx_out) ridx_out[e] = r;
+    boundary[e] = (k == 0 && (m == 0 || __ldg(ridx + m - 1) != r)) ? 1 : 0;
+}
+
+}  // namespace shacira

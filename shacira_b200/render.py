@@ -78,3 +78,31 @@ def sum_reduce(feats, boundary, starts=None):
     seg = torch.cumsum(seg, 0)
     out = torch.zeros((starts.numel() - 1, feats.shape[1]), dtype=feats.dtype, device=feats.device)
     return out.index_add_(0, seg, feats)
+
+
+def voxel_samples(origins, dirs, ridx, depth, num_samples, jitter=None):
+    """Everything `OctreeAS._raymarch_voxel` does after the ray/cell intersection (octree_as.py:195-228), one kernel:
+    (ridx [M*K] int64, samples [M*K, 3], depth_samples [M*K, 1], deltas [M*K, 1], boundary [M*K] bool) from the
+    intersection "nuggets" (ridx [M] sorted by ray, depth [M, 2] = entry/exit). `jitter` [M, K] in [0, 1) is the
+    stratified-sampling draw (the reference's `torch.rand_like`, sampling.py:51); drawn on the device when None."""
+    lib = _lib.load()
+    origins, dirs, depth = _lib._f32c(origins, "origins"), _lib._f32c(dirs, "dirs"), _lib._f32c(depth, "depth")
+    if not ridx.is_cuda:
+        raise _lib.ShaciraError(_lib.ERR_INVALID_ARGUMENT, "ridx must be a CUDA tensor (no CPU fallback)")
+    ridx32 = ridx.to(torch.int32).contiguous()
+    M, K = depth.shape[0], int(num_samples)
+    dev = depth.device
+    if jitter is None:
+        jitter = torch.rand((M, K), dtype=torch.float32, device=dev)
+    jitter = _lib._f32c(jitter, "jitter")
+    ridx_out = torch.empty((M * K,), dtype=torch.int64, device=dev)
+    samples = torch.empty((M * K, 3), dtype=torch.float32, device=dev)
+    depth_samples = torch.empty((M * K, 1), dtype=torch.float32, device=dev)
+    deltas = torch.empty((M * K, 1), dtype=torch.float32, device=dev)
+    boundary = torch.empty((M * K,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib._check(lib.shacira_voxel_samples(_lib._ptr(origins), _lib._ptr(dirs), _lib._ptr(ridx32), _lib._ptr(depth),
+                                              _lib._ptr(jitter), M, K, _lib._ptr(ridx_out), _lib._ptr(samples),
+                                              _lib._ptr(depth_samples), _lib._ptr(deltas), _lib._ptr(boundary),
+                                              _lib._stream()))
+    return ridx_out, samples, depth_samples, deltas, boundary.bool()

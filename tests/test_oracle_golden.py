@@ -204,3 +204,25 @@ def test_render_oracle_closed_forms():
     import torch
     r2, w2 = ro.exponential_integration_torch(torch.from_numpy(feats), torch.from_numpy(taus), torch.from_numpy(boundary))
     assert np.allclose(r2.numpy(), ray) and np.allclose(w2.numpy(), w)
+
+
+def test_voxel_sample_oracle_matches_the_reference_sampling_helpers():
+    """oracle.render_oracle.voxel_samples against tests/golden/sampling_ref.npz = outputs of the reference's OWN
+    wisp/ops/spc/sampling.py (sample_from_depth_intervals, expand_pack_boundary) on seeded inputs: bit-exact."""
+    import os
+    import numpy as np
+    from oracle import render_oracle as ro
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sampling_ref.npz"))
+    for name in ("a", "b", "c", "d"):
+        depth, jitter, ridx = g[name + "/depth"], g[name + "/jitter"], g[name + "/ridx"]
+        K = int(g[name + "/K"])
+        R = int(ridx.max()) + 1
+        rng = np.random.default_rng(0)
+        o, d = rng.standard_normal((R, 3)).astype(np.float32), rng.standard_normal((R, 3)).astype(np.float32)
+        ridx_out, samples, ds, deltas, boundary = ro.voxel_samples(o, d, ridx, depth, jitter)
+        assert np.array_equal(ds.reshape(-1, K).view(np.uint32), g[name + "/depth_samples"].view(np.uint32)), name
+        assert np.array_equal(boundary.astype(np.uint8), g[name + "/boundary"]), name
+        assert np.array_equal(ridx_out, np.repeat(ridx.astype(np.int64), K))
+        # deltas telescope back to the depths; samples lie on their rays
+        assert np.allclose(depth[:, 0] + deltas.reshape(-1, K).sum(1), ds.reshape(-1, K)[:, -1], rtol=1e-5)
+        assert np.allclose(samples, o[ridx_out] + d[ridx_out] * ds[:, None], rtol=1e-6, atol=1e-6)

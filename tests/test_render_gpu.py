@@ -62,3 +62,37 @@ def test_integration_rejects_cpu_tensors_and_odd_widths(lib):
         render.exponential_integration(torch.zeros(3, 3), torch.zeros(3, 1), b)
     with pytest.raises(lib.ShaciraError):
         render.exponential_integration(torch.zeros(3, 5).cuda(), torch.zeros(3, 1).cuda(), b.cuda())
+
+
+def test_voxel_samples_match_reference_helpers_bit_exactly(lib):
+    """The fused sample-generation kernel against the golden outputs of the reference's own sampling.py
+    (depth samples, boundary: bit-exact) and the oracle restatement (deltas bit-exact, samples to 1 ulp-ish: the
+    reference's addcmul may or may not contract to an FMA)."""
+    import os
+    from oracle import render_oracle as ro
+    from shacira_b200 import render
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sampling_ref.npz"))
+    for name in ("a", "b", "c", "d"):
+        depth, jitter, ridx = g[name + "/depth"], g[name + "/jitter"], g[name + "/ridx"]
+        K = int(g[name + "/K"])
+        R = int(ridx.max()) + 1
+        rng = np.random.default_rng(1)
+        o, d = rng.standard_normal((R, 3)).astype(np.float32), rng.standard_normal((R, 3)).astype(np.float32)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        ridx_out, samples, ds, deltas, boundary = render.voxel_samples(dev(o), dev(d), dev(ridx), dev(depth), K, dev(jitter))
+        want = ro.voxel_samples(o, d, ridx, depth, jitter)
+        assert np.array_equal(ds.cpu().numpy().reshape(-1, K).view(np.uint32), g[name + "/depth_samples"].view(np.uint32))
+        assert np.array_equal(boundary.cpu().numpy().astype(np.uint8), g[name + "/boundary"])
+        assert np.array_equal(ridx_out.cpu().numpy(), want[0])
+        assert np.array_equal(deltas.cpu().numpy().reshape(-1).view(np.uint32), want[3].view(np.uint32))
+        assert np.allclose(samples.cpu().numpy(), want[1], rtol=1e-6, atol=1e-6)
+    # device-drawn jitter: stratified, inside the intervals, boundaries usable by the integration
+    M, K = 1000, 16
+    depth = torch.rand(M, 1, device="cuda") * 2
+    depth = torch.cat((depth, depth + 0.1), 1)
+    ridx = torch.sort(torch.randint(0, 100, (M,), device="cuda"))[0]
+    o, d = torch.randn(100, 3, device="cuda"), torch.randn(100, 3, device="cuda")
+    r2, s2, ds2, dl2, b2 = render.voxel_samples(o, d, ridx, depth, K)
+    ds2 = ds2.reshape(M, K)
+    assert bool((ds2 >= depth[:, :1]).all()) and bool((ds2 <= depth[:, 1:]).all()) and bool((ds2.diff(dim=1) > 0).all())
+    assert int(b2.sum()) == int(torch.unique(ridx).numel()) and bool((dl2 >= 0).all())
