@@ -94,6 +94,22 @@ def main():
     ibwd = lambda i: _lib._check(lib.shacira_integrate_backward(P(feats3), P(tau), P(w), P(starts), R, 3, P(g_ray), P(g_w),
                                                                 P(g_f), P(g_t), st))
     out["integrate_rgb"] = {"rays": R, "samples": S, "fwd_us": timed(ifwd), "bwd_us": timed(ibwd)}
+    # sample generation: 4096 rays against a dense 8^3 grid (the reference's make_dense level 3),
+    # 16 stratified samples per intersected cell -- DDA count + fill + fused voxel-sample kernel
+    from shacira_b200 import render
+    occ = torch.ones((8, 8, 8), dtype=torch.uint8, device=dev)
+    org = torch.randn((4096, 3), device=dev)
+    org = org / org.norm(dim=1, keepdim=True) * 3.0
+    dirs = -org + (torch.rand((4096, 3), device=dev) - 0.5)
+    dirs = dirs / dirs.norm(dim=1, keepdim=True)
+    box = {}
+
+    def march(i):
+        box["r"] = render.raymarch_voxel(occ, org, dirs, 16)
+    t_march = timed(march)
+    out["raymarch_voxel"] = {"rays": 4096, "grid": "8^3 dense", "samples_per_cell": 16,
+                             "samples": int(box["r"][1].shape[0]), "us": t_march,
+                             "note": "includes the one host sync that sizes the outputs"}
     print(json.dumps(out), flush=True)
 
 

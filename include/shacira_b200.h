@@ -288,6 +288,18 @@ int shacira_voxel_samples(const float* origins, const float* dirs, const int32_t
                           float* samples, float* depth_samples, float* deltas, uint8_t* boundary,
                           shacira_stream_t stream);
 
+/* Ray / occupied-cell intersections against a dense occupancy grid (res^3 uint8 cells over [-1,1]^3, cell (x,y,z) at
+ * (x*res + y)*res + z): stands in for kaolin's unbatched_raytrace(..., return_depth=True, with_exit=True) as called
+ * by OctreeAS.raytrace (wisp/accelstructs/octree_as.py:148-170) on the dense / pruned grid of the hash-grid NeRFs.
+ * From-scratch 3D-DDA, parity with kaolin unpinned. Two calls: _count fills count[num_rays]; the caller turns the
+ * counts into exclusive offsets (int64 [num_rays]) and sizes the outputs; _fill writes the nuggets packed ray after
+ * ray, sorted by depth: ridx / pidx (int32 [M]) and depth [M, 2] = {entry, exit}. */
+int shacira_raytrace_dense_count(const uint8_t* occupancy, int32_t res, const float* origins, const float* dirs,
+                                 int32_t num_rays, int32_t* count, shacira_stream_t stream);
+int shacira_raytrace_dense_fill(const uint8_t* occupancy, int32_t res, const float* origins, const float* dirs,
+                                int32_t num_rays, const int64_t* offset, int32_t* ridx, int32_t* pidx, float* depth,
+                                shacira_stream_t stream);
+
 /* ---- latent bitstream (host side) ---------------------------------------------------- */
 /* Static arithmetic coder over dense symbol ranks 0..num_symbols-1 with 16-bit cumulative
  * frequencies cdf[num_symbols+1] (cdf[0] = 0, strictly increasing, cdf[num_symbols] = 65536).

@@ -66,3 +66,31 @@ def voxel_samples(origins, dirs, ridx, depth, jitter):
     boundary = np.zeros(M * K, dtype=bool)
     boundary[np.nonzero(first)[0] * K] = True
     return (np.repeat(ridx, K), samples.reshape(M * K, 3), d.reshape(-1), deltas.reshape(-1).astype(np.float32), boundary)
+
+
+def raytrace_dense_bruteforce(occupancy, origins, dirs):
+    """Ray / occupied-cell intersections by a slab test against EVERY occupied cell (no traversal logic at all), sorted
+    by entry depth per ray: the independent yardstick for the 3D-DDA kernel that stands in for kaolin's
+    unbatched_raytrace (OctreeAS.raytrace, wisp/accelstructs/octree_as.py:148-170; kaolin absent, parity unpinned).
+    float64. Returns a list per ray of (cell index, t_enter, t_exit) with t_exit - t_enter > 0."""
+    occ = np.asarray(occupancy).astype(bool)
+    res = occ.shape[0]
+    cs = 2.0 / res
+    cells = np.argwhere(occ)
+    lo = -1.0 + cells * cs
+    hi = lo + cs
+    out = []
+    for o, d in zip(np.asarray(origins, dtype=np.float64), np.asarray(dirs, dtype=np.float64)):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t0 = (lo - o) / d
+            t1 = (hi - o) / d
+        par = d == 0.0
+        inside = (o >= lo) & (o <= hi)
+        tn = np.where(par, np.where(inside, -np.inf, np.inf), np.minimum(t0, t1)).max(1)
+        tf = np.where(par, np.where(inside, np.inf, -np.inf), np.maximum(t0, t1)).min(1)
+        tn = np.maximum(tn, 0.0)
+        ok = tf > tn
+        idx = (cells[:, 0] * res + cells[:, 1]) * res + cells[:, 2]
+        hits = sorted(zip(tn[ok], tf[ok], idx[ok]))
+        out.append([(int(c), float(a), float(b)) for a, b, c in hits])
+    return out

@@ -720,6 +720,30 @@ int shacira_voxel_samples(const float* origins, const float* dirs, const int32_t
     return SHACIRA_OK;
 }
 
+int shacira_raytrace_dense_count(const uint8_t* occupancy, int32_t res, const float* origins, const float* dirs,
+                                 int32_t num_rays, int32_t* count, shacira_stream_t stream) {
+    if (res < 1 || res > 1024 || num_rays < 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "raytrace_dense: bad res / num_rays");
+    if (num_rays == 0) return SHACIRA_OK;
+    if (!occupancy || !origins || !dirs || !count) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "raytrace_dense_count: NULL argument");
+    raytrace_dense_kernel<false><<<(num_rays + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        occupancy, res, origins, dirs, num_rays, count, nullptr, nullptr, nullptr, nullptr);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
+int shacira_raytrace_dense_fill(const uint8_t* occupancy, int32_t res, const float* origins, const float* dirs,
+                                int32_t num_rays, const int64_t* offset, int32_t* ridx, int32_t* pidx, float* depth,
+                                shacira_stream_t stream) {
+    if (res < 1 || res > 1024 || num_rays < 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "raytrace_dense: bad res / num_rays");
+    if (num_rays == 0) return SHACIRA_OK;
+    if (!occupancy || !origins || !dirs || !offset || !ridx || !pidx || !depth)
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "raytrace_dense_fill: NULL argument");
+    raytrace_dense_kernel<true><<<(num_rays + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        occupancy, res, origins, dirs, num_rays, nullptr, offset, ridx, pidx, depth);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
 // ---- latent bitstream (host) ---------------------------------------------------------------
 int64_t shacira_ac_encode(const int16_t* symbols, int64_t n, const uint32_t* cdf, int32_t num_symbols, uint8_t* out,
                           int64_t out_capacity) {

@@ -155,3 +155,100 @@ voxel_samples_kernel(const float* __restrict__ origins, const float* __restrict_
 }
 
 }  // namespace shacira
+
+namespace shacira {
+
+// Ray / occupied-cell intersections against a DENSE occupancy grid (res^3 cells over [-1, 1]^3, cell (x, y, z) at
+// (x * res + y) * res + z): stands in for kaolin's `spc_render.unbatched_raytrace(octree, ..., level,
+// return_depth=True, with_exit=True)` as called by OctreeAS.raytrace (wisp/accelstructs/octree_as.py:148-170) when the
+// structure is the dense grid the reference builds for its hash-grid NeRFs (OctreeAS.make_dense, :119-127) or a
+// pruned copy of it (nerf.py:150-185). kaolin is absent: this is a from-scratch 3D-DDA (Amanatides & Woo); parity with
+// kaolin's traversal order on grazing rays is unpinned, the oracle is a brute-force slab test per occupied cell.
+// One thread per ray, two passes (count -> exclusive scan on the host side of the ABI -> fill): nuggets come out
+// packed ray after ray, sorted by depth along each ray, which is what the rest of the path expects.
+struct DdaState {
+    int cell[3], step[3];
+    float tmax[3], tdelta[3];
+    float t, tfar;
+    bool hit;
+};
+
+__device__ __forceinline__ void dda_init(const float* o, const float* d, int res, DdaState& s) {
+    float tn = 0.0f, tf = 3.0e38f;
+    float inv[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        inv[a] = d[a] != 0.0f ? 1.0f / d[a] : 3.0e38f;
+        if (d[a] != 0.0f) {
+            const float t0 = (-1.0f - o[a]) * inv[a], t1 = (1.0f - o[a]) * inv[a];
+            tn = fmaxf(tn, fminf(t0, t1));
+            tf = fminf(tf, fmaxf(t0, t1));
+        } else if (o[a] < -1.0f || o[a] > 1.0f) {
+            tf = -1.0f;  // parallel to the slab and outside it
+        }
+    }
+    s.hit = tn < tf;
+    s.t = tn;
+    s.tfar = tf;
+    if (!s.hit) return;
+    const float cs = 2.0f / (float)res;
+    const float te = tn + 1e-6f * fmaxf(1.0f, tn);  // just inside the box
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float p = fmaf(d[a], te, o[a]);
+        int c = (int)floorf((p + 1.0f) * 0.5f * (float)res);
+        c = min(max(c, 0), res - 1);
+        s.cell[a] = c;
+        s.step[a] = d[a] > 0.0f ? 1 : (d[a] < 0.0f ? -1 : 0);
+        if (d[a] != 0.0f) {
+            const float bound = -1.0f + (float)(c + (d[a] > 0.0f ? 1 : 0)) * cs;
+            s.tmax[a] = (bound - o[a]) * inv[a];
+            s.tdelta[a] = cs * fabsf(inv[a]);
+        } else {
+            s.tmax[a] = 3.0e38f;
+            s.tdelta[a] = 3.0e38f;
+        }
+    }
+}
+
+// FILL = false: count[r] = number of occupied cells ray r crosses. FILL = true: write them at offset[r].
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+raytrace_dense_kernel(const uint8_t* __restrict__ occ, int res, const float* __restrict__ origins,
+                      const float* __restrict__ dirs, int32_t num_rays, int32_t* __restrict__ count,
+                      const int64_t* __restrict__ offset, int32_t* __restrict__ ridx, int32_t* __restrict__ pidx,
+                      float* __restrict__ depth) {
+    const int r = blockIdx.x * 128 + threadIdx.x;
+    if (r >= num_rays) return;
+    const float o[3] = {origins[r * 3], origins[r * 3 + 1], origins[r * 3 + 2]};
+    const float d[3] = {dirs[r * 3], dirs[r * 3 + 1], dirs[r * 3 + 2]};
+    DdaState s;
+    dda_init(o, d, res, s);
+    int n = 0;
+    int64_t w = FILL ? offset[r] : 0;
+    if (s.hit) {
+        for (int guard = 0; guard < 3 * res + 3; ++guard) {
+            const int ax = (s.tmax[0] <= s.tmax[1]) ? (s.tmax[0] <= s.tmax[2] ? 0 : 2) : (s.tmax[1] <= s.tmax[2] ? 1 : 2);
+            const float texit = fminf(s.tmax[ax], s.tfar);
+            const int cidx = (s.cell[0] * res + s.cell[1]) * res + s.cell[2];
+            if (texit > s.t && occ[cidx]) {
+                if (FILL) {
+                    ridx[w] = r;
+                    pidx[w] = cidx;
+                    depth[2 * w] = s.t;
+                    depth[2 * w + 1] = texit;
+                    ++w;
+                }
+                ++n;
+            }
+            if (s.tmax[ax] >= s.tfar) break;
+            s.t = texit;
+            s.cell[ax] += s.step[ax];
+            if (s.cell[ax] < 0 || s.cell[ax] >= res) break;
+            s.tmax[ax] += s.tdelta[ax];
+        }
+    }
+    if (!FILL) count[r] = n;
+}
+
+}  // namespace shacira

@@ -106,3 +106,39 @@ def voxel_samples(origins, dirs, ridx, depth, num_samples, jitter=None):
                                               _lib._ptr(depth_samples), _lib._ptr(deltas), _lib._ptr(boundary),
                                               _lib._stream()))
     return ridx_out, samples, depth_samples, deltas, boundary.bool()
+
+
+def raytrace_dense(occupancy, origins, dirs):
+    """(ridx int32 [M], pidx int32 [M], depth [M, 2]) -- the fields of `OctreeAS.raytrace(rays, level, with_exit=True)`
+    (octree_as.py:148-170) for a dense occupancy grid `occupancy` [res, res, res] (bool / uint8, indexed [x, y, z]) over
+    [-1, 1]^3. Nuggets are packed ray after ray and sorted by depth."""
+    lib = _lib.load()
+    origins, dirs = _lib._f32c(origins, "origins"), _lib._f32c(dirs, "dirs")
+    if not occupancy.is_cuda:
+        raise _lib.ShaciraError(_lib.ERR_INVALID_ARGUMENT, "occupancy must be a CUDA tensor (no CPU fallback)")
+    occ = occupancy.to(torch.uint8).contiguous()
+    res, R, dev = occ.shape[0], origins.shape[0], origins.device
+    if occ.dim() != 3 or occ.shape[1] != res or occ.shape[2] != res:
+        raise _lib.ShaciraError(_lib.ERR_INVALID_ARGUMENT, "occupancy must be [res, res, res]")
+    count = torch.empty((R,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib._check(lib.shacira_raytrace_dense_count(_lib._ptr(occ), res, _lib._ptr(origins), _lib._ptr(dirs), R,
+                                                     _lib._ptr(count), _lib._stream()))
+        incl = torch.cumsum(count.to(torch.int64), 0)
+        M = int(incl[-1].item()) if R else 0          # the one host sync of the path: output sizes
+        offset = (incl - count).contiguous()
+        ridx = torch.empty((M,), dtype=torch.int32, device=dev)
+        pidx = torch.empty((M,), dtype=torch.int32, device=dev)
+        depth = torch.empty((M, 2), dtype=torch.float32, device=dev)
+        if M:
+            _lib._check(lib.shacira_raytrace_dense_fill(_lib._ptr(occ), res, _lib._ptr(origins), _lib._ptr(dirs), R,
+                                                        _lib._ptr(offset), _lib._ptr(ridx), _lib._ptr(pidx),
+                                                        _lib._ptr(depth), _lib._stream()))
+    return ridx, pidx, depth
+
+
+def raymarch_voxel(occupancy, origins, dirs, num_samples, jitter=None):
+    """`OctreeAS._raymarch_voxel` (octree_as.py:172-228) on a dense occupancy grid: intersect, then `num_samples`
+    stratified samples per intersected cell. Returns (ridx, samples, depth_samples, deltas, boundary)."""
+    ridx, _, depth = raytrace_dense(occupancy, origins, dirs)
+    return voxel_samples(origins, dirs, ridx, depth, num_samples, jitter)

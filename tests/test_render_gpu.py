@@ -96,3 +96,46 @@ def test_voxel_samples_match_reference_helpers_bit_exactly(lib):
     ds2 = ds2.reshape(M, K)
     assert bool((ds2 >= depth[:, :1]).all()) and bool((ds2 <= depth[:, 1:]).all()) and bool((ds2.diff(dim=1) > 0).all())
     assert int(b2.sum()) == int(torch.unique(ridx).numel()) and bool((dl2 >= 0).all())
+
+
+@pytest.mark.parametrize("res,fill", [(8, 0.3), (16, 0.1), (4, 1.0), (32, 0.02)])
+def test_dense_raytrace_matches_bruteforce_slab_tests(lib, res, fill):
+    """3D-DDA kernel (stand-in for kaolin's unbatched_raytrace on the dense grid) against slab tests of every occupied
+    cell. Grazing hits (interval shorter than 1e-5) may legitimately differ and are ignored on both sides."""
+    from oracle import render_oracle as ro
+    from shacira_b200 import render
+    rng = np.random.default_rng(res)
+    occ = rng.random((res, res, res)) < fill
+    R = 200
+    o = (rng.standard_normal((R, 3)) * 1.5).astype(np.float32)
+    o[: R // 4] = (rng.random((R // 4, 3)) * 1.6 - 0.8).astype(np.float32)       # some origins inside the box
+    tgt = (rng.random((R, 3)) * 2 - 1).astype(np.float32)
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[5] = [1.0, 0.0, 0.0]                                                        # axis-parallel rays
+    d[6] = [0.0, -1.0, 0.0]
+    d = d.astype(np.float32)
+    ridx, pidx, depth = render.raytrace_dense(torch.from_numpy(occ).cuda(), torch.from_numpy(o).cuda(),
+                                              torch.from_numpy(d).cuda())
+    ridx, pidx, depth = ridx.cpu().numpy(), pidx.cpu().numpy(), depth.cpu().numpy()
+    assert np.all(np.diff(ridx) >= 0)                                              # packed ray after ray
+    want = ro.raytrace_dense_bruteforce(occ, o, d)
+    eps = 1e-5
+    total = 0
+    for r in range(R):
+        got = [(int(c), float(a), float(b)) for c, (a, b) in zip(pidx[ridx == r], depth[ridx == r]) if b - a > eps]
+        ref = [h for h in want[r] if h[2] - h[1] > eps]
+        assert [g[0] for g in got] == [h[0] for h in ref], r
+        for g, h in zip(got, ref):
+            assert abs(g[1] - h[1]) <= 1e-4 * max(1.0, h[1]) and abs(g[2] - h[2]) <= 1e-4 * max(1.0, h[2])
+        ent = [g[1] for g in got]
+        assert ent == sorted(ent)                                                  # sorted by depth along the ray
+        total += len(got)
+    assert total > 0
+    # end to end: the reference's voxel raymarch on the dense grid, then integrate
+    r2, samples, ds, deltas, boundary = render.raymarch_voxel(torch.from_numpy(occ).cuda(), torch.from_numpy(o).cuda(),
+                                                              torch.from_numpy(d).cuda(), 4)
+    assert samples.shape[0] == 4 * pidx.shape[0] and bool((samples.abs() <= 1.0 + 1e-4).all())
+    if samples.shape[0]:
+        ray, w = render.exponential_integration(torch.rand(samples.shape[0], 3, device="cuda"), deltas * 5.0, boundary)
+        assert ray.shape[0] == int(boundary.sum()) and bool(torch.isfinite(ray).all())
