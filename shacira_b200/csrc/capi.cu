@@ -263,28 +263,40 @@ int launch_mlp16(const float* x, const float* gt, int64_t n, const float* W1, co
 }
 
 // IN = 16 on the tensor cores (mlp16_tc_step_kernel: mma.sync TF32 with 3xTF32 compensation)
-int launch_mlp_tc(const float* x, const float* gt, int64_t n, const float* W1, const float* b1, const float* W2,
-                  const float* b2, const float* W3, const float* b3, float* gx, float* pred, void* out, float* absmax,
-                  cudaStream_t s) {
+template <int MT, int WARPS, int MINB>
+int launch_mlp_tc_cfg(const float* x, const float* gt, int64_t n, const float* W1, const float* b1, const float* W2,
+                      const float* b2, const float* W3, const float* b3, float* gx, float* pred, void* out, float* absmax,
+                      cudaStream_t s) {
+    using Smem = MlpTcSmem<MT, WARPS>;
     static bool configured = false;
     if (!configured) {
-        CUDA_OK(cudaFuncSetAttribute(mlp16_tc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(MlpTcSmem)));
+        CUDA_OK(cudaFuncSetAttribute(mlp16_tc_step_kernel<MT, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(Smem)));
         configured = true;
     }
     const size_t out_bytes = 8 + sizeof(float) * kMlpConstFloats;
     CUDA_OK(cudaMemsetAsync(out, 0, out_bytes, s));
     if (absmax) CUDA_OK(cudaMemsetAsync(absmax, 0, sizeof(float) * 16, s));
-    int64_t warps = (n + 31) / 32;
-    int64_t blocks = (warps + kTcWarps - 1) / kTcWarps;
-    const int64_t cap = (int64_t)sm_count() * 2;  // persistent: 2 CTAs per SM fit the shared memory
+    const int64_t groups = (n + 16 * MT - 1) / (16 * MT);
+    int64_t blocks = (groups + WARPS - 1) / WARPS;
+    const int64_t cap = (int64_t)sm_count() * MINB;  // persistent CTAs
     if (blocks > cap) blocks = cap;
     const float scale = (float)(2.0 / ((double)n * 3.0));
-    mlp16_tc_step_kernel<<<(int)blocks, kTcThreads, sizeof(MlpTcSmem), s>>>(x, gt, n, W1, b1, W2, b2, W3, b3, scale, gx,
-                                                                            pred, (double*)out, (float*)((char*)out + 8),
-                                                                            (unsigned*)absmax);
+    mlp16_tc_step_kernel<MT, WARPS, MINB><<<(int)blocks, WARPS * 32, sizeof(Smem), s>>>(
+        x, gt, n, W1, b1, W2, b2, W3, b3, scale, gx, pred, (double*)out, (float*)((char*)out + 8), (unsigned*)absmax);
     LAUNCHED();
     return SHACIRA_OK;
+}
+
+// IN = 16 on the tensor cores (mlp16_tc_step_kernel: mma.sync TF32 with 3xTF32 compensation)
+int launch_mlp_tc(const float* x, const float* gt, int64_t n, const float* W1, const float* b1, const float* W2,
+                  const float* b2, const float* W3, const float* b3, float* gx, float* pred, void* out, float* absmax,
+                  cudaStream_t s) {
+    // SHACIRA_MLP_MT: 2 = two m16 tiles per warp iteration, 6 warps x 2 CTAs per SM; 1 = one tile, 6 warps x 3 CTAs (11: 8 warps x 2 CTAs)
+    static const int mt = [] { const char* e = getenv("SHACIRA_MLP_MT"); return e ? atoi(e) : 2; }();
+    if (mt == 1) return launch_mlp_tc_cfg<1, 6, 3>(x, gt, n, W1, b1, W2, b2, W3, b3, gx, pred, out, absmax, s);
+    if (mt == 11) return launch_mlp_tc_cfg<1, 8, 2>(x, gt, n, W1, b1, W2, b2, W3, b3, gx, pred, out, absmax, s);
+    return launch_mlp_tc_cfg<2, 6, 2>(x, gt, n, W1, b1, W2, b2, W3, b3, gx, pred, out, absmax, s);
 }
 
 template <int IN>

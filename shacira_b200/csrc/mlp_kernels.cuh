@@ -538,16 +538,18 @@ mlp16_mse_step_kernel(const float* __restrict__ x, const float* __restrict__ gt,
 // Weight gradients need the point index as K: the activations are staged per warp in shared memory ([point][24],
 // conflict-free for both the fragment-layout stores and the transposed fragment loads).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kTcWarps = 6;
-constexpr int kTcThreads = kTcWarps * 32;
 constexpr int kTcStride = 24;   // floats per staged point row
 
+// MT = m16 tiles (16 points each) a warp runs per iteration; WARPS per CTA. MT = 2 halves the per-point overhead
+// (weight-fragment loads, loop control); MT = 1 halves the registers and the staging rows, i.e. doubles the warps
+// an SM can hold. Both are built; the launcher picks (SHACIRA_MLP_MT, default chosen by measurement).
+template <int MT, int WARPS>
 struct MlpTcSmem {
     uint4 wf[20][32];                       // weight fragments (see the enum in the kernel)
     float b1[16], b2[16], b3[4];
-    float x[kTcWarps][32][kTcStride], h1[kTcWarps][32][kTcStride], h2[kTcWarps][32][kTcStride];
-    float d1[kTcWarps][32][kTcStride], d2[kTcWarps][32][kTcStride];
-    float dy[kTcWarps][32][8];
+    float x[WARPS][16 * MT][kTcStride], h1[WARPS][16 * MT][kTcStride], h2[WARPS][16 * MT][kTcStride];
+    float d1[WARPS][16 * MT][kTcStride], d2[WARPS][16 * MT][kTcStride];
+    float dy[WARPS][16 * MT][8];
     float g[kMlpConstFloats + 1];           // block reduction of the gradients (packed order)
     unsigned cmax[16];                      // max |feature gradient| per input column (bit patterns)
     double loss;
@@ -581,16 +583,16 @@ __device__ __forceinline__ void tile_to_a(const float (&c)[4], uint32_t (&hi)[4]
 }
 
 // out[mt][nt] (+)= in[mt][ks] x W-fragments; KS k-steps, NT n-tiles; fragment f(ks, nt) = wf[base + ks * NT + nt]
-template <int KS, int NT>
-__device__ __forceinline__ void tc_layer(const uint4 (*wf)[32], int base, int lane, const float (&in)[2][2][4],
-                                         float (&out)[2][2][4]) {
+template <int KS, int NT, int MT>
+__device__ __forceinline__ void tc_layer(const uint4 (*wf)[32], int base, int lane, const float (&in)[MT][2][4],
+                                         float (&out)[MT][2][4]) {
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
         uint4 f[NT];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) f[nt] = wf[base + ks * NT + nt][lane];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
             uint32_t ahi[4], alo[4];
             tile_to_a(in[mt][ks], ahi, alo);
 #pragma unroll
@@ -600,9 +602,10 @@ __device__ __forceinline__ void tc_layer(const uint4 (*wf)[32], int base, int la
 }
 
 // stage a [32 points x 16] activation held in accumulator layout as rows of kTcStride floats
-__device__ __forceinline__ void tc_stage(float (*rows)[kTcStride], int g, int t, const float (&a)[2][2][4]) {
+template <int MT>
+__device__ __forceinline__ void tc_stage(float (*rows)[kTcStride], int g, int t, const float (&a)[MT][2][4]) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
             *reinterpret_cast<float2*>(&rows[16 * mt + g][8 * nt + 2 * t]) = make_float2(a[mt][nt][0], a[mt][nt][1]);
@@ -611,11 +614,11 @@ __device__ __forceinline__ void tc_stage(float (*rows)[kTcStride], int g, int t,
 }
 
 // acc[nt] += A^T B over the warp's 32 points: A = rowsA[p][16] (M index = column of A), B = rowsB[p][8 * NT]
-template <int NT, int SB>
+template <int NT, int SB, int MT>
 __device__ __forceinline__ void tc_wgrad(const float (*rowsA)[kTcStride], const float (*rowsB)[SB], int g, int t,
                                          float (&acc)[NT][4]) {
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
+    for (int ks = 0; ks < 2 * MT; ++ks) {
         const int p0 = 8 * ks + t, p1 = p0 + 4;
         uint32_t ahi[4], alo[4];
         split_tf32(rowsA[p0][g], ahi[0], alo[0]);
@@ -632,7 +635,8 @@ __device__ __forceinline__ void tc_wgrad(const float (*rowsA)[kTcStride], const 
     }
 }
 
-__global__ void __launch_bounds__(kTcThreads, 2)
+template <int MT, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, int64_t n,
                      const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                      const float* __restrict__ b2, const float* __restrict__ W3, const float* __restrict__ b3,
@@ -644,7 +648,9 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
     // 12..15, feature gradient (ks, nt) 16..19
     enum { F_L1 = 0, F_L2 = 4, F_L3 = 8, B_D2 = 10, B_D1 = 12, B_GX = 16 };
     extern __shared__ __align__(16) unsigned char s_raw[];
-    MlpTcSmem& S = *reinterpret_cast<MlpTcSmem*>(s_raw);
+    constexpr int kTcThreads = WARPS * 32, kTcWarps = WARPS, PTS = 16 * MT;
+    using Smem = MlpTcSmem<MT, WARPS>;
+    Smem& S = *reinterpret_cast<Smem*>(s_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     for (int e = tid; e < 20 * 32; e += kTcThreads) {
         const int f = e >> 5, fl = e & 31, fg = fl >> 2, ft = fl & 3;
@@ -698,10 +704,10 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
     float (*sdy)[8] = S.dy[warp];
 
     const int64_t warps_total = (int64_t)gridDim.x * kTcWarps;
-    float X[2][2][4];
+    float X[MT][2][4];
     auto load_x = [&](int64_t b) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const int64_t row = b + 16 * mt + g + 8 * hh;
@@ -714,13 +720,13 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
                 }
             }
     };
-    load_x(((int64_t)blockIdx.x * kTcWarps + warp) * 32);
-    for (int64_t base = ((int64_t)blockIdx.x * kTcWarps + warp) * 32; base < n; base += warps_total * 32) {
+    load_x(((int64_t)blockIdx.x * kTcWarps + warp) * PTS);
+    for (int64_t base = ((int64_t)blockIdx.x * kTcWarps + warp) * PTS; base < n; base += warps_total * PTS) {
         // rows of this lane: base + 16 mt + g + 8 h. X was loaded by the previous iteration (software pipeline);
         // the targets of this iteration are requested now, long before the loss needs them
-        float T[2][4];
+        float T[MT][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int col = 2 * t + (r & 1);
@@ -728,20 +734,20 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
                 T[mt][r] = (col < OUT && row < n) ? __ldg(gt + row * OUT + col) : 0.0f;
             }
         __syncwarp();  // the previous iteration's weight-gradient reads of the staging rows are done
-        tc_stage(sx, g, t, X);
+        tc_stage<MT>(sx, g, t, X);
         // ---- forward ----
-        float h1[2][2][4], h2[2][2][4];
+        float h1[MT][2][4], h2[MT][2][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
                 const float2 bb = *reinterpret_cast<const float2*>(&S.b1[8 * nt + 2 * t]);
                 h1[mt][nt][0] = h1[mt][nt][2] = bb.x;
                 h1[mt][nt][1] = h1[mt][nt][3] = bb.y;
             }
-        tc_layer<2, 2>(S.wf, F_L1, lane, X, h1);
+        tc_layer<2, 2, MT>(S.wf, F_L1, lane, X, h1);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
                 const float2 bb = *reinterpret_cast<const float2*>(&S.b2[8 * nt + 2 * t]);
@@ -750,21 +756,21 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
                 h2[mt][nt][0] = h2[mt][nt][2] = bb.x;
                 h2[mt][nt][1] = h2[mt][nt][3] = bb.y;
             }
-        tc_stage(sh1, g, t, h1);
-        tc_layer<2, 2>(S.wf, F_L2, lane, h1, h2);
-        float Y[2][2][4];   // [mt][0] used (8 padded outputs); the second tile is a dummy of the generic helper
+        tc_stage<MT>(sh1, g, t, h1);
+        tc_layer<2, 2, MT>(S.wf, F_L2, lane, h1, h2);
+        float Y[MT][2][4];   // [mt][0] used (8 padded outputs); the second tile is a dummy of the generic helper
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) h2[mt][nt][r] = fmaxf(h2[mt][nt][r], 0.0f);
             }
-        tc_stage(sh2, g, t, h2);
+        tc_stage<MT>(sh2, g, t, h2);
         {
             const float2 bb = *reinterpret_cast<const float2*>(&S.b3[(2 * t) & 3]);
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) {
                 Y[mt][0][0] = Y[mt][0][2] = (t < 2) ? bb.x : 0.0f;
                 Y[mt][0][1] = Y[mt][0][3] = (t < 2) ? bb.y : 0.0f;
 #pragma unroll
@@ -776,7 +782,7 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
             for (int ks = 0; ks < 2; ++ks) {
                 const uint4 f = S.wf[F_L3 + ks][lane];
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
+                for (int mt = 0; mt < MT; ++mt) {
                     uint32_t ahi[4], alo[4];
                     tile_to_a(h2[mt][ks], ahi, alo);
                     mma3(Y[mt][0], ahi, alo, f.x, f.y, f.z, f.w);
@@ -784,9 +790,9 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
             }
         }
         // ---- loss and its gradient (columns 2t, 2t+1 < 3 are real) ----
-        float DY[2][2][4];
+        float DY[MT][2][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int col = 2 * t + (r & 1);
@@ -808,16 +814,16 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
             accb3[1] += DY[mt][0][1] + DY[mt][0][3];
         }
         // ---- backward to the features ----
-        float D[2][2][4];
+        float D[MT][2][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) D[mt][nt][r] = 0.0f;
-        tc_layer<1, 2>(S.wf, B_D2, lane, DY, D);                  // d2 = dy W3   (K = 8 padded outputs)
+        tc_layer<1, 2, MT>(S.wf, B_D2, lane, DY, D);                  // d2 = dy W3   (K = 8 padded outputs)
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
 #pragma unroll
@@ -825,16 +831,16 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
                 accb2[nt][0] += D[mt][nt][0] + D[mt][nt][2];
                 accb2[nt][1] += D[mt][nt][1] + D[mt][nt][3];
             }
-        tc_stage(sd2, g, t, D);
+        tc_stage<MT>(sd2, g, t, D);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) h2[mt][nt][r] = 0.0f;   // h2 is dead: reuse as d1
-        tc_layer<2, 2>(S.wf, B_D1, lane, D, h2);                  // d1 = d2 W2
+        tc_layer<2, 2, MT>(S.wf, B_D1, lane, D, h2);                  // d1 = d2 W2
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
 #pragma unroll
@@ -845,10 +851,10 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
                 accb1[nt][0] += h2[mt][nt][0] + h2[mt][nt][2];
                 accb1[nt][1] += h2[mt][nt][1] + h2[mt][nt][3];
             }
-        tc_stage(sd1, g, t, h2);
-        tc_layer<2, 2>(S.wf, B_GX, lane, h2, D);                  // gx = d1 W1
+        tc_stage<MT>(sd1, g, t, h2);
+        tc_layer<2, 2, MT>(S.wf, B_GX, lane, h2, D);                  // gx = d1 W1
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const int64_t row = base + 16 * mt + g + 8 * hh;
@@ -862,12 +868,12 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
                     }
                 }
             }
-        load_x(base + warps_total * 32);   // next iteration's features: in flight behind the weight-gradient stage
+        load_x(base + warps_total * PTS);   // next iteration's features: in flight behind the weight-gradient stage
         __syncwarp();
         // ---- weight gradients: K = the warp's 32 points, operands from the staged rows ----
-        tc_wgrad<2, kTcStride>(sd1, sx, g, t, accW1);    // dW1[i][m] = sum_p d1[p][i] x[p][m]
-        tc_wgrad<2, kTcStride>(sd2, sh1, g, t, accW2);   // dW2[j][i] = sum_p d2[p][j] h1[p][i]
-        tc_wgrad<1, 8>(sh2, sdy, g, t, accW3);           // dW3^T[j][k] = sum_p h2[p][j] dy[p][k]
+        tc_wgrad<2, kTcStride, MT>(sd1, sx, g, t, accW1);    // dW1[i][m] = sum_p d1[p][i] x[p][m]
+        tc_wgrad<2, kTcStride, MT>(sd2, sh1, g, t, accW2);   // dW2[j][i] = sum_p d2[p][j] h1[p][i]
+        tc_wgrad<1, 8, MT>(sh2, sdy, g, t, accW3);           // dW3^T[j][k] = sum_p h2[p][j] dy[p][k]
     }
     // ---- block reduction in shared memory, then one global add per CTA and value ----
 #pragma unroll
