@@ -111,7 +111,7 @@ def clamped_psnr(pred, gt):
     return 20 * np.log10(255.0) - 10 * np.log10(max(mse, 1e-12))
 
 
-def _native_setup(seed, dev):
+def _native_setup(seed, dev, device_noise=False):
     from shacira_b200.grids import LatentGrid
     from shacira_b200.image_fit import ImageFitStep
     torch.manual_seed(seed)
@@ -124,7 +124,7 @@ def _native_setup(seed, dev):
     grid, mlp = grid.to(dev), mlp.to(dev)
     coords, gt = make_data(seed, dev)
     fs = ImageFitStep(grid, mlp, coords, gt, lr=1e-3, grid_lr=2e-2, ldec_lr=1e-2, prob_lr=1e-4, weight_decay=0.0,
-                      weight_decay_decoder=1e-2)
+                      weight_decay_decoder=1e-2, device_noise=device_noise, noise_seed=10_000 + seed)
     return grid, mlp, coords, gt, fs
 
 
@@ -149,14 +149,15 @@ def fit_native_many(seeds, steps, dev, use_graph, noise_cpu):
     every kernel of the step alone leaves most of the SMs' issue slots idle (ncu: 35-50 % busy), so two or three fits in
     flight overlap each other's latency. `ms_per_step` is wall time per step of the whole group divided by the group
     size, i.e. the throughput figure that fits/hour is made of."""
-    fits = [_native_setup(s, dev) for s in seeds]
+    fits = [_native_setup(s, dev, device_noise=not noise_cpu) for s in seeds]
     gens = [torch.Generator().manual_seed(10_000 + s) for s in seeds]
     streams = [torch.cuda.Stream(device=dev) for _ in seeds]
 
     def host_side(k, it):
         fs = fits[k][4]
         fs.set_lambda(1e-4 + 0.5 * (1e-3 - 1e-4) * (1 + math.cos(math.pi * it / steps)))
-        fs.draw_noise(gens[k] if noise_cpu else None)
+        if noise_cpu:
+            fs.draw_noise(gens[k])      # otherwise the bit-rate kernel draws its own noise (device_noise)
         if it + 1 in (1, 2, 5, 10):
             fs.update_div()
 

@@ -176,6 +176,16 @@ int shacira_entropy_bits(const float* latents, const float* noise, int64_t table
 /* Device scratch for the block partials of shacira_entropy_bits: zero-fill it ONCE, then reuse it for every call
  * on the same stream (the kernel leaves it ready). scratch == NULL makes the call allocate from the stream's
  * memory pool instead (more launch overhead). */
+/* The same in training mode with the U(-0.5, 0.5) noise (latent_grid.py:128-132) drawn INSIDE the kernel from a
+ * counter-based hash of (element, *rng_step, seed) instead of read from a buffer: no RNG kernel, no noise tensor,
+ * and a captured CUDA graph draws fresh noise on every replay because the call advances *rng_step (device uint64)
+ * itself. `scratch` (shacira_entropy_scratch_bytes, zero-initialised once) is mandatory here. The reference's
+ * torch.rand stream cannot be reproduced by any device generator; parity runs inject the noise through
+ * shacira_entropy_bits. */
+int shacira_entropy_bits_rng(const float* latents, uint64_t seed, uint64_t* rng_step, int64_t table_rows,
+                             int32_t latent_dim, const float* params, int32_t num_layers, const int32_t* first_idx,
+                             int32_t num_lods, double* bits, float* grad_latents, float* grad_params, void* scratch,
+                             int64_t scratch_bytes, shacira_stream_t stream);
 int64_t shacira_entropy_scratch_bytes(int32_t latent_dim, int32_t num_lods);
 
 /* ---- symbols / histogram for LatentGrid.size() --------------------------------------- */

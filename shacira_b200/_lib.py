@@ -57,6 +57,7 @@ SIGNATURES = {
     "shacira_latent_backward_planned": (ctypes.c_int, [_vp, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "shacira_latent_backward_planned_bounded": (ctypes.c_int, [_vp, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "shacira_entropy_bits": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _c_int32_p, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "shacira_entropy_bits_rng": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp, _i64, _i32, _vp, _i32, _c_int32_p, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "shacira_entropy_scratch_bytes": (_i64, [_i32, _i32]),
     "shacira_quantize_symbols": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "shacira_symbol_histogram": (ctypes.c_int, [_vp, _i64, _i32, _c_int32_p, _i32, _vp, _vp]),
@@ -413,6 +414,26 @@ def entropy_bits(latents, noise, params, num_layers, first_idx=None, want_grads=
         _check(lib.shacira_entropy_bits(_ptr(latents), _ptr(noise), T, C, _ptr(params), num_layers, fi, L,
                                         _ptr(bits), _ptr(gl), _ptr(gp), _ptr(scratch),
                                         scratch.numel() if scratch is not None else 0, _stream()))
+    return bits, gl, gp
+
+
+def entropy_bits_rng(latents, seed, rng_step, params, num_layers, first_idx=None, scratch=None):
+    """Training-mode bit-rate estimate with the noise drawn inside the kernel (shacira_entropy_bits_rng).
+    `rng_step`: device int64/uint64 scalar tensor, advanced by the call. Returns (bits[1+L] f64, grad_latents, grad_params)."""
+    lib = load()
+    latents, params = _f32c(latents, "latents"), _f32c(params, "params")
+    T, C = latents.shape
+    fi, L = _i32_array(first_idx) if first_idx is not None else (None, 0)
+    dev = latents.device
+    bits = torch.empty((1 + L,), dtype=torch.float64, device=dev)
+    gl = torch.empty_like(latents)
+    gp = torch.empty((4, 3, C), dtype=torch.float32, device=dev)
+    if scratch is None:
+        scratch = torch.zeros(int(lib.shacira_entropy_scratch_bytes(C, L)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.shacira_entropy_bits_rng(_ptr(latents), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(rng_step), T, C,
+                                            _ptr(params), num_layers, fi, L, _ptr(bits), _ptr(gl), _ptr(gp),
+                                            _ptr(scratch), scratch.numel(), _stream()))
     return bits, gl, gp
 
 

@@ -467,10 +467,10 @@ int shacira_latent_backward(int32_t dim, const float* coords, int64_t n, const f
                                               grad_shift, s)))
 }
 
-int shacira_entropy_bits(const float* latents, const float* noise, int64_t table_rows, int32_t latent_dim,
-                         const float* params, int32_t num_layers, const int32_t* first_idx, int32_t num_lods,
-                         double* bits, float* grad_latents, float* grad_params, void* scratch, int64_t scratch_bytes,
-                         shacira_stream_t stream) {
+static int entropy_bits_impl(const float* latents, const float* noise, int64_t table_rows, int32_t latent_dim,
+                             const float* params, int32_t num_layers, const int32_t* first_idx, int32_t num_lods,
+                             double* bits, float* grad_latents, float* grad_params, void* scratch,
+                             int64_t scratch_bytes, uint64_t rng_seed, uint64_t* rng_step, shacira_stream_t stream) {
     if (!latents || !params || !bits) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "latents/params/bits is NULL");
     if (table_rows < 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "table_rows is negative");
     if (latent_dim < 1 || latent_dim > kMaxEntC || (latent_dim & (latent_dim - 1)))
@@ -510,12 +510,31 @@ int shacira_entropy_bits(const float* latents, const float* noise, int64_t table
     }
     unsigned* ticket = (unsigned*)(buf + part_bytes);
     entropy_kernel<<<(int)blocks, kEntBlock, 0, s>>>(latents, noise, total, latent_dim, params, num_layers, lb, bits,
-                                                     grad_latents, grad_params, (float*)buf, ticket);
+                                                     grad_latents, grad_params, (float*)buf, ticket,
+                                                     (unsigned long long)rng_seed, (unsigned long long*)rng_step);
     launch_counter().fetch_add(1);
     const cudaError_t le = cudaGetLastError();
     if (own) cudaFreeAsync(buf, s);
     if (le != cudaSuccess) return fail(SHACIRA_ERR_CUDA, "entropy launch: %s", cudaGetErrorString(le));
     return SHACIRA_OK;
+}
+
+int shacira_entropy_bits(const float* latents, const float* noise, int64_t table_rows, int32_t latent_dim,
+                         const float* params, int32_t num_layers, const int32_t* first_idx, int32_t num_lods,
+                         double* bits, float* grad_latents, float* grad_params, void* scratch, int64_t scratch_bytes,
+                         shacira_stream_t stream) {
+    return entropy_bits_impl(latents, noise, table_rows, latent_dim, params, num_layers, first_idx, num_lods, bits,
+                             grad_latents, grad_params, scratch, scratch_bytes, 0, nullptr, stream);
+}
+
+int shacira_entropy_bits_rng(const float* latents, uint64_t seed, uint64_t* rng_step, int64_t table_rows,
+                             int32_t latent_dim, const float* params, int32_t num_layers, const int32_t* first_idx,
+                             int32_t num_lods, double* bits, float* grad_latents, float* grad_params, void* scratch,
+                             int64_t scratch_bytes, shacira_stream_t stream) {
+    if (!rng_step) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "entropy_bits_rng: rng_step is NULL");
+    if (!scratch) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "entropy_bits_rng: needs the caller's scratch");
+    return entropy_bits_impl(latents, nullptr, table_rows, latent_dim, params, num_layers, first_idx, num_lods, bits,
+                             grad_latents, grad_params, scratch, scratch_bytes, seed, rng_step, stream);
 }
 
 int64_t shacira_entropy_scratch_bytes(int32_t latent_dim, int32_t num_lods) {

@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(kEntBlock)
 entropy_kernel(const float* __restrict__ latents, const float* __restrict__ noise, int64_t total, int C,
                const float* __restrict__ params, int num_layers, const __grid_constant__ LevelBounds lb,
                double* __restrict__ bits, float* __restrict__ grad_latents, float* __restrict__ grad_params,
-               float* __restrict__ partials, unsigned* __restrict__ ticket) {
+               float* __restrict__ partials, unsigned* __restrict__ ticket, unsigned long long rng_seed,
+               unsigned long long* __restrict__ rng_step) {
     __shared__ float s_sp[4 * kMaxEntC], s_b[4 * kMaxEntC], s_ta[4 * kMaxEntC];
     __shared__ float s_dsp[4 * kMaxEntC], s_dta[4 * kMaxEntC];  // chain-rule factors
     __shared__ float s_lvl[SHACIRA_MAX_LEVELS];
@@ -115,6 +116,16 @@ entropy_kernel(const float* __restrict__ latents, const float* __restrict__ nois
     const int64_t stride = (int64_t)gridDim.x * kEntBlock;  // multiple of C (C divides 256)
     const int ch = (int)(((int64_t)blockIdx.x * kEntBlock + tid) % C);
     const int64_t rounds = (total + stride - 1) / stride;
+    // in-kernel training noise: U(-0.5, 0.5) from a counter-based hash of (element, step, seed); the step counter
+    // lives on the device and is advanced by the last CTA, so a captured graph draws fresh noise on every replay
+    const bool rng = rng_step != nullptr;
+    const bool train = rng || noise != nullptr;
+    uint32_t rng_base = 0u;
+    if (rng) {
+        const unsigned long long st = *rng_step;
+        rng_base = (uint32_t)st * 0x9E3779B9u + (uint32_t)(st >> 32) * 0x7F4A7C15u + (uint32_t)rng_seed * 0x85EBCA6Bu +
+                   (uint32_t)(rng_seed >> 32) * 0xC2B2AE35u;
+    }
     for (int64_t r = 0; r < rounds; ++r) {
         const int64_t e = r * stride + (int64_t)blockIdx.x * kEntBlock + tid;
         const bool live = e < total;
@@ -122,7 +133,15 @@ entropy_kernel(const float* __restrict__ latents, const float* __restrict__ nois
         int lvl = 0;
         if (live) {
             const float w = __ldg(latents + e);
-            const float x = noise ? (w + __ldg(noise + e)) : rintf(w);  // latent_grid.py:132
+            float x;
+            if (rng) {
+                uint32_t h = (uint32_t)e + rng_base;      // lowbias32 finaliser, two multiply-xorshift rounds
+                h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+                h += (uint32_t)(e >> 32) * 0x9E3779B9u;
+                x = w + ((float)(h >> 8) * 5.9604644775390625e-08f - 0.5f);   // 24-bit uniform in [0, 1) - 0.5
+            } else {
+                x = noise ? (w + __ldg(noise + e)) : rintf(w);  // latent_grid.py:132
+            }
             CdfTrace up, lo;
             const float Fu = cdf_forward(x + 0.5f, m, s_sp, s_b, s_ta, C, ch, up);
             const float Fl = cdf_forward(x - 0.5f, m, s_sp, s_b, s_ta, C, ch, lo);
@@ -134,7 +153,7 @@ entropy_kernel(const float* __restrict__ latents, const float* __restrict__ nois
             const float g_p = -g_raw * inv_ln2 / (p + 1e-10f);
             const float gx_u = cdf_backward(g_p, m, s_sp, s_ta, C, ch, up, d_sp, d_b, d_ta);
             const float gx_l = cdf_backward(-g_p, m, s_sp, s_ta, C, ch, lo, d_sp, d_b, d_ta);
-            if (grad_latents) grad_latents[e] = noise ? (gx_u + gx_l) : 0.0f;  // round() has zero gradient
+            if (grad_latents) grad_latents[e] = train ? (gx_u + gx_l) : 0.0f;  // round() has zero gradient
             if (lb.num_lods > 0) {
                 const int32_t row = (int32_t)(e / C);
                 int a = 0, bnd = lb.num_lods;  // last level whose first row <= row
@@ -209,7 +228,10 @@ entropy_kernel(const float* __restrict__ latents, const float* __restrict__ nois
             else if (grad_params) grad_params[v - 1 - L] = (float)sum;
         }
     }
-    if (tid == 0) *ticket = 0u;  // ready for the next launch on this scratch
+    if (tid == 0) {
+        *ticket = 0u;  // ready for the next launch on this scratch
+        if (rng) *rng_step += 1ull;  // every CTA has read it (this is the last one to arrive)
+    }
 }
 
 // ---- fused Adam over one tensor ---------------------------------------------------

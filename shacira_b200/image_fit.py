@@ -30,10 +30,13 @@ from . import _lib, grid_ops
 
 class ImageFitStep:
     def __init__(self, grid, mlp, coords, target, lr=1e-3, grid_lr=2e-2, ldec_lr=1e-2, prob_lr=1e-4,
-                 weight_decay=0.0, weight_decay_decoder=1e-2, betas=(0.9, 0.999), eps=1e-8):
+                 weight_decay=0.0, weight_decay_decoder=1e-2, betas=(0.9, 0.999), eps=1e-8, device_noise=False,
+                 noise_seed=0):
         """`grid`: shacira_b200.grids.LatentGrid (2D, single affine decoder, STE rounding); `mlp`:
         nn.Sequential(Linear(L*F,16), ReLU, Linear(16,16), ReLU, Linear(16,3)); coords [N,2], target [N,3].
-        Learning rates / weight decays: the reference's parameter groups (base_trainer.py:219-239; kodak.yaml:61-70)."""
+        Learning rates / weight decays: the reference's parameter groups (base_trainer.py:219-239; kodak.yaml:61-70).
+        device_noise=True draws the bit-rate noise inside the kernel (fresh on every step, also under graph replay:
+        `draw_noise` is then unnecessary); False reads `self.noise`, which `draw_noise` fills (parity runs)."""
         dec = grid.latent_dec
         if getattr(dec, "use_sga", False):
             raise _lib.ShaciraError(_lib.ERR_UNSUPPORTED, "ImageFitStep: SGA sampling runs on the PyTorch path")
@@ -93,6 +96,8 @@ class ImageFitStep:
         self.bits = torch.zeros((1 + self.L,), dtype=torch.float64, device=dev)
         self.noise = torch.zeros((self.T, self.C), **f32)
         self.lam = torch.zeros((), **f32)
+        self.device_noise, self.noise_seed = bool(device_noise), int(noise_seed)
+        self.rng_step = torch.zeros((), dtype=torch.int64, device=dev)
         self.ent_scratch = torch.zeros(int(_lib.load().shacira_entropy_scratch_bytes(self.C, self.L)),
                                        dtype=torch.uint8, device=dev)
         # Adam state
@@ -190,9 +195,16 @@ class ImageFitStep:
             cur = torch.cuda.current_stream(self.dev)
             self.side.wait_stream(cur)
             with torch.cuda.stream(self.side):
-                chk(lib.shacira_entropy_bits(P(lat), P(self.noise), self.T, self.C, P(self.prob), self.num_prob_layers,
-                                             self.fi, self.L, P(self.bits), P(self.g_ent), P(self.g_prob),
-                                             P(self.ent_scratch), self.ent_scratch.numel(), _lib._stream()))
+                if self.device_noise:
+                    chk(lib.shacira_entropy_bits_rng(P(lat), self.noise_seed, P(self.rng_step), self.T, self.C,
+                                                     P(self.prob), self.num_prob_layers, self.fi, self.L, P(self.bits),
+                                                     P(self.g_ent), P(self.g_prob), P(self.ent_scratch),
+                                                     self.ent_scratch.numel(), _lib._stream()))
+                else:
+                    chk(lib.shacira_entropy_bits(P(lat), P(self.noise), self.T, self.C, P(self.prob),
+                                                 self.num_prob_layers, self.fi, self.L, P(self.bits), P(self.g_ent),
+                                                 P(self.g_prob), P(self.ent_scratch), self.ent_scratch.numel(),
+                                                 _lib._stream()))
             chk(lib.shacira_latent_forward_planned(self.plan.handle, P(lat), self.fi, self.rs, self.L, self.bw, self.C,
                                                    self.F, 1, P(self.A), P(shift), 0, P(self.feats), st))
             # the MLP kernel reduces max |feature gradient| per column on the way; the tiled backward takes its

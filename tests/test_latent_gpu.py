@@ -253,3 +253,36 @@ def test_launch_counter_counts_kernels(lib, golden):
     before = lib.launch_count()
     lib.hashgrid_forward(_dev(c["coords"]), torch.zeros((c["T"], 2), device="cuda"), c["first_idx"], c["resolutions"], c["bw"])
     assert lib.launch_count() == before + 1   # all levels in ONE launch (the reference: one per level)
+
+
+def test_in_kernel_noise_matches_buffer_noise_statistically(lib):
+    """shacira_entropy_bits_rng: noise from a counter-based hash inside the kernel. Same seed and step -> identical
+    result; the step advances by itself; and the estimate agrees with torch-drawn U(-0.5, 0.5) noise to the sampling
+    error of 4e5 entries (bits are a mean of i.i.d. terms), as do the parameter gradients."""
+    torch.manual_seed(0)
+    T, C = 400000, 1
+    lat = (torch.randn(T, C, device="cuda") * 3.0)
+    params = torch.zeros(4, 3, C, device="cuda")
+    params[0, 0], params[0, 1], params[0, 2] = 0.3, 0.1, 0.2
+    params[3, 0], params[3, 1] = -0.5, 0.05
+    step = torch.zeros((), dtype=torch.int64, device="cuda")
+    b0, g0, p0 = lib.entropy_bits_rng(lat, 7, step, params, 2)
+    assert int(step) == 1
+    b1, g1, p1 = lib.entropy_bits_rng(lat, 7, step, params, 2)
+    assert int(step) == 2 and float(b0[0]) != float(b1[0])            # fresh noise every call
+    step.zero_()
+    b0r, g0r, _ = lib.entropy_bits_rng(lat, 7, step, params, 2)
+    assert float(b0r[0]) == float(b0[0]) and torch.equal(g0r, g0)      # counter-based: reproducible
+    b_other, _, _ = lib.entropy_bits_rng(lat, 8, torch.zeros((), dtype=torch.int64, device="cuda"), params, 2)
+    assert float(b_other[0]) != float(b0[0])
+    refs = []
+    for _ in range(4):
+        noise = torch.rand(T, C, device="cuda") - 0.5
+        rb, rg, rp = lib.entropy_bits(lat, noise, params, 2)
+        refs.append((float(rb[0]), rp))
+    mean_ref = sum(r[0] for r in refs) / len(refs)
+    for b in (b0, b1):
+        assert abs(float(b[0]) - mean_ref) <= 3e-3 * mean_ref
+    assert torch.isfinite(g0).all() and float(g0.abs().max()) > 0
+    ref_p = sum(r[1] for r in refs) / len(refs)
+    assert float((p0 - ref_p).abs().max()) <= 0.02 * float(ref_p.abs().max())
