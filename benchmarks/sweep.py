@@ -117,7 +117,9 @@ def main():
         rmax = 2048 if bw < 21 else 1290  # SURVEY Q2 window
         for logn in (16, 18, 20, 22):
             for (C, F) in ((2, 2), (1, 4)):
-                for planned in (False, True):
+                # 3D runs on the point-parallel kernels (+ coarse shared-memory backward); --tiled3d adds the
+                # tiled path, measured slower there (most 3D levels do not fit a tile's shared-memory box)
+                for planned in ((False, True) if "--tiled3d" in sys.argv else (False,)):
                     run(3, 16, bw, 16, rmax, 1 << logn, C, F, planned, peak)
 
 
