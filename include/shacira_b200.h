@@ -230,10 +230,11 @@ int shacira_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_
 /* Same update with the gradient taken as grad + (*scale2 * scale2_mul) * grad2: the image fit adds the bit-rate
  * gradient (lambda / rows, lambda a device scalar that changes every step) to the grid gradient without a pass of
  * its own (wisp/trainers/image_trainer.py:298-319). grad2 / scale2 may be NULL. With advance == 0 the step counter
- * is left to a later shacira_multi_adam_step (extra_step), saving the one-thread launch. */
+ * is left to a later shacira_multi_adam_step (extra_step), saving the one-thread launch. zero_grad != 0 clears `grad`
+ * after use (the next backward then accumulates into it without a memset of its own). */
 int shacira_adam_step_sum(float* param, const float* grad, const float* grad2, const float* scale2, float scale2_mul,
                           float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
-                          float weight_decay, float* step, int32_t advance, shacira_stream_t stream);
+                          float weight_decay, float* step, int32_t advance, int32_t zero_grad, shacira_stream_t stream);
 
 /* Adam over MANY small tensors in ONE single-CTA launch (the reference's trainer steps ~20 tensors of 1..256
  * elements: decoder MLP, latent-decoder scale/shift, density-model h/b/a; wisp/trainers/base_trainer.py:206-266

@@ -275,8 +275,12 @@ int launch_mlp_tc_cfg(const float* x, const float* gt, int64_t n, const float* W
         configured = true;
     }
     const size_t out_bytes = 8 + sizeof(float) * kMlpConstFloats;
-    CUDA_OK(cudaMemsetAsync(out, 0, out_bytes, s));
-    if (absmax) CUDA_OK(cudaMemsetAsync(absmax, 0, sizeof(float) * 16, s));
+    if (absmax && (char*)absmax == (char*)out + out_bytes) {   // caller keeps the bound behind `out`: one memset node
+        CUDA_OK(cudaMemsetAsync(out, 0, out_bytes + sizeof(float) * 16, s));
+    } else {
+        CUDA_OK(cudaMemsetAsync(out, 0, out_bytes, s));
+        if (absmax) CUDA_OK(cudaMemsetAsync(absmax, 0, sizeof(float) * 16, s));
+    }
     const int64_t groups = (n + 16 * MT - 1) / (16 * MT);
     int64_t blocks = (groups + WARPS - 1) / WARPS;
     const int64_t cap = (int64_t)sm_count() * MINB;  // persistent CTAs
@@ -562,14 +566,14 @@ int shacira_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_
 
 int shacira_adam_step_sum(float* param, const float* grad, const float* grad2, const float* scale2, float scale2_mul,
                           float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
-                          float weight_decay, float* step, int32_t advance, shacira_stream_t stream) {
+                          float weight_decay, float* step, int32_t advance, int32_t zero_grad, shacira_stream_t stream) {
     if (!param || !grad || !exp_avg || !exp_avg_sq || !step)
         return fail(SHACIRA_ERR_INVALID_ARGUMENT, "adam_step_sum: NULL argument");
     if (n <= 0) return SHACIRA_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t blocks = (n + 1023) / 1024;
     adam_step_sum_kernel<<<(int)blocks, 256, 0, s>>>(param, grad, grad2, scale2, scale2_mul, exp_avg, exp_avg_sq, n, lr,
-                                                     beta1, beta2, eps, weight_decay, step);
+                                                     beta1, beta2, eps, weight_decay, step, zero_grad);
     LAUNCHED();
     if (advance) {
         adam_advance_kernel<<<1, 1, 0, s>>>(step);

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256)
 adam_step_sum_kernel(float* __restrict__ p, const float* __restrict__ g, const float* __restrict__ g2,
                      const float* __restrict__ scale2, float mul2, float* __restrict__ m, float* __restrict__ v,
                      int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                     const float* __restrict__ step) {
+                     const float* __restrict__ step, int zero_grad) {
     const float t = *step + 1.0f;
     const float bc1 = 1.0f - powf(beta1, t), bc2 = 1.0f - powf(beta2, t);
     const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
@@ -311,9 +311,11 @@ adam_step_sum_kernel(float* __restrict__ p, const float* __restrict__ g, const f
         *reinterpret_cast<float4*>(p + i4) = pp;
         *reinterpret_cast<float4*>(m + i4) = mm;
         *reinterpret_cast<float4*>(v + i4) = vv;
+        if (zero_grad) *reinterpret_cast<float4*>(const_cast<float*>(g) + i4) = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
         for (int64_t i = i4; i < min(n, i4 + 4); ++i) {
             const float gi = g2 ? fmaf(s2, g2[i], g[i]) : g[i];
+            if (zero_grad) const_cast<float*>(g)[i] = 0.0f;
             const float gk = fmaf(weight_decay, p[i], gi);
             const float mk = fmaf(beta1, m[i], (1.0f - beta1) * gk);
             const float vk = fmaf(beta2, v[i], (1.0f - beta2) * gk * gk);

@@ -85,11 +85,14 @@ class ImageFitStep:
         self.A = torch.empty((1, self.C, self.F), **f32)
         self.feats = torch.empty((self.n, self.L * self.F), **f32)
         self.gfeat = torch.empty_like(self.feats)
-        self.gfeat_max = torch.zeros((self.L * self.F,), **f32)   # max |feature gradient| per column (MLP kernel)
         self.use_bound = self.IN == 16 and os.environ.get("SHACIRA_MLP_IMPL", "tc") == "tc"   # the tensor-core kernel
         n_par = self.H * self.IN + self.H + self.H * self.H + self.H + self.OUT * self.H + self.OUT
-        self.mlp_out = torch.zeros(2 + n_par, **f32)            # double SSE | packed MLP gradients
-        self.g_grid = torch.empty((self.T, self.C), **f32)
+        # double SSE | packed MLP gradients | max |feature gradient| per column (reduced by the MLP kernel; kept behind
+        # the gradients so that the call clears everything with one memset)
+        self.mlp_out = torch.zeros(2 + n_par + 16, **f32)
+        self.gfeat_max = self.mlp_out[2 + n_par:]
+        # accumulated into by the backward, cleared by the table's Adam kernel after use: no memset per step
+        self.g_grid = torch.zeros((self.T, self.C), **f32)
         self.g_ent = torch.empty((self.T, self.C), **f32)
         self.g_prob = torch.zeros((4, 3, self.C), **f32)
         self.g_dec = torch.zeros((self.L * self.C * self.F + self.L * self.F,), **f32)   # dA rows | dshift rows
@@ -123,7 +126,7 @@ class ImageFitStep:
             s.lr, s.weight_decay, s.grad_mul, s.zero_grad = lr, wd, mul, 1.0 if zero else 0.0
             segs.append(s)
 
-        packed = self.mlp_out[2:]
+        packed = self.mlp_out[2:2 + n_par]
         off = 0
         for lin in self.lin:                       # decoder group: lr, weight decay 0 (base_trainer.py:222-224)
             for p in (lin.weight, lin.bias):
@@ -218,14 +221,14 @@ class ImageFitStep:
                 self.g_dec[self.L * self.C * self.F:].zero_()   # no segment consumes (and clears) the shift rows
             CF = self.C * self.F
             chk(lib.shacira_latent_backward_planned_bounded(self.plan.handle, P(self.gfeat), P(lat), self.fi, self.rs,
-                                                            self.L, self.bw, self.C, self.F, 1, P(self.A), 0, self.T, 1,
+                                                            self.L, self.bw, self.C, self.F, 1, P(self.A), 0, self.T, 0,
                                                             P(self.g_grid), P(self.g_dec), P(self.g_dec[self.L * CF:]),
                                                             bound, st))
             cur.wait_stream(self.side)
             chk(lib.shacira_adam_step_sum(P(lat), P(self.g_grid), P(self.g_ent), P(self.lam), 1.0 / self.T,
                                           P(self.m_table), P(self.v_table), self.T * self.C, self.grid_lr,
                                           self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                          P(self.step_table), 0, st))
+                                          P(self.step_table), 0, 1, st))
             chk(lib.shacira_multi_adam_step(ctypes.cast(self.segs, ctypes.c_void_p), self.nseg, self.betas[0],
                                             self.betas[1], self.eps, P(self.step_small), P(self.step_table),
                                             P(self.layer.scale.data), P(dec.div.data), P(self.A), self.C, self.F,
