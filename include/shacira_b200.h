@@ -133,6 +133,12 @@ int shacira_plan_info(const shacira_plan_t* plan, int64_t* n, int32_t* dim, int3
 /* Device pointers of the plan's arrays (perm[n], coords_sorted[n,dim], tile_off[ntiles+1]) for tests. */
 int shacira_plan_debug(const shacira_plan_t* plan, const int32_t** perm, const float** coords_sorted,
                        const int32_t** tile_off);
+/* sorted_io != 0: the planned forward writes row j of `feats`, and the planned backward reads row j of
+ * `grad_output`, for the point at SORTED position j (perm[j] of shacira_plan_debug is its original index) instead of
+ * at the original index. A consumer that is order independent -- a per-point MLP with a mean loss over a static
+ * coordinate set, its targets permuted once -- then exchanges contiguous, tile-ordered rows with the grid, and the
+ * kernels lose the perm -> row dependent load. Off by default (reference semantics). */
+int shacira_plan_set_sorted_io(shacira_plan_t* plan, int32_t sorted_io);
 /* Same contract as shacira_latent_forward (no zsave: the backward recomputes the interpolation). */
 int shacira_latent_forward_planned(const shacira_plan_t* plan, const float* latents, const int32_t* first_idx,
                                    const int32_t* resolutions, int32_t num_lods, int32_t codebook_bitwidth,

@@ -53,6 +53,7 @@ SIGNATURES = {
     "shacira_plan_destroy": (ctypes.c_int, [_vp]),
     "shacira_plan_info": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), _c_int32_p, _c_int32_p, _c_int32_p]),
     "shacira_plan_debug": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    "shacira_plan_set_sorted_io": (ctypes.c_int, [_vp, _i32]),
     "shacira_latent_forward_planned": (ctypes.c_int, [_vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "shacira_latent_backward_planned": (ctypes.c_int, [_vp, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "shacira_latent_backward_planned_bounded": (ctypes.c_int, [_vp, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -292,6 +293,17 @@ class Plan:
             _check(load().shacira_plan_rebuild(self.handle, dim, _ptr(coords), coords.shape[0], int(tile_points), _stream()))
         self.dim, self.n, self.coords = dim, coords.shape[0], coords
         return self
+
+    def set_sorted_io(self, flag=True):
+        """Exchange feats / grad_output rows in the plan's sorted order (see shacira_plan_set_sorted_io)."""
+        _check(load().shacira_plan_set_sorted_io(self.handle, 1 if flag else 0))
+        self.sorted_io = bool(flag)
+        return self
+
+    def perm_tensor(self):
+        """perm [n] int64 on the plan's device: original index of the point at each sorted position."""
+        import numpy as np
+        return torch.from_numpy(self.arrays()[0].astype(np.int64)).to(self.device)
 
     def info(self):
         n, d, g, t = ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)

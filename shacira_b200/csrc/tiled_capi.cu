@@ -23,6 +23,7 @@ struct shacira_plan {
     int32_t* perm;
     float* coords_sorted;
     int32_t* tile_off;
+    int32_t sorted_io;  // rows of feats / grad_output indexed by sorted position (shacira_plan_set_sorted_io)
 };
 
 namespace {
@@ -46,7 +47,7 @@ size_t smem_pad(size_t smem) {
 
 PlanView view_of(const shacira_plan* p) {
     PlanView v;
-    v.perm = p->perm;
+    v.perm = p->sorted_io ? nullptr : p->perm;
     v.coords_sorted = p->coords_sorted;
     v.tile_off = p->tile_off;
     v.n = p->n;
@@ -297,6 +298,12 @@ int shacira_plan_debug(const shacira_plan_t* plan, const int32_t** perm, const f
     if (perm) *perm = plan->perm;
     if (coords_sorted) *coords_sorted = plan->coords_sorted;
     if (tile_off) *tile_off = plan->tile_off;
+    return SHACIRA_OK;
+}
+
+int shacira_plan_set_sorted_io(shacira_plan_t* plan, int32_t sorted_io) {
+    if (!plan) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan is NULL");
+    plan->sorted_io = sorted_io ? 1 : 0;
     return SHACIRA_OK;
 }
 

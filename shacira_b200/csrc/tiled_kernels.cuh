@@ -35,7 +35,7 @@ constexpr int kPts = SHACIRA_KPTS;  // points per thread whose loads are issued 
 constexpr int kBatch = 2048;  // points accumulated between two flushes of a tile (bounds the fixed-point sums)
 
 struct PlanView {
-    const int32_t* perm;          // sorted position -> original point index
+    const int32_t* perm;          // sorted position -> original point index; NULL: rows are exchanged in SORTED order
     const float* coords_sorted;   // [n, D] coordinates in sorted order
     const int32_t* tile_off;      // [ntiles + 1]
     int64_t n;
@@ -572,7 +572,7 @@ latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, co
 #pragma unroll
             for (int d = 0; d < D; ++d) t[k][d] = 0.5;
             if (j < end) {
-                orig[k] = __ldg(pv.perm + j);
+                orig[k] = pv.perm ? __ldg(pv.perm + j) : j;
                 load_unit_coords<D>(pv.coords_sorted, j, t[k]);
             }
         }
@@ -730,7 +730,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
 #pragma unroll
                 for (int k = 0; k < KP1; ++k) {
                     const int j = base + k * kTileThreads + threadIdx.x;
-                    rows[k] = (j < b1) ? grad_out + (int64_t)__ldg(pv.perm + j) * L * F : nullptr;
+                    rows[k] = (j < b1) ? grad_out + (int64_t)(pv.perm ? __ldg(pv.perm + j) : j) * L * F : nullptr;
                 }
                 for (int l0 = 0; l0 < L; l0 += 8) {  // 8 levels = two 16-byte vectors per point in flight
                     float g[KP1][2][4 * F];
@@ -821,7 +821,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
 #pragma unroll
                     for (int d = 0; d < D; ++d) tk[k][d] = 0.5;
                     if (livek[k]) {
-                        load_row<kLv * F>(grad_out + (int64_t)__ldg(pv.perm + j) * L * F + l0 * F, gk[k]);
+                        load_row<kLv * F>(grad_out + (int64_t)(pv.perm ? __ldg(pv.perm + j) : j) * L * F + l0 * F, gk[k]);
                         load_unit_coords<D>(pv.coords_sorted, j, tk[k]);
                     }
                 }

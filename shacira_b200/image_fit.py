@@ -64,10 +64,13 @@ class ImageFitStep:
         self.IN, self.H, self.OUT = self.lin[0].in_features, self.lin[0].out_features, self.lin[2].out_features
         if self.IN != self.L * self.F:
             raise _lib.ShaciraError(_lib.ERR_INVALID_ARGUMENT, "MLP input width must be num_lods * feature_dim")
-        self.plan = grid_ops.plan_for(self.coords)
-        if self.plan is None:
-            raise _lib.ShaciraError(_lib.ERR_UNSUPPORTED, "ImageFitStep: coordinate set too small for the tiled kernels")
-        self.plan.users += 1   # pinned for the life of this object
+        if self.n < grid_ops.PLAN_MIN_POINTS or self.L % 4:
+            raise _lib.ShaciraError(_lib.ERR_UNSUPPORTED, "ImageFitStep: coordinate set / level count outside the tiled path")
+        # A plan of its own, in sorted-I/O mode: the step's consumers of the feature rows (per-point MLP, mean loss)
+        # do not care about the order of the points, so grid and MLP exchange rows in the plan's tile order (targets
+        # permuted once here) and the grid kernels lose their perm -> row dependent loads.
+        self.plan = _lib.Plan(self.coords).set_sorted_io(True)
+        self.target = self.target[self.plan.perm_tensor()].contiguous()
         f32 = dict(dtype=torch.float32, device=dev)
         # density-model parameters live in ONE [4, 3, C] buffer (the kernel's layout); the module's h / b / a become
         # views of it, so nothing is packed per step
@@ -243,5 +246,5 @@ class ImageFitStep:
 
     def close(self):
         if self.plan is not None:
-            self.plan.users = max(0, self.plan.users - 1)
+            self.plan.close()
             self.plan = None

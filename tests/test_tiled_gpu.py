@@ -285,3 +285,27 @@ def test_mlp_step_reports_feature_gradient_bound(lib):
     ws = [mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias, mlp[4].weight, mlp[4].bias]
     _, gx, _, _ = lib.mlp_mse_step(x, gt, *[w.detach() for w in ws], absmax_out=bound)
     assert torch.equal(bound, gx.abs().amax(dim=0))
+
+
+def test_sorted_io_plan_exchanges_rows_in_tile_order(lib):
+    """shacira_plan_set_sorted_io: forward rows come out at the sorted position, backward rows are read there;
+    values are the same numbers as with the default (original-index) exchange."""
+    c = _case(2, 16, 16, 16, 512, 60000, 1, 1, seed=33, kind="pixels")
+    coords, lat, A, S, g = _dev(c["coords"]), _dev(c["lat"]), _dev(c["A"]), _dev(c["S"]), _dev(c["g"])
+    plan = lib.Plan(coords)
+    feats = lib.latent_forward_planned(plan, lat, c["first"], c["res"], 16, A, S, 1, True)
+    gl, gA, gS = lib.latent_backward_planned(plan, g, lat, c["first"], c["res"], 16, A, 1, 1, c["T"], True, True)
+    plan2 = lib.Plan(coords).set_sorted_io(True)
+    perm = plan2.perm_tensor()
+    assert torch.equal(torch.sort(perm)[0], torch.arange(coords.shape[0], device="cuda"))
+    feats_s = lib.latent_forward_planned(plan2, lat, c["first"], c["res"], 16, A, S, 1, True)
+    assert torch.equal(feats_s, feats[perm])
+    gl_s, gA_s, gS_s = lib.latent_backward_planned(plan2, g[perm].contiguous(), lat, c["first"], c["res"], 16, A, 1, 1,
+                                                   c["T"], True, True)
+    # per tile the fixed-point sums are order independent; nodes shared by neighbouring tiles receive their few
+    # float adds in launch order, hence last-bit differences between two launches
+    assert rel_err(gl_s.cpu().numpy(), gl.cpu().numpy()) <= 1e-6
+    assert rel_err(gA_s.cpu().numpy().sum(0), gA.cpu().numpy().sum(0)) <= 1e-5
+    assert rel_err(gS_s.cpu().numpy().sum(0), gS.cpu().numpy().sum(0)) <= 1e-5
+    plan.close()
+    plan2.close()
