@@ -52,6 +52,18 @@ def main():
                                                                 bench.BITWIDTH, 1, 1, 1, p(A), 0, T, 1, p(s["gl"]),
                                                                 p(gA), p(gS), p(s["gmax"]), st))
 
+    for s_ in sets:
+        s_["plan_sorted"] = _lib.Plan(s_["coords"]).set_sorted_io(True)
+
+    def fwd_sorted(s, st):
+        _lib._check(lib.shacira_latent_forward_planned(s["plan_sorted"].handle, p(lat), fi, rs, L, bench.BITWIDTH, 1, 1, 1,
+                                                       p(A), p(shift), 0, p(s["feats"]), st))
+
+    def bwd_sorted_bounded(s, st):
+        _lib._check(lib.shacira_latent_backward_planned_bounded(s["plan_sorted"].handle, p(s["grad_out"]), p(lat), fi, rs,
+                                                                L, bench.BITWIDTH, 1, 1, 1, p(A), 0, T, 1, p(s["gl"]),
+                                                                p(gA), p(gS), p(s["gmax"]), st))
+
     def fwd_pp(s, st):
         _lib._check(lib.shacira_latent_forward(2, p(s["coords"]), n, p(lat), fi, rs, L, bench.BITWIDTH, 1, 1, 1, p(A),
                                                p(shift), 0, p(s["feats"]), p(s["z"]), st))
@@ -84,7 +96,8 @@ def main():
 
     out = {}
     only_ent = bool(os.environ.get("ONLY_ENT"))
-    for name, fn in ((("entropy_fwd_bwd", ent),) if only_ent else (("entropy_fwd_bwd", ent), ("mlp_mse_step", mlpk), ("fwd_tiled", fwd), ("bwd_tiled_dec", bwd), ("bwd_tiled_nodec", lambda s, st: bwd(s, st, False)), ("bwd_tiled_dec_bounded", bwd_bounded),
+    for name, fn in ((("entropy_fwd_bwd", ent),) if only_ent else (("entropy_fwd_bwd", ent), ("mlp_mse_step", mlpk), ("fwd_tiled", fwd), ("bwd_tiled_dec", bwd), ("bwd_tiled_nodec", lambda s, st: bwd(s, st, False)), ("bwd_tiled_dec_bounded", bwd_bounded), ("fwd_tiled_sorted_io", fwd_sorted),
+                     ("bwd_tiled_dec_bounded_sorted_io", bwd_sorted_bounded),
                      ("fwd_pointparallel", fwd_pp), ("bwd_pointparallel", bwd_pp),
                      ("step_tiled", lambda s, st: (fwd(s, st), bwd(s, st))))):
         stream = torch.cuda.Stream()
