@@ -34,6 +34,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     steps, warmup, sets_n = 30, 5, 4
+    chunks = 1
+    if "--chunks" in sys.argv:
+        chunks = int(sys.argv[sys.argv.index("--chunks") + 1])
     res = geometric_resolutions(16, 2048, L)
     sizes = [min(2 ** BW, r ** 3) for r in res]
     first = [0]
@@ -58,7 +61,43 @@ def main():
     rs, _ = _lib._i32_array(res)
     P = _lib._ptr
 
+    # level chunks with about equal numbers of rows: [level_lo, level_hi), flat range of the rows in the arena
+    bounds = [0]
+    for k in range(1, chunks):
+        tgt = T * k // chunks
+        l = min(range(1, L), key=lambda l_: abs(first[l_] - tgt))
+        bounds.append(max(l, bounds[-1] + 1))
+    bounds.append(L)
+    spans = []
+    for k in range(chunks):
+        lo, hi = bounds[k], bounds[k + 1]
+        mask = sum(1 << l for l in range(lo, hi))
+        r0 = first[lo] * C
+        r1 = (first[hi] * C) if hi < L else arena.flat.numel()      # the last chunk carries the decoder gradients too
+        spans.append((mask, r0, r1))
+
+    def step_chunked(i):
+        """Backward in level chunks; the all-reduce of a chunk's rows is in flight while the next chunk computes."""
+        s = sets[i % sets_n]
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib._check(lib.shacira_latent_forward(3, P(s["coords"]), S, P(lat), fi, rs, L, BW, C, F, 1, P(A), P(shift), 0,
+                                               P(feats), P(z), st))
+        gA.grad.zero_()
+        gS.grad.zero_()
+        handles = []
+        for k, (mask, r0, r1) in enumerate(spans):
+            _lib._check(lib.shacira_latent_backward_levels(3, P(s["coords"]), S, P(s["g"]), P(z), fi, rs, L, BW, C, F, P(A),
+                                                           0, T, 1 if k == 0 else 0, mask, P(glat.grad), P(gA.grad),
+                                                           P(gS.grad), st))
+            if world > 1:
+                handles.append(dist.all_reduce(arena.flat[r0:r1], op=dist.ReduceOp.SUM, async_op=True))
+        for h in handles:
+            h.wait()
+        return len(handles)
+
     def step(i):
+        if chunks > 1:
+            return step_chunked(i)
         s = sets[i % sets_n]
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         _lib._check(lib.shacira_latent_forward(3, P(s["coords"]), S, P(lat), fi, rs, L, BW, C, F, 1, P(A), P(shift), 0,
@@ -94,7 +133,7 @@ def main():
                           "ms_per_step": ms, "samples_per_s": S * world / ms * 1e3, "rays_per_s": RAYS * world / ms * 1e3,
                           "allreduce_bytes": T * C * 4, "collectives_per_step": ncoll,
                           "alg_GBs_per_gpu": (bf + bb) * S / ms / 1e6, "frac_hbm_peak": (bf + bb) * S / ms / 1e6 / peak,
-                          "path": "point-parallel 3D kernels"}), flush=True)
+                          "backward_level_chunks": chunks, "path": "point-parallel 3D kernels"}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

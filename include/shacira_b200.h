@@ -109,6 +109,18 @@ int shacira_latent_backward(int32_t dim, const float* coords, int64_t n, const f
                             int32_t num_lods, int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim,
                             const float* A, int32_t per_level, int64_t table_rows, int32_t zero_first,
                             float* grad_latents, float* grad_A, float* grad_shift, shacira_stream_t stream);
+/* The same restricted to the levels whose bit is set in `level_mask` (bit l = level l): gradients of the other
+ * levels' rows and decoder slots are left untouched. The rows of a level are a contiguous range of the table, so a
+ * data-parallel caller can run the backward in a few level chunks and start the all-reduce of one chunk's rows while
+ * the next chunk computes (benchmarks/nerf_dp.py --chunks). zero_first clears the WHOLE table: pass it with the first
+ * chunk only. */
+int shacira_latent_backward_levels(int32_t dim, const float* coords, int64_t n, const float* grad_output,
+                                   const float* zsave, const int32_t* first_idx, const int32_t* resolutions,
+                                   int32_t num_lods, int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim,
+                                   const float* A, int32_t per_level, int64_t table_rows, int32_t zero_first,
+                                   uint32_t level_mask, float* grad_latents, float* grad_A, float* grad_shift,
+                                   shacira_stream_t stream);
+
 
 /* ---- tiled fast path: spatial plan + planned fused forward / backward ----------------- */
 /* A plan bins the points of ONE coordinate set into power-of-two spatial tiles (about

@@ -48,6 +48,7 @@ SIGNATURES = {
     "shacira_hashgrid_corners": (ctypes.c_int, [_i32, _vp, _i64, _c_int32_p, _i32, _i32, _vp, _vp, _vp]),
     "shacira_latent_forward": (ctypes.c_int, [_i32, _vp, _i64, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "shacira_latent_backward": (ctypes.c_int, [_i32, _vp, _i64, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "shacira_latent_backward_levels": (ctypes.c_int, [_i32, _vp, _i64, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, ctypes.c_uint32, _vp, _vp, _vp, _vp]),
     "shacira_plan_create": (ctypes.c_int, [_i32, _vp, _i64, _i32, _vp, ctypes.POINTER(_vp)]),
     "shacira_plan_rebuild": (ctypes.c_int, [_vp, _i32, _vp, _i64, _i32, _vp]),
     "shacira_plan_destroy": (ctypes.c_int, [_vp]),
@@ -241,8 +242,9 @@ def latent_forward(coords, latents, first_idx, resolutions, bitwidth, A, shift, 
 
 
 def latent_backward(coords, grad_output, z, first_idx, resolutions, bitwidth, A, latent_dim, feature_dim,
-                    table_rows, want_decoder_grads):
-    """Returns (grad_latents[T, C], grad_A[L, C, F] or None, grad_shift[L, F] or None)."""
+                    table_rows, want_decoder_grads, level_chunks=None):
+    """Returns (grad_latents[T, C], grad_A[L, C, F] or None, grad_shift[L, F] or None). `level_chunks`: list of level
+    bit masks; the backward then runs as one launch per chunk (shacira_latent_backward_levels) into the same buffers."""
     lib = load()
     coords = _f32c(coords, "coords")
     grad_output = _f32c(grad_output, "grad_output")
@@ -259,9 +261,11 @@ def latent_backward(coords, grad_output, z, first_idx, resolutions, bitwidth, A,
         gA = torch.zeros((L, latent_dim, feature_dim), dtype=torch.float32, device=dev)
         gS = torch.zeros((L, feature_dim), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _check(lib.shacira_latent_backward(dim, _ptr(coords), n, _ptr(grad_output), _ptr(z), fi, rs, L, bitwidth,
-                                           latent_dim, feature_dim, _ptr(A), per_level, table_rows, 1, _ptr(gl),
-                                           _ptr(gA), _ptr(gS), _stream()))
+        for k, mask in enumerate(level_chunks or [0xFFFFFFFF]):
+            _check(lib.shacira_latent_backward_levels(dim, _ptr(coords), n, _ptr(grad_output), _ptr(z), fi, rs, L,
+                                                      bitwidth, latent_dim, feature_dim, _ptr(A), per_level, table_rows,
+                                                      1 if k == 0 else 0, int(mask) & 0xFFFFFFFF, _ptr(gl), _ptr(gA),
+                                                      _ptr(gS), _stream()))
     return gl, gA, gS
 
 

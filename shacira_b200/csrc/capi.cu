@@ -129,13 +129,14 @@ inline int join_side_stream(cudaStream_t s) {
 }
 template <int D, int C, int F, bool LATENT>
 int launch_coarse_bwd(const float* coords, int64_t n, const float* g, const LevelParams& lp, const float* A,
-                      int per_level, float* gt, cudaStream_t s, uint32_t& mask, bool& pending_join) {
+                      int per_level, float* gt, cudaStream_t s, uint32_t& mask, bool& pending_join,
+                      uint32_t level_mask = 0xffffffffu) {
     mask = 0;
     pending_join = false;
     if (n < 65536 || coarse_max_slabs() == 0) return SHACIRA_OK;
     CoarseJobs jobs;
     constexpr int NV = LATENT ? C : F;
-    const uint32_t m = plan_coarse_jobs(D, lp, NV, n, sm_count(), coarse_max_slabs(), jobs);
+    const uint32_t m = plan_coarse_jobs(D, lp, NV, n, sm_count(), coarse_max_slabs(), jobs, level_mask);
     if (!m) return SHACIRA_OK;
     const size_t smem = coarse_smem_bytes(jobs, NV);
     static size_t configured = 0;
@@ -191,15 +192,16 @@ int launch_latent_fwd(const float* coords, int64_t n, const float* lat, const Le
 }
 template <int D, int C, int F>
 int launch_latent_bwd(const float* coords, int64_t n, const float* g, const float* zsave, const LevelParams& lp,
-                      const float* A, int per_level, float* gl, float* gA, float* gS, cudaStream_t s) {
+                      const float* A, int per_level, float* gl, float* gA, float* gS, cudaStream_t s,
+                      uint32_t level_mask = 0xffffffffu) {
     const int nA = per_level ? lp.num_lods : 1;
     const size_t smem = sizeof(float) * (size_t)(nA * C * F + lp.num_lods * C * F + lp.num_lods * F);
     uint32_t skip = 0;
     bool join = false;
-    int rc = launch_coarse_bwd<D, C, F, true>(coords, n, g, lp, A, per_level, gl, s, skip, join);
+    int rc = launch_coarse_bwd<D, C, F, true>(coords, n, g, lp, A, per_level, gl, s, skip, join, level_mask);
     if (rc) return rc;
     latent_bwd_kernel<D, C, F><<<grid_for(n, kBlock), kBlock, smem, s>>>(coords, n, g, zsave, lp, A, per_level, skip,
-                                                                          gl, gA, gS);
+                                                                          level_mask, gl, gA, gS);
     LAUNCHED();
     return join ? join_side_stream(s) : SHACIRA_OK;
 }
@@ -444,11 +446,12 @@ int shacira_latent_forward(int32_t dim, const float* coords, int64_t n, const fl
                                               s)))
 }
 
-int shacira_latent_backward(int32_t dim, const float* coords, int64_t n, const float* grad_output,
-                            const float* zsave, const int32_t* first_idx, const int32_t* resolutions,
-                            int32_t num_lods, int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim,
-                            const float* A, int32_t per_level, int64_t table_rows, int32_t zero_first,
-                            float* grad_latents, float* grad_A, float* grad_shift, shacira_stream_t stream) {
+int shacira_latent_backward_levels(int32_t dim, const float* coords, int64_t n, const float* grad_output,
+                                   const float* zsave, const int32_t* first_idx, const int32_t* resolutions,
+                                   int32_t num_lods, int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim,
+                                   const float* A, int32_t per_level, int64_t table_rows, int32_t zero_first,
+                                   uint32_t level_mask, float* grad_latents, float* grad_A, float* grad_shift,
+                                   shacira_stream_t stream) {
     LevelParams lp;
     int rc = build_levels(dim, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
     if (rc) return rc;
@@ -464,11 +467,21 @@ int shacira_latent_backward(int32_t dim, const float* coords, int64_t n, const f
     if (dim == 2) {
         DISPATCH_CF(latent_dim, feature_dim,
                     (launch_latent_bwd<2, kC, kF>(coords, n, grad_output, zsave, lp, A, per_level, grad_latents,
-                                                  grad_A, grad_shift, s)))
+                                                  grad_A, grad_shift, s, level_mask)))
     }
     DISPATCH_CF(latent_dim, feature_dim,
                 (launch_latent_bwd<3, kC, kF>(coords, n, grad_output, zsave, lp, A, per_level, grad_latents, grad_A,
-                                              grad_shift, s)))
+                                              grad_shift, s, level_mask)))
+}
+
+int shacira_latent_backward(int32_t dim, const float* coords, int64_t n, const float* grad_output,
+                            const float* zsave, const int32_t* first_idx, const int32_t* resolutions,
+                            int32_t num_lods, int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim,
+                            const float* A, int32_t per_level, int64_t table_rows, int32_t zero_first,
+                            float* grad_latents, float* grad_A, float* grad_shift, shacira_stream_t stream) {
+    return shacira_latent_backward_levels(dim, coords, n, grad_output, zsave, first_idx, resolutions, num_lods,
+                                          codebook_bitwidth, latent_dim, feature_dim, A, per_level, table_rows,
+                                          zero_first, 0xffffffffu, grad_latents, grad_A, grad_shift, stream);
 }
 
 static int entropy_bits_impl(const float* latents, const float* noise, int64_t table_rows, int32_t latent_dim,

@@ -123,13 +123,13 @@ coarse_bwd_kernel(const float* __restrict__ coords, int64_t n, const float* __re
 // Host side: which dense levels go to shared memory, cut into slabs, and how the CTAs are shared out.
 // Returns the mask of the levels covered (0: nothing to do). `max_slabs` bounds the scan overhead per level.
 inline uint32_t plan_coarse_jobs(int dim, const LevelParams& lp, int nv, int64_t n, int sms, int max_slabs,
-                                 CoarseJobs& jobs) {
+                                 CoarseJobs& jobs, uint32_t level_mask = 0xffffffffu) {
     memset(&jobs, 0, sizeof(jobs));
     uint32_t mask = 0;
     double weight[kCoarseMaxJobs];
     double wsum = 0.0;
     for (int l = 0; l < lp.num_lods; ++l) {
-        if (!((lp.dense_mask >> l) & 1u)) continue;
+        if (!((lp.dense_mask >> l) & 1u) || !((level_mask >> l) & 1u)) continue;
         const int64_t res = lp.res[l];
         const int64_t plane = dim == 2 ? res : res * res;
         const int64_t max_planes = kCoarseBudgetFloats / (nv * plane);

@@ -239,8 +239,8 @@ template <int D, int C, int F>
 __global__ void __launch_bounds__(kBlock)
 latent_bwd_kernel(const float* __restrict__ coords, int64_t n, const float* __restrict__ grad_out,
                   const float* __restrict__ zsave, const __grid_constant__ LevelParams lp,
-                  const float* __restrict__ A, int per_level, uint32_t skip_mask, float* __restrict__ grad_latents,
-                  float* __restrict__ grad_A, float* __restrict__ grad_shift) {
+                  const float* __restrict__ A, int per_level, uint32_t skip_mask, uint32_t level_mask,
+                  float* __restrict__ grad_latents, float* __restrict__ grad_A, float* __restrict__ grad_shift) {
     extern __shared__ float s_mem[];  // A [nA*C*F] | gA [L*C*F] | gS [L*F]
     const int L = lp.num_lods;
     const int nA = per_level ? L : 1;
@@ -263,6 +263,7 @@ latent_bwd_kernel(const float* __restrict__ coords, int64_t n, const float* __re
     const bool vec_z = (C == 1) || ((L * C) % (C >= 4 ? 4 : C) == 0);
 #pragma unroll 2
     for (int l = 0; l < L; ++l) {
+        if (!((level_mask >> l) & 1u)) continue;  // not part of this launch (level-chunked backward)
         // levels accumulated in shared memory by coarse_bwd_kernel: only the decoder gradients remain here
         const bool scatter = !((skip_mask >> l) & 1u);
         if (!scatter && !want_dec) continue;

@@ -246,3 +246,24 @@ def test_latent_backward_large_batch_3d_matches_oracle(lib):
     assert rel_err(gl.cpu().numpy(), want) <= BWD_TOL
     want_gS = c["grad_out"].reshape(n, L, F).astype(np.float64).sum(0)
     assert rel_err(gS.cpu().numpy(), want_gS) <= BWD_TOL
+
+
+def test_level_chunked_backward_equals_one_launch(lib):
+    """shacira_latent_backward_levels: the backward as a few level chunks (what lets a data-parallel caller overlap
+    the all-reduce of one chunk's rows with the next chunk's compute) fills the same buffers as one launch."""
+    dim, L, bw, C, F, n = 3, 16, 19, 1, 4, 1 << 17
+    c = make_case(dim, L, bw, 16, 2048, n, F, seed=5, coord_kind="uniform")
+    rng = np.random.default_rng(6)
+    A = rng.standard_normal((1, C, F)).astype(np.float32)
+    z = torch.from_numpy(rng.standard_normal((n, L * C)).astype(np.float32)).cuda()
+    args = (_dev(c["coords"]), _dev(c["grad_out"]), z, c["first_idx"], c["resolutions"], bw, _dev(A), C, F, c["T"], True)
+    gl, gA, gS = lib.latent_backward(*args)
+    chunks = [0x000F, 0x03F0, 0xFC00]
+    gl2, gA2, gS2 = lib.latent_backward(*args, level_chunks=chunks)
+    assert rel_err(gl2.cpu().numpy(), gl.cpu().numpy()) <= 1e-5
+    assert rel_err(gA2.cpu().numpy(), gA.cpu().numpy()) <= 1e-5 and rel_err(gS2.cpu().numpy(), gS.cpu().numpy()) <= 1e-5
+    # one chunk alone leaves every other level's rows at zero
+    gl3, _, gS3 = lib.latent_backward(*args, level_chunks=[0x0030])
+    first = list(c["first_idx"]) + [c["T"]]
+    assert not bool(gl3[:first[4]].any()) and not bool(gl3[first[6]:].any()) and bool(gl3[first[4]:first[6]].any())
+    assert not bool(gS3[:4].any()) and not bool(gS3[6:].any())
