@@ -329,6 +329,15 @@ int shacira_raytrace_dense_fill(const uint8_t* occupancy, int32_t res, const flo
                                 int32_t num_rays, const int64_t* offset, int32_t* ridx, int32_t* pidx, float* depth,
                                 shacira_stream_t stream);
 
+/* Occupancy pruning on the dense grid (NeuralRadianceField.prune, wisp/models/nefs/nerf.py:150-185), cell layout of
+ * shacira_raytrace_dense_*. _samples: one jittered sample per cell, ((cell + jitter) / res) * 2 - 1 (jitter [res^3, 3]
+ * in [0, 1), the reference's torch.rand, injected). _update: occupancy = max(density, occupancy * decay) in place and
+ * mask = occupancy > min_density (uint8, the grid the ray tracer reads). The caller evaluates the density at the
+ * samples in between (its own network). */
+int shacira_prune_samples(int32_t res, const float* jitter, float* samples, shacira_stream_t stream);
+int shacira_prune_update(int64_t cells, const float* density, float decay, float min_density, float* occupancy,
+                         uint8_t* mask, shacira_stream_t stream);
+
 /* ---- latent bitstream (host side) ---------------------------------------------------- */
 /* Static arithmetic coder over dense symbol ranks 0..num_symbols-1 with 16-bit cumulative
  * frequencies cdf[num_symbols+1] (cdf[0] = 0, strictly increasing, cdf[num_symbols] = 65536).

@@ -94,3 +94,21 @@ def raytrace_dense_bruteforce(occupancy, origins, dirs):
         hits = sorted(zip(tn[ok], tf[ok], idx[ok]))
         out.append([(int(c), float(a), float(b)) for a, b, c in hits])
     return out
+
+
+def prune_dense(occupancy, density, jitter, density_decay, min_density):
+    """float32 numpy restatement of NeuralRadianceField.prune on a dense grid (wisp/models/nefs/nerf.py:158-171), cell
+    (x, y, z) at (x*res + y)*res + z, jitter and density injected:
+        occupancy *= decay; samples = ((points + jitter) / res) * 2 - 1; occupancy = max(density, occupancy)
+        mask = occupancy > min_density
+    Returns (samples [res^3, 3], new occupancy [res^3], mask [res^3] bool)."""
+    occ = np.asarray(occupancy, dtype=np.float32).reshape(-1)
+    res = round(occ.shape[0] ** (1.0 / 3.0))
+    g = np.arange(res)
+    pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    samples = pts + np.asarray(jitter, dtype=np.float32)
+    samples = samples / np.float32(res)
+    samples = samples * np.float32(2.0) - np.float32(1.0)
+    occ = occ * np.float32(density_decay)
+    occ = np.maximum(np.asarray(density, dtype=np.float32).reshape(-1), occ)
+    return samples, occ, occ > np.float32(min_density)

@@ -792,6 +792,26 @@ int shacira_raytrace_dense_fill(const uint8_t* occupancy, int32_t res, const flo
     return SHACIRA_OK;
 }
 
+int shacira_prune_samples(int32_t res, const float* jitter, float* samples, shacira_stream_t stream) {
+    if (res < 1 || res > 1024) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "prune_samples: bad res");
+    if (!jitter || !samples) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "prune_samples: NULL argument");
+    const int64_t cells = (int64_t)res * res * res;
+    prune_samples_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(res, jitter, samples);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
+int shacira_prune_update(int64_t cells, const float* density, float decay, float min_density, float* occupancy,
+                         uint8_t* mask, shacira_stream_t stream) {
+    if (cells < 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "prune_update: cells is negative");
+    if (cells == 0) return SHACIRA_OK;
+    if (!density || !occupancy || !mask) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "prune_update: NULL argument");
+    prune_update_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cells, density, decay,
+                                                                                           min_density, occupancy, mask);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
 // ---- latent bitstream (host) ---------------------------------------------------------------
 int64_t shacira_ac_encode(const int16_t* symbols, int64_t n, const uint32_t* cdf, int32_t num_symbols, uint8_t* out,
                           int64_t out_capacity) {

@@ -252,3 +252,35 @@ raytrace_dense_kernel(const uint8_t* __restrict__ occ, int res, const float* __r
 }
 
 }  // namespace shacira
+
+namespace shacira {
+
+// Occupancy pruning on the dense grid (NeuralRadianceField.prune, wisp/models/nefs/nerf.py:150-185): one jittered
+// sample per cell, then occupancy = max(density, occupancy * decay) and the cells above `min_density` stay.
+// Cell e = (x * res + y) * res + z, the layout raytrace_dense_kernel reads.
+//   sample = ((cell + jitter) / res) * 2 - 1                       nerf.py:160-165
+__global__ void __launch_bounds__(256)
+prune_samples_kernel(int res, const float* __restrict__ jitter, float* __restrict__ samples) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t cells = (int64_t)res * res * res;
+    if (e >= cells) return;
+    const int c[3] = {(int)(e / ((int64_t)res * res)), (int)((e / res) % res), (int)(e % res)};
+    const float r = (float)res;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float s = __fdiv_rn(__fadd_rn((float)c[a], __ldg(jitter + e * 3 + a)), r);
+        samples[e * 3 + a] = __fsub_rn(__fmul_rn(s, 2.0f), 1.0f);
+    }
+}
+//   occupancy = max(density, occupancy * decay);  mask = occupancy > min_density        nerf.py:158,169-171
+__global__ void __launch_bounds__(256)
+prune_update_kernel(int64_t cells, const float* __restrict__ density, float decay, float min_density,
+                    float* __restrict__ occupancy, uint8_t* __restrict__ mask) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= cells) return;
+    const float o = fmaxf(__ldg(density + e), __fmul_rn(occupancy[e], decay));
+    occupancy[e] = o;
+    mask[e] = o > min_density ? 1 : 0;
+}
+
+}  // namespace shacira

@@ -142,3 +142,28 @@ def raymarch_voxel(occupancy, origins, dirs, num_samples, jitter=None):
     stratified samples per intersected cell. Returns (ridx, samples, depth_samples, deltas, boundary)."""
     ridx, _, depth = raytrace_dense(occupancy, origins, dirs)
     return voxel_samples(origins, dirs, ridx, depth, num_samples, jitter)
+
+
+def prune_dense(occupancy, density_fn, density_decay, min_density, jitter=None):
+    """`NeuralRadianceField.prune` (nerf.py:150-185) on a dense grid: `occupancy` float [res, res, res] is the running
+    estimate (updated in place: max(density, occupancy * decay)); `density_fn(samples [res^3, 3]) -> [res^3]` is the
+    caller's network evaluated at one jittered sample per cell. Returns the uint8 mask grid [res, res, res] that
+    `raytrace_dense` / `raymarch_voxel` take (unchanged occupancy when nothing would survive, as the reference)."""
+    lib = _lib.load()
+    occ = _lib._f32c(occupancy, "occupancy")
+    if occ.data_ptr() != occupancy.data_ptr():
+        raise _lib.ShaciraError(_lib.ERR_INVALID_ARGUMENT, "occupancy must be contiguous float32 (it is updated in place)")
+    res, dev = occ.shape[0], occ.device
+    cells = res ** 3
+    if jitter is None:
+        jitter = torch.rand((cells, 3), dtype=torch.float32, device=dev)
+    jitter = _lib._f32c(jitter, "jitter")
+    samples = torch.empty((cells, 3), dtype=torch.float32, device=dev)
+    mask = torch.empty((res, res, res), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib._check(lib.shacira_prune_samples(res, _lib._ptr(jitter), _lib._ptr(samples), _lib._stream()))
+        with torch.no_grad():
+            density = _lib._f32c(density_fn(samples).reshape(-1).float(), "density")
+        _lib._check(lib.shacira_prune_update(cells, _lib._ptr(density), float(density_decay), float(min_density),
+                                             _lib._ptr(occ), _lib._ptr(mask), _lib._stream()))
+    return mask

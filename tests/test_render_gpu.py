@@ -139,3 +139,31 @@ def test_dense_raytrace_matches_bruteforce_slab_tests(lib, res, fill):
     if samples.shape[0]:
         ray, w = render.exponential_integration(torch.rand(samples.shape[0], 3, device="cuda"), deltas * 5.0, boundary)
         assert ray.shape[0] == int(boundary.sum()) and bool(torch.isfinite(ray).all())
+
+
+def test_prune_dense_matches_reference_restatement(lib):
+    """NeuralRadianceField.prune on the dense grid (nerf.py:158-171): samples, running occupancy and mask bit-exact
+    against the numpy restatement with the same jitter and densities; the mask drives the ray tracer."""
+    from oracle import render_oracle as ro
+    from shacira_b200 import render
+    res = 16
+    rng = np.random.default_rng(3)
+    occ0 = rng.random(res ** 3).astype(np.float32) * 0.05
+    jitter = rng.random((res ** 3, 3)).astype(np.float32)
+    dens = (rng.random(res ** 3).astype(np.float32) ** 4 * 0.2)
+    occ = torch.from_numpy(occ0.copy()).cuda().reshape(res, res, res)
+    seen = {}
+
+    def density_fn(samples):
+        seen["samples"] = samples.clone()
+        return torch.from_numpy(dens).cuda()
+
+    mask = render.prune_dense(occ, density_fn, 0.6, 0.01, jitter=torch.from_numpy(jitter).cuda())
+    want_s, want_occ, want_mask = ro.prune_dense(occ0, dens, jitter, 0.6, 0.01)
+    assert np.array_equal(seen["samples"].cpu().numpy().view(np.uint32), want_s.view(np.uint32))
+    assert np.array_equal(occ.cpu().numpy().reshape(-1).view(np.uint32), want_occ.view(np.uint32))
+    assert np.array_equal(mask.cpu().numpy().reshape(-1).astype(bool), want_mask) and 0 < int(mask.sum()) < res ** 3
+    o = torch.tensor([[-3.0, 0.1, 0.2]], device="cuda")
+    d = torch.tensor([[1.0, 0.0, 0.0]], device="cuda")
+    ridx, pidx, depth = render.raytrace_dense(mask, o, d)
+    assert bool(mask.reshape(-1)[pidx.long()].all())             # only surviving cells are hit
