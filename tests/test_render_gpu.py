@@ -167,3 +167,25 @@ def test_prune_dense_matches_reference_restatement(lib):
     d = torch.tensor([[1.0, 0.0, 0.0]], device="cuda")
     ridx, pidx, depth = render.raytrace_dense(mask, o, d)
     assert bool(mask.reshape(-1)[pidx.long()].all())             # only surviving cells are hit
+
+
+def test_render_helpers_on_empty_and_missing_inputs(lib):
+    """Rays that miss the grid, zero rays, zero nuggets: empty outputs, no launches on NULL pointers."""
+    from shacira_b200 import render
+    occ = torch.ones((4, 4, 4), dtype=torch.uint8, device="cuda")
+    o = torch.tensor([[5.0, 5.0, 5.0], [0.0, 3.0, 0.0]], device="cuda")
+    d = torch.tensor([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]], device="cuda")       # both point away from the box
+    ridx, pidx, depth = render.raytrace_dense(occ, o, d)
+    assert ridx.numel() == 0 and pidx.numel() == 0 and depth.shape == (0, 2)
+    r2, samples, ds, deltas, boundary = render.raymarch_voxel(occ, o, d, 8)
+    assert samples.shape == (0, 3) and ds.shape == (0, 1) and boundary.numel() == 0
+    ray, w = render.exponential_integration(torch.zeros((0, 3), device="cuda"), torch.zeros((0, 1), device="cuda"),
+                                            torch.zeros((0,), dtype=torch.bool, device="cuda"))
+    assert ray.shape == (0, 3) and w.shape == (0, 1)
+    ridx0, _, _ = render.raytrace_dense(occ, torch.zeros((0, 3), device="cuda"), torch.zeros((0, 3), device="cuda"))
+    assert ridx0.numel() == 0
+    # an empty grid: nothing is hit even by rays through the box
+    none = torch.zeros((4, 4, 4), dtype=torch.uint8, device="cuda")
+    ridx1, _, _ = render.raytrace_dense(none, torch.tensor([[-3.0, 0.1, 0.1]], device="cuda"),
+                                        torch.tensor([[1.0, 0.0, 0.0]], device="cuda"))
+    assert ridx1.numel() == 0
