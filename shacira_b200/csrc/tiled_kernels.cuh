@@ -28,6 +28,9 @@ namespace shacira {
 #endif
 constexpr int kTileThreads = SHACIRA_TILE_THREADS;
 constexpr int kMaxTiles = 4096;
+#ifndef SHACIRA_KP1
+#define SHACIRA_KP1 2   // points per thread in flight in the backward's max pass (F = 1)
+#endif
 #ifndef SHACIRA_KPTS
 #define SHACIRA_KPTS 2
 #endif
@@ -724,7 +727,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
         // group of KP1 points instead of one per level chunk. Per-level running maxima live in shared memory
         // (REDUX over the warp, then one shared atomicMax per warp, level and group).
         {
-            constexpr int KP1 = (F == 1) ? 2 : 1;
+            constexpr int KP1 = (F == 1) ? SHACIRA_KP1 : 1;
             for (int base = b0; base < b1; base += kTileThreads * KP1) {
                 const float* rows[KP1];
 #pragma unroll
