@@ -8,6 +8,10 @@ Differences from the reference, all deliberate:
   * `require_grad_coords` is accepted and ignored: the reference computes grad_coords with
     wrong indices and never returns it (hashgrid_interpolate.cpp:182).
   * all levels run in ONE kernel launch instead of one launch per level.
+  * large 2D batches take the tiled fast path (spatial plan cached per coordinate tensor, shared-memory node staging,
+    fixed-point shared-memory accumulation): a plain table is the latent grid with C = F, identity decoder and no
+    rounding, so the same kernels serve it. Forward values are equal to the point-parallel kernel's (x*1 + y*0
+    is exact); 3D and small batches stay on the point-parallel kernels.
 """
 import torch
 
@@ -30,15 +34,48 @@ def _host_ints(t):
     return got
 
 
+_eye_cache = {}
+
+
+def _identity_decoder(F, device):
+    key = (F, str(device))
+    A = _eye_cache.get(key)
+    if A is None:
+        A = torch.eye(F, dtype=torch.float32, device=device).unsqueeze(0).contiguous()
+        _eye_cache[key] = A
+    return A
+
+
+def _tiled_plan(coords, feature_dim, resolution):
+    """The cached tile plan of `coords` when the tiled kernels cover this call, else None."""
+    if not (isinstance(coords, torch.Tensor) and coords.is_cuda and coords.dtype == torch.float32 and coords.dim() == 2
+            and coords.shape[1] == 2 and coords.is_contiguous()):
+        return None
+    if feature_dim not in (1, 2, 4) or len(resolution) % 4:
+        return None
+    from .. import grid_ops
+    return grid_ops.plan_for(coords)
+
+
 def hashgrid_interpolate_cuda(coords, codebook, codebook_first_idx, resolution, codebook_bitwidth):
-    return _lib.hashgrid_forward(coords, codebook, _host_ints(codebook_first_idx), list(resolution),
-                                 int(codebook_bitwidth))
+    first, res, bw = _host_ints(codebook_first_idx), list(resolution), int(codebook_bitwidth)
+    plan = _tiled_plan(coords, codebook.shape[1] if codebook.dim() == 2 else 0, res)
+    if plan is not None:
+        F = codebook.shape[1]
+        return _lib.latent_forward_planned(plan, codebook, first, res, bw, _identity_decoder(F, codebook.device), None,
+                                           F, False)
+    return _lib.hashgrid_forward(coords, codebook, first, res, bw)
 
 
 def hashgrid_interpolate_backward_cuda(coords, grad_output, codebook, codebook_first_idx, resolution,
                                        codebook_bitwidth, feature_dim, require_grad_coords):
-    return _lib.hashgrid_backward(coords, grad_output, _host_ints(codebook_first_idx), list(resolution),
-                                  int(codebook_bitwidth), int(feature_dim), codebook.shape[0])
+    first, res, bw = _host_ints(codebook_first_idx), list(resolution), int(codebook_bitwidth)
+    F, rows = int(feature_dim), codebook.shape[0]
+    plan = _tiled_plan(coords, F, res)
+    if plan is not None:
+        return _lib.latent_backward_planned(plan, grad_output, None, first, res, bw,
+                                            _identity_decoder(F, grad_output.device), F, F, rows, False, False)[0]
+    return _lib.hashgrid_backward(coords, grad_output, first, res, bw, F, rows)
 
 
 def hashgrid_interpolate2d_cuda(coords, codebook, codebook_first_idx, resolution, codebook_bitwidth):

@@ -71,6 +71,13 @@ _amp_fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
 _amp_bwd = torch.amp.custom_bwd(device_type="cuda")
 
 
+class _ShapeOnly:
+    """Stands in for the codebook in the backward entry point, which only reads its shape (as the reference's does)."""
+
+    def __init__(self, rows, feature_dim):
+        self.shape = (rows, feature_dim)
+
+
 class HashGridInterpolate(torch.autograd.Function):
     """wisp/ops/grid.py:69-111. fp32 compute also under autocast (the reference casts to half)."""
 
@@ -92,9 +99,11 @@ class HashGridInterpolate(torch.autograd.Function):
     def backward(ctx, grad_output):
         coords, first_idx = ctx.saved_tensors
         rows, feature_dim = ctx.table_shape
-        grad_codebook = _lib.hashgrid_backward(coords.float().contiguous(), grad_output.contiguous(),
-                                               _host_ints(first_idx), list(ctx.resolutions), ctx.codebook_bitwidth,
-                                               feature_dim, rows)
+        # through the drop-in entry point: large 2D batches reuse the forward's cached tile plan
+        grad_codebook = _ops.hashgrid_interpolate_backward_cuda(coords.float().contiguous(), grad_output.contiguous(),
+                                                                _ShapeOnly(rows, feature_dim), first_idx,
+                                                                ctx.resolutions, ctx.codebook_bitwidth, feature_dim,
+                                                                False)
         return (None, None, None, None, grad_codebook, None, None)
 
 

@@ -309,3 +309,33 @@ def test_sorted_io_plan_exchanges_rows_in_tile_order(lib):
     assert rel_err(gS_s.cpu().numpy().sum(0), gS.cpu().numpy().sum(0)) <= 1e-5
     plan.close()
     plan2.close()
+
+
+def test_drop_in_entry_points_take_the_tiled_path_for_large_2d_batches(lib):
+    """wisp._C.ops-compatible entry points: a plain table is the latent grid with identity decoder and no rounding,
+    so large 2D batches run on the tiled kernels; values equal the point-parallel kernels', gradients agree."""
+    from shacira_b200 import grid_ops
+    from shacira_b200._C import ops
+    c = _case(2, 16, 16, 16, 512, 70000, 2, 2, seed=12, kind="pixels")
+    coords, g = _dev(c["coords"]), _dev(c["g"])
+    table = _dev(np.random.default_rng(1).standard_normal((c["T"], 2)).astype(np.float32))
+    first = torch.tensor(c["first"], dtype=torch.int32, device="cuda")
+    grid_ops.clear_plans()
+    before = dict(grid_ops.plan_stats)
+    feats = ops.hashgrid_interpolate2d_cuda(coords, table, first, c["res"], 16)
+    assert grid_ops.plan_stats["builds"] == before["builds"] + 1                   # the tiled path ran
+    want = lib.hashgrid_forward(coords, table, c["first"], c["res"], 16)           # point-parallel kernel
+    assert torch.equal(feats, want)
+    gt = ops.hashgrid_interpolate2d_backward_cuda(coords, g, table, first, c["res"], 16, 2, False)
+    assert grid_ops.plan_stats["hits"] >= before["hits"] + 1                        # the forward's plan, reused
+    want_g = lib.hashgrid_backward(coords, g, c["first"], c["res"], 16, 2, c["T"])
+    assert rel_err(gt.cpu().numpy(), want_g.cpu().numpy()) <= BWD_TOL
+    # autograd through the reference-named op
+    t2 = table.clone().requires_grad_(True)
+    out = grid_ops.hashgrid2d(coords, c["res"], 16, 0, t2, None, first)
+    out.backward(g)
+    assert rel_err(t2.grad.cpu().numpy(), want_g.cpu().numpy()) <= BWD_TOL
+    # 3D and small batches stay on the point-parallel kernels
+    builds = grid_ops.plan_stats["builds"]
+    small = ops.hashgrid_interpolate2d_cuda(coords[:1000].contiguous(), table, first, c["res"], 16)
+    assert grid_ops.plan_stats["builds"] == builds and torch.equal(small, want[:1000])
