@@ -94,6 +94,15 @@ inline int coarse_max_slabs() {
     }
     return v;
 }
+// cudaFuncSetAttribute is per DEVICE: remember which devices a kernel has been configured on (bit per ordinal),
+// so a process that drives several GPUs configures each of them.
+inline bool needs_config(unsigned long long& done_mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    if ((done_mask >> dev) & 1ull) return false;
+    done_mask |= 1ull << dev;
+    return true;
+}
 inline int sm_count() {
     static int sms = 0;
     if (!sms) {
@@ -139,12 +148,10 @@ int launch_coarse_bwd(const float* coords, int64_t n, const float* g, const Leve
     const uint32_t m = plan_coarse_jobs(D, lp, NV, n, sm_count(), coarse_max_slabs(), jobs, level_mask);
     if (!m) return SHACIRA_OK;
     const size_t smem = coarse_smem_bytes(jobs, NV);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static unsigned long long configured = 0ull;
+    if (needs_config(configured))
         CUDA_OK(cudaFuncSetAttribute(coarse_bwd_kernel<D, C, F, LATENT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(sizeof(float) * kCoarseBudgetFloats)));
-        configured = sizeof(float) * kCoarseBudgetFloats;
-    }
     // The coarse kernel is bound by shared-memory CAS, the point-parallel kernel by L2 atomics: fork a side stream so
     // that both run at once (one coarse CTA per SM is placed first, the other kernel fills the rest of the SM).
     // Event fork/join composes with stream capture (the side stream joins the caller's capture).
@@ -231,12 +238,10 @@ namespace {
 // them); the copies are stream ordered and capturable.
 int launch_mlp16(const float* x, const float* gt, int64_t n, const float* W1, const float* b1, const float* W2,
                  const float* b2, const float* W3, const float* b3, float* gx, float* pred, void* out, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0ull;
+    if (needs_config(configured))
         CUDA_OK(cudaFuncSetAttribute(mlp16_mse_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(Mlp16Smem)));
-        configured = true;
-    }
     const float* src[6] = {W1, b1, W2, b2, W3, b3};
     const size_t cnt[6] = {256, 16, 256, 16, 48, 3};
     bool packed = true;
@@ -270,12 +275,10 @@ int launch_mlp_tc_cfg(const float* x, const float* gt, int64_t n, const float* W
                       const float* b2, const float* W3, const float* b3, float* gx, float* pred, void* out, float* absmax,
                       cudaStream_t s) {
     using Smem = MlpTcSmem<MT, WARPS>;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0ull;
+    if (needs_config(configured))
         CUDA_OK(cudaFuncSetAttribute(mlp16_tc_step_kernel<MT, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(Smem)));
-        configured = true;
-    }
     const size_t out_bytes = 8 + sizeof(float) * kMlpConstFloats;
     if (absmax && (char*)absmax == (char*)out + out_bytes) {   // caller keeps the bound behind `out`: one memset node
         CUDA_OK(cudaMemsetAsync(out, 0, out_bytes + sizeof(float) * 16, s));
@@ -309,12 +312,10 @@ template <int IN>
 int launch_mlp(const float* x, const float* gt, int64_t n, const float* W1, const float* b1, const float* W2,
                const float* b2, const float* W3, const float* b3, float* gx, float* pred, void* out, cudaStream_t s) {
     using Smem = MlpSmem<IN, 16, 3>;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0ull;
+    if (needs_config(configured))
         CUDA_OK(cudaFuncSetAttribute(mlp_mse_step_kernel<IN, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(Smem)));
-        configured = true;
-    }
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t out_bytes = 8 + sizeof(float) * (16 * IN + 16 + 16 * 16 + 16 + 3 * 16 + 3);
