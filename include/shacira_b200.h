@@ -176,6 +176,24 @@ int shacira_latent_backward_planned_bounded(const shacira_plan_t* plan, const fl
                                             int64_t table_rows, int32_t zero_first, float* grad_latents, float* grad_A,
                                             float* grad_shift, const float* level_max, shacira_stream_t stream);
 
+/* 3D plans (NeRF samples, new coordinates every step: shacira_plan_rebuild per step). The planned 3D kernels run one
+ * thread per sample over the plan's tile-sorted samples -- neighbouring lanes share the cache lines of the coarse
+ * and middle levels -- fetch the two x-neighbour corners of a cell with ONE aligned 16-byte load (forward) / add to
+ * them with ONE vector red (backward), and accumulate the coarse levels per tile in shared memory (fixed point) on a
+ * forked stream. `zsave` [n, L*C] is scratch private to this pair of calls (rows in the plan's sorted order): the
+ * forward writes the interpolated latents, the backward reads them for grad_A. Other arguments as
+ * shacira_latent_forward / shacira_latent_backward. latent_dim in {1, 2}; tables 16-byte aligned. */
+int shacira_latent_forward_planned_z(const shacira_plan_t* plan, const float* latents, const int32_t* first_idx,
+                                     const int32_t* resolutions, int32_t num_lods, int32_t codebook_bitwidth,
+                                     int32_t latent_dim, int32_t feature_dim, int32_t round_flag, const float* A,
+                                     const float* shift, int32_t per_level, float* feats, float* zsave,
+                                     shacira_stream_t stream);
+int shacira_latent_backward_planned_z(const shacira_plan_t* plan, const float* grad_output, const float* zsave,
+                                      const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                                      int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim, const float* A,
+                                      int32_t per_level, int64_t table_rows, int32_t zero_first, float* grad_latents,
+                                      float* grad_A, float* grad_shift, shacira_stream_t stream);
+
 /* ---- factorized-density bit-rate estimate -------------------------------------------- */
 /* LatentGrid.ent_loss (latent_grid.py:122-136) + BitEstimator/Bitparm
  * (wisp/models/prob_models/bit_estimator.py:9-65), forward and backward in one pass:

@@ -58,6 +58,8 @@ SIGNATURES = {
     "shacira_latent_forward_planned": (ctypes.c_int, [_vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "shacira_latent_backward_planned": (ctypes.c_int, [_vp, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "shacira_latent_backward_planned_bounded": (ctypes.c_int, [_vp, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "shacira_latent_forward_planned_z": (ctypes.c_int, [_vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "shacira_latent_backward_planned_z": (ctypes.c_int, [_vp, _vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "shacira_entropy_bits": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _c_int32_p, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "shacira_entropy_bits_rng": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp, _i64, _i32, _vp, _i32, _c_int32_p, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "shacira_entropy_scratch_bytes": (_i64, [_i32, _i32]),
@@ -392,6 +394,57 @@ def latent_backward_planned(plan, grad_output, latents, first_idx, resolutions, 
             plan.handle, _ptr(grad_output), _ptr(latents), fi, rs, L, bitwidth, latent_dim, feature_dim,
             1 if round_flag else 0, _ptr(A), per_level, table_rows, 1, _ptr(gl), _ptr(gA), _ptr(gS),
             _ptr(_f32c(level_max, "level_max") if level_max is not None else None), _stream()))
+    return gl, gA, gS
+
+
+def latent_forward_planned_z(plan, latents, first_idx, resolutions, bitwidth, A, shift, feature_dim, round_flag,
+                             save_z, feats=None, z=None):
+    """3D plans: feats [n, L*F] (original order unless the plan is in sorted-I/O mode) and, with save_z, the
+    interpolated latents z [n, L*C] in the plan's sorted order (scratch for latent_backward_planned_z)."""
+    lib = load()
+    latents = _f32c(latents, "latents")
+    A = _f32c(A, "A")
+    shift = _f32c(shift, "shift") if shift is not None else None
+    fi, L = _i32_array(first_idx)
+    rs, _ = _i32_array(resolutions)
+    C = latents.shape[1]
+    per_level = 1 if A.shape[0] == L and L > 1 else 0
+    if A.shape[0] not in (1, L) or tuple(A.shape[1:]) != (C, feature_dim):
+        raise ShaciraError(ERR_INVALID_ARGUMENT, "A must be [1|L, C, F], got %s" % (tuple(A.shape),))
+    if feats is None:
+        feats = torch.empty((plan.n, L * feature_dim), dtype=torch.float32, device=plan.device)
+    if save_z and z is None:
+        z = torch.empty((plan.n, L * C), dtype=torch.float32, device=plan.device)
+    with torch.cuda.device(plan.device):
+        _check(lib.shacira_latent_forward_planned_z(plan.handle, _ptr(latents), fi, rs, L, bitwidth, C, feature_dim,
+                                                    1 if round_flag else 0, _ptr(A), _ptr(shift), per_level,
+                                                    _ptr(feats), _ptr(z if save_z else None), _stream()))
+    return feats, (z if save_z else None)
+
+
+def latent_backward_planned_z(plan, grad_output, z, first_idx, resolutions, bitwidth, A, latent_dim, feature_dim,
+                              table_rows, want_decoder_grads, out=None):
+    """3D plans: (grad_latents[T, C], grad_A[L, C, F] | None, grad_shift[L, F] | None); `z` from the planned forward.
+    `out`: accumulate into an existing (zeroed by the caller) grad_latents buffer instead of allocating one."""
+    lib = load()
+    grad_output = _f32c(grad_output, "grad_output")
+    A = _f32c(A, "A")
+    fi, L = _i32_array(first_idx)
+    rs, _ = _i32_array(resolutions)
+    per_level = 1 if A.shape[0] == L and L > 1 else 0
+    dev = plan.device
+    if tuple(grad_output.shape) != (plan.n, L * feature_dim):
+        raise ShaciraError(ERR_INVALID_ARGUMENT, "grad_output must be [n, L*F], got %s" % (tuple(grad_output.shape),))
+    gl = out if out is not None else torch.empty((table_rows, latent_dim), dtype=torch.float32, device=dev)
+    gA = gS = None
+    if want_decoder_grads:
+        gA = torch.zeros((L, latent_dim, feature_dim), dtype=torch.float32, device=dev)
+        gS = torch.zeros((L, feature_dim), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.shacira_latent_backward_planned_z(plan.handle, _ptr(grad_output), _ptr(z), fi, rs, L, bitwidth,
+                                                     latent_dim, feature_dim, _ptr(A), per_level, table_rows,
+                                                     0 if out is not None else 1, _ptr(gl), _ptr(gA), _ptr(gS),
+                                                     _stream()))
     return gl, gA, gS
 
 

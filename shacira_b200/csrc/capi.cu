@@ -103,37 +103,10 @@ inline bool needs_config(unsigned long long& done_mask) {
     done_mask |= 1ull << dev;
     return true;
 }
-inline int sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-            sms = 148;
-    }
-    return sms;
-}
-struct SideStream {
-    int dev = -1;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-    int ensure() {
-        int d = 0;
-        CUDA_OK(cudaGetDevice(&d));
-        if (d == dev) return SHACIRA_OK;
-        CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-        CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-        dev = d;
-        return SHACIRA_OK;
-    }
-};
-inline SideStream& side_stream() {
-    thread_local SideStream ss;
-    return ss;
-}
-inline int join_side_stream(cudaStream_t s) {
-    CUDA_OK(cudaStreamWaitEvent(s, side_stream().join, 0));
+inline int join_side(cudaStream_t s) {
+    SideStream* ss = nullptr;
+    if (int rc = side_stream(&ss)) return rc;
+    CUDA_OK(cudaStreamWaitEvent(s, ss->join, 0));
     return SHACIRA_OK;
 }
 template <int D, int C, int F, bool LATENT>
@@ -163,8 +136,9 @@ int launch_coarse_bwd(const float* coords, int64_t n, const float* g, const Leve
         mask = m;
         return SHACIRA_OK;
     }
-    SideStream& ss = side_stream();
-    if (int rc = ss.ensure()) return rc;
+    SideStream* ssp = nullptr;
+    if (int rc = side_stream(&ssp)) return rc;
+    SideStream& ss = *ssp;
     CUDA_OK(cudaEventRecord(ss.fork, s));
     CUDA_OK(cudaStreamWaitEvent(ss.stream, ss.fork, 0));
     coarse_bwd_kernel<D, C, F, LATENT><<<coarse_total_ctas(jobs), kCoarseThreads, smem, ss.stream>>>(
@@ -184,12 +158,14 @@ int launch_plain_bwd(const float* coords, int64_t n, const float* g, const Level
     if (rc) return rc;
     hashgrid_bwd_kernel<D, F><<<grid_for(n, kBlock), kBlock, 0, s>>>(coords, n, g, lp, skip, gt);
     LAUNCHED();
-    return join ? join_side_stream(s) : SHACIRA_OK;
+    return join ? join_side(s) : SHACIRA_OK;
 }
 template <int D, int C, int F>
 int launch_latent_fwd(const float* coords, int64_t n, const float* lat, const LevelParams& lp, const float* A,
                       const float* shift, int per_level, int round_flag, float* feats, float* zsave,
                       cudaStream_t s) {
+    if (D == 3 && grid3d_merge_mode() > 0 && grid3d_supported(C, F, lat))   // merged x-pair loads (grid3d_kernels.cuh)
+        return launch_fwd3d(C, F, coords, nullptr, n, lat, lp, A, shift, per_level, round_flag, feats, zsave, s);
     const int nA = per_level ? lp.num_lods : 1;
     const size_t smem = sizeof(float) * (size_t)(nA * C * F + nA * F);
     latent_fwd_kernel<D, C, F><<<grid_for(n, kBlock), kBlock, smem, s>>>(coords, n, lat, lp, A, shift, per_level,
@@ -207,10 +183,16 @@ int launch_latent_bwd(const float* coords, int64_t n, const float* g, const floa
     bool join = false;
     int rc = launch_coarse_bwd<D, C, F, true>(coords, n, g, lp, A, per_level, gl, s, skip, join, level_mask);
     if (rc) return rc;
+    if (D == 3 && grid3d_red_mode() >= 0 && grid3d_supported(C, F, gl)) {   // vector reds per x-pair (grid3d_kernels.cuh)
+        rc = launch_bwd3d(C, F, coords, nullptr, n, g, zsave, lp, A, per_level, skip, level_mask, grid3d_red_mode(), gl,
+                          gA, gS, s);
+        if (rc) return rc;
+        return join ? join_side(s) : SHACIRA_OK;
+    }
     latent_bwd_kernel<D, C, F><<<grid_for(n, kBlock), kBlock, smem, s>>>(coords, n, g, zsave, lp, A, per_level, skip,
                                                                           level_mask, gl, gA, gS);
     LAUNCHED();
-    return join ? join_side_stream(s) : SHACIRA_OK;
+    return join ? join_side(s) : SHACIRA_OK;
 }
 
 #define DISPATCH_F(D_, F_, CALL)                                                                   \
@@ -316,8 +298,7 @@ int launch_mlp(const float* x, const float* gt, int64_t n, const float* W1, cons
     if (needs_config(configured))
         CUDA_OK(cudaFuncSetAttribute(mlp_mse_step_kernel<IN, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(Smem)));
-    int sms = 148, dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     const size_t out_bytes = 8 + sizeof(float) * (16 * IN + 16 + 16 * 16 + 16 + 3 * 16 + 3);
     CUDA_OK(cudaMemsetAsync(out, 0, out_bytes, s));
     int64_t warps = (n + 31) / 32;
@@ -508,9 +489,7 @@ static int entropy_bits_impl(const float* latents, const float* noise, int64_t t
     lb.num_lods = num_lods;
     for (int l = 0; l < num_lods; ++l) lb.first[l] = first_idx[l];
     lb.first[num_lods] = (int32_t)table_rows;
-    int sms = 148;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     int64_t blocks = (total + kEntBlock - 1) / kEntBlock;
     static const int per_sm = [] { const char* e = getenv("SHACIRA_ENT_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
     const int64_t cap = (int64_t)sms * per_sm;  // per-block prologue/epilogue (~500 instructions) vs parallelism: tuned on B200
@@ -556,9 +535,7 @@ int shacira_entropy_bits_rng(const float* latents, uint64_t seed, uint64_t* rng_
 }
 
 int64_t shacira_entropy_scratch_bytes(int32_t latent_dim, int32_t num_lods) {
-    int sms = 148, dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t blocks = (int64_t)sms * 8;  // upper bound of the launch grid
+    const int64_t blocks = (int64_t)sm_count() * 8;  // upper bound of the launch grid
     const int64_t P = 1 + num_lods + 12 * (int64_t)latent_dim;
     return ((4 * blocks * P + 255) & ~(int64_t)255) + 256;
 }

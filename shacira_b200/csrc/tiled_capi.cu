@@ -59,6 +59,7 @@ PlanView view_of(const shacira_plan* p) {
 }
 
 int node_capacity(const shacira_plan* p, const LevelParams& lp, int cap_max);
+inline bool num_lods_ok(const LevelParams& lp) { return lp.num_lods % 4 == 0; }
 
 // The node table depends on the tile grid and the level configuration only. It is (re)built when either
 // changes -- once per fit -- with the largest node capacity any kernel uses, so that every kernel's staged
@@ -139,11 +140,90 @@ int launch_bwd(shacira_plan* p, const float* g, const float* lat, const LevelPar
     smem = smem_pad(smem);
     if (dec)
         latent_bwd_tiled_kernel<D, C, F, true><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), g, lat, lp, A, per_level,
-                                                                                      round_flag, gl, gA, gS, cap, cap_acc, level_max);
+                                                                                      round_flag, gl, gA, gS, cap, cap_acc, level_max, SHACIRA_MAX_LEVELS, 0);
     else
         latent_bwd_tiled_kernel<D, C, F, false><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), g, lat, lp, A, per_level,
-                                                                                       round_flag, gl, gA, gS, cap, cap_acc, level_max);
+                                                                                       round_flag, gl, gA, gS, cap, cap_acc, level_max, SHACIRA_MAX_LEVELS, 0);
     LAUNCHED();
+    return SHACIRA_OK;
+}
+
+// ---- 3D (NeRF samples): sorted point-parallel kernels with merged x-pair accesses + tile-staged coarse levels ------
+// Number of leading levels the tiled backward stages in shared memory for this plan: while the (upper bound of the)
+// node box of a tile stays below the corner touches of an average tile (otherwise staging only adds a flush) and
+// the boxes fit the shared-memory budget. SHACIRA_3D_STAGED overrides (0 = none).
+int staged_prefix_3d(const shacira_plan* p, const LevelParams& lp, int cap_max, int* cap_out) {
+    const char* env = getenv("SHACIRA_3D_STAGED");
+    const int forced = env ? atoi(env) : -1;
+    const double touches = 8.0 * (double)p->n / (double)p->ntiles;
+    long long run = 0;
+    int ns = 0;
+    for (int l = 0; l < lp.num_lods; ++l) {
+        const long long w = lp.res[l] / p->g + 3, nodes = w * w * w;
+        if (run + nodes > cap_max) break;
+        if (forced >= 0 ? l >= forced : (double)nodes > touches) break;
+        run += nodes;
+        ++ns;
+    }
+    if (run < 32) run = 32;
+    *cap_out = (int)((run + 3) & ~3LL);
+    return ns;
+}
+
+template <int C, int F>
+int launch_bwd_staged3d(shacira_plan* p, const float* g, const LevelParams& lp, const float* A, int per_level, float* gl,
+                        int ns, int cap, cudaStream_t s) {
+    const int nA = per_level ? lp.num_lods : 1;
+    const int rep = (kRepBudget / C) & ~3;
+    const int cap_acc = cap + rep;
+    const size_t smem = sizeof(float) * ((size_t)cap_acc * C + nA * C * F);
+    PlanView v = view_of(p);
+    v.node_tab = nullptr;   // rows from the tile geometry at flush time (a 3D node table would be tens of MB)
+    v.node_stride = 0;
+    latent_bwd_tiled_kernel<3, C, F, false><<<p->ntiles, kTileThreads, smem, s>>>(
+        v, g, nullptr, lp, A, per_level, 0, gl, nullptr, nullptr, cap, cap_acc, nullptr, ns, 1);
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
+int backward_3d(shacira_plan* p, const float* g, const float* zsave, const LevelParams& lp, int C, int F, const float* A,
+                int per_level, float* gl, float* gA, float* gS, cudaStream_t s) {
+    int cap = 32;
+    const int budget = smem_budget();
+    const int rep = (kRepBudget / C) & ~3;
+    const int ns = (num_lods_ok(lp) && grid3d_red_mode() >= 0) ? staged_prefix_3d(p, lp, (budget - rep * 4 * C) / (4 * C), &cap) : 0;
+    bool forked = false;
+    SideStream* ss = nullptr;
+    if (ns > 0) {
+        if (int rc = side_stream(&ss)) return rc;
+        CUDA_OK(cudaEventRecord(ss->fork, s));
+        CUDA_OK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+        int rc = SHACIRA_OK;
+        if (C == 1) {
+            switch (F) {
+                case 1: rc = launch_bwd_staged3d<1, 1>(p, g, lp, A, per_level, gl, ns, cap, ss->stream); break;
+                case 2: rc = launch_bwd_staged3d<1, 2>(p, g, lp, A, per_level, gl, ns, cap, ss->stream); break;
+                case 4: rc = launch_bwd_staged3d<1, 4>(p, g, lp, A, per_level, gl, ns, cap, ss->stream); break;
+                default: rc = launch_bwd_staged3d<1, 8>(p, g, lp, A, per_level, gl, ns, cap, ss->stream); break;
+            }
+        } else {
+            switch (F) {
+                case 1: rc = launch_bwd_staged3d<2, 1>(p, g, lp, A, per_level, gl, ns, cap, ss->stream); break;
+                case 2: rc = launch_bwd_staged3d<2, 2>(p, g, lp, A, per_level, gl, ns, cap, ss->stream); break;
+                case 4: rc = launch_bwd_staged3d<2, 4>(p, g, lp, A, per_level, gl, ns, cap, ss->stream); break;
+                default: rc = launch_bwd_staged3d<2, 8>(p, g, lp, A, per_level, gl, ns, cap, ss->stream); break;
+            }
+        }
+        if (rc) return rc;
+        CUDA_OK(cudaEventRecord(ss->join, ss->stream));
+        forked = true;
+    }
+    const uint32_t skip = ns >= 32 ? 0xffffffffu : ((1u << ns) - 1u);
+    const int red_w = grid3d_red_mode() < 0 ? 0 : grid3d_red_mode();
+    int rc = launch_bwd3d(C, F, p->coords_sorted, p->sorted_io ? nullptr : p->perm, p->n, g, zsave, lp, A, per_level, skip,
+                          0xffffffffu, red_w, gl, gA, gS, s);
+    if (rc) return rc;
+    if (forked) CUDA_OK(cudaStreamWaitEvent(s, ss->join, 0));
     return SHACIRA_OK;
 }
 
@@ -316,8 +396,11 @@ int shacira_latent_forward_planned(const shacira_plan_t* plan, const float* late
     int rc = build_levels(plan->dim, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
     if (rc) return rc;
     if (!latents || !feats || !A) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "latents/feats/A is NULL");
-    if (num_lods % 4) return fail(SHACIRA_ERR_UNSUPPORTED, "the tiled path needs num_lods %% 4 == 0 (got %d)", num_lods);
     cudaStream_t s = (cudaStream_t)stream;
+    if (plan->dim == 3 && grid3d_merge_mode() > 0 && grid3d_supported(latent_dim, feature_dim, latents))
+        return launch_fwd3d(latent_dim, feature_dim, plan->coords_sorted, plan->sorted_io ? nullptr : plan->perm, plan->n,
+                            latents, lp, A, shift, per_level, round_flag, feats, nullptr, s);
+    if (num_lods % 4) return fail(SHACIRA_ERR_UNSUPPORTED, "the tiled path needs num_lods %% 4 == 0 (got %d)", num_lods);
     if (plan->dim == 2) {
         T_DISPATCH_CF(latent_dim, feature_dim,
                       (launch_fwd<2, kC, kF>(const_cast<shacira_plan*>(plan), latents, lp, A, shift, per_level, round_flag, feats, s)))
@@ -341,8 +424,14 @@ int shacira_latent_backward_planned_bounded(const shacira_plan_t* plan, const fl
         return fail(SHACIRA_ERR_INVALID_ARGUMENT, "decoder gradients need the latents (the interpolation is recomputed)");
     if (latent_dim != 1 && latent_dim != 2 && latent_dim != 4)
         return fail(SHACIRA_ERR_UNSUPPORTED, "latent_dim %d not in {1,2,4}", latent_dim);
-    if (num_lods % 4) return fail(SHACIRA_ERR_UNSUPPORTED, "the tiled path needs num_lods %% 4 == 0 (got %d)", num_lods);
     cudaStream_t s = (cudaStream_t)stream;
+    if (plan->dim == 3 && !grad_A && !grad_shift && grid3d_red_mode() >= 0 &&
+        grid3d_supported(latent_dim, feature_dim, grad_latents)) {
+        if (zero_first) CUDA_OK(cudaMemsetAsync(grad_latents, 0, sizeof(float) * (size_t)table_rows * latent_dim, s));
+        return backward_3d(const_cast<shacira_plan*>(plan), grad_output, nullptr, lp, latent_dim, feature_dim, A, per_level,
+                           grad_latents, nullptr, nullptr, s);
+    }
+    if (num_lods % 4) return fail(SHACIRA_ERR_UNSUPPORTED, "the tiled path needs num_lods %% 4 == 0 (got %d)", num_lods);
     if (zero_first) CUDA_OK(cudaMemsetAsync(grad_latents, 0, sizeof(float) * (size_t)table_rows * latent_dim, s));
     if (plan->dim == 2) {
         T_DISPATCH_CF(latent_dim, feature_dim,
@@ -354,6 +443,47 @@ int shacira_latent_backward_planned_bounded(const shacira_plan_t* plan, const fl
                                          grad_shift, level_max, s)))
 }
 
+
+int shacira_latent_forward_planned_z(const shacira_plan_t* plan, const float* latents, const int32_t* first_idx,
+                                     const int32_t* resolutions, int32_t num_lods, int32_t codebook_bitwidth,
+                                     int32_t latent_dim, int32_t feature_dim, int32_t round_flag, const float* A,
+                                     const float* shift, int32_t per_level, float* feats, float* zsave,
+                                     shacira_stream_t stream) {
+    if (!plan) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (plan->dim != 3) return fail(SHACIRA_ERR_UNSUPPORTED, "forward_planned_z: 3D plans only (2D recomputes z on chip)");
+    LevelParams lp;
+    int rc = build_levels(plan->dim, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
+    if (rc) return rc;
+    if (!latents || !feats || !A) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "latents/feats/A is NULL");
+    if (!grid3d_supported(latent_dim, feature_dim, latents))
+        return fail(SHACIRA_ERR_UNSUPPORTED, "forward_planned_z: latent_dim %d / feature_dim %d / table alignment", latent_dim, feature_dim);
+    return launch_fwd3d(latent_dim, feature_dim, plan->coords_sorted, plan->sorted_io ? nullptr : plan->perm, plan->n,
+                        latents, lp, A, shift, per_level, round_flag, feats, zsave, (cudaStream_t)stream);
+}
+
+int shacira_latent_backward_planned_z(const shacira_plan_t* plan, const float* grad_output, const float* zsave,
+                                      const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
+                                      int32_t codebook_bitwidth, int32_t latent_dim, int32_t feature_dim, const float* A,
+                                      int32_t per_level, int64_t table_rows, int32_t zero_first, float* grad_latents,
+                                      float* grad_A, float* grad_shift, shacira_stream_t stream) {
+    if (!plan) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (plan->dim != 3) return fail(SHACIRA_ERR_UNSUPPORTED, "backward_planned_z: 3D plans only");
+    LevelParams lp;
+    int rc = build_levels(plan->dim, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
+    if (rc) return rc;
+    if (!grad_latents || !A || !grad_output) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "grad_latents/A/grad_output is NULL");
+    if (grad_A && !zsave) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "grad_A requested without zsave");
+    if (!grid3d_supported(latent_dim, feature_dim, grad_latents))
+        return fail(SHACIRA_ERR_UNSUPPORTED, "backward_planned_z: latent_dim %d / feature_dim %d / table alignment", latent_dim, feature_dim);
+    for (int l = 0; l < num_lods; ++l)
+        if ((int64_t)lp.first[l] + lp.rows[l] > table_rows)
+            return fail(SHACIRA_ERR_INVALID_ARGUMENT, "level %d ends at row %lld, past table_rows %lld", l,
+                        (long long)lp.first[l] + lp.rows[l], (long long)table_rows);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (zero_first) CUDA_OK(cudaMemsetAsync(grad_latents, 0, sizeof(float) * (size_t)table_rows * latent_dim, s));
+    return backward_3d(const_cast<shacira_plan*>(plan), grad_output, zsave, lp, latent_dim, feature_dim, A, per_level,
+                       grad_latents, grad_A, grad_shift, s);
+}
 
 int shacira_latent_backward_planned(const shacira_plan_t* plan, const float* grad_output, const float* latents,
                                     const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,

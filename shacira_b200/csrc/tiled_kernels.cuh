@@ -171,7 +171,8 @@ constexpr int kRepBudget = SHACIRA_REP_BUDGET;  // ints of lane-replicated accum
 // use the direct path.
 template <int D>
 __device__ __forceinline__ void tile_geometry(TileGeom<D>& tg, const LevelParams& lp, const int (&ti)[D], int g,
-                                              int cap, int cap_acc = 0x3fffffff, int rep_budget = 0) {
+                                              int cap, int cap_acc = 0x3fffffff, int rep_budget = 0,
+                                              int max_staged = SHACIRA_MAX_LEVELS) {
     if (threadIdx.x < 32) {
         const int l = threadIdx.x;
         const double inv_g = 1.0 / (double)g;  // g is a power of two: exact
@@ -210,7 +211,7 @@ __device__ __forceinline__ void tile_geometry(TileGeom<D>& tg, const LevelParams
             const int v = __shfl_up_sync(0xffffffffu, acc_incl, o);
             if (l >= o) acc_incl = min(acc_incl + v, 0x3fffffff);
         }
-        const bool fits = (l < lp.num_lods) && incl <= cap && acc_incl <= cap_acc;
+        const bool fits = (l < lp.num_lods) && l < max_staged && incl <= cap && acc_incl <= cap_acc;
         const unsigned fit_mask = __ballot_sync(0xffffffffu, fits);
         // staged = the leading run of levels that fit
         const unsigned all = (lp.num_lods >= 32) ? 0xffffffffu : ((1u << lp.num_lods) - 1u);
@@ -653,7 +654,10 @@ __global__ void __launch_bounds__(kTileThreads, (C * F <= 4) ? SHACIRA_MIN_CTAS 
 latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, const float* __restrict__ latents,
                         const __grid_constant__ LevelParams lp, const float* __restrict__ A, int per_level,
                         int round_flag, float* __restrict__ grad_latents, float* __restrict__ grad_A,
-                        float* __restrict__ grad_shift, int cap, int cap_acc, const float* __restrict__ level_max) {
+                        float* __restrict__ grad_shift, int cap, int cap_acc, const float* __restrict__ level_max,
+                        int max_staged, int skip_direct) {
+    // max_staged / skip_direct (3D): stage exactly the first max_staged levels (the host sized `cap` for them) and leave
+    // every other level to the point-parallel kernel that runs beside this one (latent_bwd3d_kernel, skip_mask).
     constexpr bool SG = DEC && (F <= C);
     constexpr bool ZP = DEC && !SG;          // per-point z recomputation
     constexpr int CA = SG ? F : C;           // accumulator channels
@@ -684,8 +688,10 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
     for (int e = threadIdx.x; e < nA * C * F; e += kTileThreads) s_A[e] = A[e];
     if (DEC)
         for (int e = threadIdx.x; e < (ZP ? NW : 1) * L * (C * F + F); e += kTileThreads) s_gA[e] = 0.0f;
-    tile_geometry<D>(tg, lp, ti, pv.g, cap, cap_acc, cap_acc - cap);
+    tile_geometry<D>(tg, lp, ti, pv.g, cap, cap_acc, cap_acc - cap, max_staged);
     bool staged_lat = false;
+    // levels this launch touches: all of them, or the staged prefix rounded up to the level blocking
+    const int Lrun = skip_direct ? min(L, ((__popc(tg.staged) + kLv - 1) / kLv) * kLv) : L;
 
     for (int b0 = beg; b0 < end; b0 += kBatch) {
         const int b1 = min(end, b0 + kBatch);
@@ -735,7 +741,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                     const int j = base + k * kTileThreads + threadIdx.x;
                     rows[k] = (j < b1) ? grad_out + (int64_t)(pv.perm ? __ldg(pv.perm + j) : j) * L * F : nullptr;
                 }
-                for (int l0 = 0; l0 < L; l0 += 8) {  // 8 levels = two 16-byte vectors per point in flight
+                for (int l0 = 0; l0 < Lrun; l0 += 8) {  // 8 levels = two 16-byte vectors per point in flight
                     float g[KP1][2][4 * F];
 #pragma unroll
                     for (int k = 0; k < KP1; ++k)
@@ -743,7 +749,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                         for (int h = 0; h < 2; ++h) {
 #pragma unroll
                             for (int e = 0; e < 4 * F; ++e) g[k][h][e] = 0.0f;
-                            if (rows[k] && l0 + 4 * h < L) load_row<4 * F>(rows[k] + (l0 + 4 * h) * F, g[k][h]);
+                            if (rows[k] && l0 + 4 * h < Lrun) load_row<4 * F>(rows[k] + (l0 + 4 * h) * F, g[k][h]);
                         }
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
@@ -788,7 +794,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
         }
         __syncthreads();
         // pass 2: accumulate
-        for (int l0 = 0; l0 < L; l0 += kLv) {
+        for (int l0 = 0; l0 < Lrun; l0 += kLv) {
             float accS[ZP ? kLv * F : 1], accA[ZP ? kLv * C * F : 1];
             if (ZP) {
 #pragma unroll
@@ -881,6 +887,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
 #pragma unroll
                     for (int q = 0; q < kLv; ++q) {
                         const int l = l0 + q;
+                        if (skip_direct && !lr[q].staged) continue;
                         float gz[CA], z[C];
 #pragma unroll
                         for (int ch = 0; ch < C; ++ch) z[ch] = 0.0f;
@@ -997,7 +1004,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
         for (int e = 0; e < (SG ? C * F : 1); ++e) pA[e] = 0.0f;
         const int num_staged = __popc(tg.staged);
         const int total_nodes = tg.total;
-        const int2* tab = pv.node_tab + (size_t)tile * pv.node_stride;
+        const int2* tab = pv.node_tab ? pv.node_tab + (size_t)tile * pv.node_stride : nullptr;
         // One thread per node over ALL staged levels at once (flat slot index; level and table row come from the
         // plan's node table): full lanes on the small coarse levels, no per-node index math. With per-level
         // decoders in scatter-g mode the partial sums must be kept per level, so that (rare) case walks level by level.
@@ -1006,7 +1013,14 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
             const int e_begin = by_level ? tg.off[lvl] : 0;
             const int e_end = by_level ? ((lvl + 1 < num_staged) ? tg.off[lvl + 1] : total_nodes) : total_nodes;
             for (int e = e_begin + threadIdx.x; e < e_end; e += kTileThreads) {
-                const int2 ent = __ldg(&tab[e]);
+                int2 ent;
+                if (pv.node_tab) {
+                    ent = __ldg(&tab[e]);
+                } else {   // no node table (3D: it would be tens of MB): level and table row from the tile geometry
+                    const int le = level_of_slot<D>(tg, num_staged, e);
+                    const int r = node_row<D>(tg, lp, le, e - tg.off[le], false);
+                    ent = make_int2(lp.first[le] + max(r, 0), le | (r >= 0 ? 0 : kNodeInvalid));
+                }
                 const int l = ent.y & 0xff;
                 const int nloc = e - tg.off[l];
                 const float inv = s_inv[l];
