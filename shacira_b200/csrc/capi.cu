@@ -38,8 +38,8 @@ int build_levels(int32_t dim, const int32_t* first_idx, const int32_t* resolutio
     int64_t running = 0;
     for (int l = 0; l < num_lods; ++l) {
         const int64_t r = resolutions[l];
-        if (r < 2 || r > (1 << 24))
-            return fail(SHACIRA_ERR_INVALID_ARGUMENT, "resolution[%d] = %lld out of range [2, 2^24]", l, (long long)r);
+        if (r < 2 || r > (1 << 22))
+            return fail(SHACIRA_ERR_INVALID_ARGUMENT, "resolution[%d] = %lld out of range [2, 2^22]", l, (long long)r);
         // the reference's predicate, with its int32 wrap-around (hashgrid_interpolate_cuda.cu:27-29)
         const int32_t r32 = (int32_t)r;
         const int32_t rr32 = (int32_t)((uint32_t)r32 * (uint32_t)r32);
@@ -54,6 +54,7 @@ int build_levels(int32_t dim, const int32_t* first_idx, const int32_t* resolutio
                         "indexes outside the table; parity is undefined (SURVEY Q2)", l, (long long)r, bitwidth);
         if (dense) lp.dense_mask |= (1u << l);
         lp.res[l] = r32;
+        lp.resd[l] = (double)r32;
         lp.rows[l] = (int32_t)(pts < T ? pts : T);
         lp.hi[l] = (float)((double)(r32 - 1) - 1e-5);
         lp.first[l] = first_idx ? first_idx[l] : (int32_t)running;

@@ -97,7 +97,7 @@ int launch_fwd3d(int latent_dim, int feature_dim, const float* coords, const int
 int launch_bwd3d(int latent_dim, int feature_dim, const float* coords, const int32_t* perm, int64_t n,
                  const float* grad_out, const float* zsave, const LevelParams& lp, const float* A, int per_level,
                  uint32_t skip_mask, uint32_t level_mask, int red_w, float* grad_latents, float* grad_A,
-                 float* grad_shift, cudaStream_t s);
+                 float* grad_shift, cudaStream_t s, int ctas_per_sm = 4);
 // tuning knobs (environment, read per call: A/B runs flip them inside one process)
 int grid3d_merge_mode();   // SHACIRA_3D_MERGE: 1 (default) = merged forward loads, 0 = point-parallel kernel
 int grid3d_red_mode();     // SHACIRA_3D_RED:   4 (default) / 2 = vector reds, 0 = scalar, -1 = point-parallel kernel

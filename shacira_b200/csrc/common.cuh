@@ -16,6 +16,7 @@ constexpr uint32_t kPrimeZ = 805459861u;   // hashgrid_interpolate_cuda.cu:25
 
 // Passed by value as a __grid_constant__ kernel parameter (lives in constant bank 0).
 struct LevelParams {
+    double resd[SHACIRA_MAX_LEVELS];    // (double)res: x = float(resd * t) without a per-level conversion
     int32_t res[SHACIRA_MAX_LEVELS];    // grid resolution of the level
     int32_t first[SHACIRA_MAX_LEVELS];  // first table row of the level
     int32_t rows[SHACIRA_MAX_LEVELS];   // rows of the level = min(2^bw, res^dim)
@@ -33,11 +34,21 @@ __device__ __forceinline__ double unit_coord(float c) { return fma((double)c, 0.
 // x = clamp((float)(res * t), 0, hi); cell = floor(x); f = x - cell; g = 1 - f.
 // (1.0 - f is a double subtraction narrowed to float in the reference; it is exact in
 // double for every reachable f, hence equal to the float subtraction -- DESIGN.md.)
+// floor(x) and float(floor(x)) for 0 <= x < 2^22 without the conversion unit: x + 2^23 rounded DOWN is exactly
+// 2^23 + floor(x) (floats in [2^23, 2^24) are the integers), whose mantissa is the cell and which minus 2^23 is the
+// cell as a float. F2I / I2F run on the quarter-rate XU pipe with scoreboard latency; FADD.RM is a plain FMA-pipe op.
+// (Resolutions are capped at 2^22 by build_levels.)
+__device__ __forceinline__ void floor_cell(float x, int32_t& cell, float& cellf) {
+    const float y = __fadd_rd(x, 8388608.0f);
+    cell = __float_as_int(y) - 0x4B000000;
+    cellf = __fsub_rn(y, 8388608.0f);
+}
 __device__ __forceinline__ void locate(double t, int32_t res, float hi, int32_t& cell, float& f, float& g) {
     float x = __double2float_rn(__dmul_rn((double)res, t));
     x = fmaxf(0.0f, fminf(hi, x));
-    cell = __float2int_rd(x);
-    f = __fsub_rn(x, (float)cell);
+    float cf;
+    floor_cell(x, cell, cf);
+    f = __fsub_rn(x, cf);
     g = __fsub_rn(1.0f, f);
 }
 

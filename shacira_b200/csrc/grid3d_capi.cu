@@ -57,7 +57,7 @@ int fwd3d(const float* coords, const int32_t* perm, int64_t n, const float* lat,
 template <int C, int F>
 int bwd3d(const float* coords, const int32_t* perm, int64_t n, const float* g, const float* zsave, const LevelParams& lp,
           const float* A, int per_level, uint32_t skip_mask, uint32_t level_mask, int red_w, float* gl, float* gA,
-          float* gS, cudaStream_t s) {
+          float* gS, cudaStream_t s, int ctas_per_sm) {
     const int nA = per_level ? lp.num_lods : 1;
     if (red_w >= 8) {   // lane pairs, persistent CTAs
         const bool dec = gA != nullptr || gS != nullptr;
@@ -67,7 +67,7 @@ int bwd3d(const float* coords, const int32_t* perm, int64_t n, const float* g, c
         if (needs_config(configured))
             CUDA_OK(cudaFuncSetAttribute(latent_bwd3d_lp_kernel<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         const char* e_ctas = getenv("SHACIRA_3D_BWD_CTAS");
-        const int per_sm = (e_ctas && atoi(e_ctas) > 0) ? atoi(e_ctas) : 4;
+        const int per_sm = (e_ctas && atoi(e_ctas) > 0) ? atoi(e_ctas) : ctas_per_sm;
         int64_t blocks = (n + kLpChunk - 1) / kLpChunk;
         const int64_t cap = (int64_t)sm_count() * per_sm;
         if (blocks > cap) blocks = cap;
@@ -106,9 +106,10 @@ int launch_fwd3d(int C, int F, const float* coords, const int32_t* perm, int64_t
 
 int launch_bwd3d(int C, int F, const float* coords, const int32_t* perm, int64_t n, const float* grad_out,
                  const float* zsave, const LevelParams& lp, const float* A, int per_level, uint32_t skip_mask,
-                 uint32_t level_mask, int red_w, float* grad_latents, float* grad_A, float* grad_shift, cudaStream_t s) {
+                 uint32_t level_mask, int red_w, float* grad_latents, float* grad_A, float* grad_shift, cudaStream_t s,
+                 int ctas_per_sm) {
     G3_DISPATCH(C, F, (bwd3d<kC, kF>(coords, perm, n, grad_out, zsave, lp, A, per_level, skip_mask, level_mask, red_w,
-                                     grad_latents, grad_A, grad_shift, s)))
+                                     grad_latents, grad_A, grad_shift, s, ctas_per_sm)))
 }
 
 }  // namespace shacira

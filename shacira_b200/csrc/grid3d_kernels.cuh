@@ -404,7 +404,13 @@ constexpr int kLpWarps = 8;                  // warps per CTA
 constexpr int kLpBlock = kLpWarps * 32;
 constexpr int kLpSamples = 16;               // samples per warp pass
 constexpr int kLpChunk = kLpWarps * kLpSamples;  // samples per CTA pass
-constexpr int kLpLv = 4;                     // levels in flight per lane (16 loads)
+#ifndef SHACIRA_LP_LV
+#define SHACIRA_LP_LV 2
+#endif
+#ifndef SHACIRA_LP_MINB
+#define SHACIRA_LP_MINB 5
+#endif
+constexpr int kLpLv = SHACIRA_LP_LV;         // levels in flight per lane (4 loads each)
 constexpr int kLpFlush = 8;                  // levels per output flush of the forward
 
 // this lane's side of the cell at level l: 4 corner rows (absolute) j = dy*2 + dz and their weights
@@ -412,14 +418,22 @@ struct Side3 {
     int32_t idx[4];
     float w[4];
 };
+__device__ __forceinline__ void locate_d(double t, double resd, float hi, int32_t& cell, float& f, float& g) {
+    float x = __double2float_rn(__dmul_rn(resd, t));
+    x = fmaxf(0.0f, fminf(hi, x));
+    float cf;
+    floor_cell(x, cell, cf);
+    f = __fsub_rn(x, cf);
+    g = __fsub_rn(1.0f, f);
+}
 __device__ __forceinline__ void side3(const double (&t)[3], const LevelParams& lp, int l, int dx, Side3& o) {
-    const int32_t res = lp.res[l];
+    const double resd = lp.resd[l];
     const float hi = lp.hi[l];
     const int32_t first = lp.first[l];
     int32_t p[3];
     float f[3], g[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) locate(t[d], res, hi, p[d], f[d], g[d]);
+    for (int d = 0; d < 3; ++d) locate_d(t[d], resd, hi, p[d], f[d], g[d]);
     const float X = dx ? f[0] : g[0];
     const float xy0 = __fmul_rn(X, g[1]), xy1 = __fmul_rn(X, f[1]);   // reference: (wx * wy) * wz, left to right
     o.w[0] = __fmul_rn(xy0, g[2]);
@@ -427,19 +441,24 @@ __device__ __forceinline__ void side3(const double (&t)[3], const LevelParams& l
     o.w[2] = __fmul_rn(xy1, g[2]);
     o.w[3] = __fmul_rn(xy1, f[2]);
     if ((lp.dense_mask >> l) & 1u) {
-        const int32_t last = lp.rows[l] - 1;   // zero-weight corners stay inside the level
+        const int32_t res = lp.res[l];
+        const int32_t last = first + lp.rows[l] - 1;   // zero-weight corners stay inside the level
         const int32_t rr = res * res;
-        const int32_t base = p[0] + dx + p[1] * res + p[2] * rr;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o.idx[j] = first + min(base + ((j >> 1) & 1) * res + (j & 1) * rr, last);
+        const int32_t base = first + p[0] + dx + p[1] * res + p[2] * rr;
+        o.idx[0] = min(base, last);
+        o.idx[1] = min(base + rr, last);
+        o.idx[2] = min(base + res, last);
+        o.idx[3] = min(base + res + rr, last);
     } else {
         const uint32_t m = lp.hash_mask;
         const uint32_t hx = (uint32_t)(p[0] + dx);
         const uint32_t hy0 = (uint32_t)p[1] * kPrimeY, hz0 = (uint32_t)p[2] * kPrimeZ;
-        const uint32_t hy[2] = {hy0, hy0 + kPrimeY};
-        const uint32_t hz[2] = {hz0, hz0 + kPrimeZ};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o.idx[j] = first + (int32_t)((hx ^ hy[(j >> 1) & 1] ^ hz[j & 1]) & m);
+        const uint32_t a0 = hx ^ hy0, a1 = hx ^ (hy0 + kPrimeY);
+        const uint32_t hz1 = hz0 + kPrimeZ;
+        o.idx[0] = first + (int32_t)((a0 ^ hz0) & m);
+        o.idx[1] = first + (int32_t)((a0 ^ hz1) & m);
+        o.idx[2] = first + (int32_t)((a1 ^ hz0) & m);
+        o.idx[3] = first + (int32_t)((a1 ^ hz1) & m);
     }
 }
 
@@ -454,8 +473,71 @@ struct LpFwdLayout {
     static size_t bytes(int nA) { return sizeof(float) * (size_t)(lp_dec_floats(nA, C, F) + kLpWarps * kWarpFloats); }
 };
 
+template <int N>
+__device__ __forceinline__ void sts_row(float* p, const float (&v)[N]) {
+    if constexpr (N == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if constexpr (N == 8) {
+        reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else if constexpr (N == 2) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < N; ++e) p[e] = v[e];
+    }
+}
+
+// NQ levels l .. l+NQ-1 of one lane: sides, the 4*NQ gathers in flight together, interpolation, decode into the tile
+template <int C, int F, int NQ>
+__device__ __forceinline__ void lp_fwd_levels(const double (&t)[3], const LevelParams& lp, int l, int dx, int per_level,
+                                              int round_flag, const float* __restrict__ latents, const float* s_A,
+                                              const float* s_shift, float* ft, float* zt) {
+    Side3 sd[NQ];
+    float v[NQ][4][C];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) side3(t, lp, l + q, dx, sd[q]);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) load_row<C>(latents + (int64_t)sd[q].idx[j] * C, v[q][j]);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const int la = per_level ? (l + q) : 0;
+        float z[C];
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            float r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = round_flag ? rintf(v[q][j][ch]) : v[q][j][ch];
+            // reference order: fma(v0,w0, v1*w1), then corners 2..7; the even lane (x) runs 0..3 and hands over
+            float acc = __fmul_rn(r[1], sd[q].w[1]);
+            acc = __fmaf_rn(r[0], sd[q].w[0], acc);
+            acc = __fmaf_rn(r[2], sd[q].w[2], acc);
+            acc = __fmaf_rn(r[3], sd[q].w[3], acc);
+            float cont = __shfl_xor_sync(0xffffffffu, acc, 1);   // odd lane: the even lane's partial sum
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cont = __fmaf_rn(r[j], sd[q].w[j], cont);
+            z[ch] = cont;   // meaningful on odd lanes
+        }
+        if (dx) {
+            float o[F];
+            const float* Ap = s_A + la * C * F;
+#pragma unroll
+            for (int jf = 0; jf < F; ++jf) {
+                float acc = s_shift[la * F + jf];
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) acc = __fmaf_rn(z[ch], Ap[ch * F + jf], acc);
+                o[jf] = acc;
+            }
+            sts_row<F>(ft + q * F, o);
+            sts_row<C>(zt + q * C, z);
+        }
+    }
+}
+
 template <int C, int F>
-__global__ void __launch_bounds__(kLpBlock)
+__global__ void __launch_bounds__(kLpBlock, SHACIRA_LP_MINB)
 latent_fwd3d_lp_kernel(const float* __restrict__ coords, const int32_t* __restrict__ perm, int64_t n,
                        const float* __restrict__ latents, const __grid_constant__ LevelParams lp,
                        const float* __restrict__ A, const float* __restrict__ shift, int per_level, int round_flag,
@@ -478,75 +560,38 @@ latent_fwd3d_lp_kernel(const float* __restrict__ coords, const int32_t* __restri
     const int dx = lane & 1, sp = lane >> 1;
     const int64_t base = (int64_t)blockIdx.x * kLpChunk + warp * kLpSamples;   // first sample of this warp
     if (base >= n) return;
-    const int64_t i = base + sp;
-    const bool live = i < n;
-    double t[3] = {0.5, 0.5, 0.5};
-    if (live) {
-        load_unit_coords<3>(coords, i, t);
-        if (dx) s_row[sp] = perm ? (long long)__ldg(perm + i) : (long long)i;
-    }
-    __syncwarp();
     const int nlive = (int)min((int64_t)kLpSamples, n - base);
+    // lanes past the end recompute the last sample (never flushed): no predicates in the level loop
+    const int64_t i = min(base + sp, n - 1);
+    double t[3];
+    load_unit_coords<3>(coords, i, t);
+    if (dx) s_row[sp] = perm ? (long long)__ldg(perm + i) : (long long)i;
+    __syncwarp();
     const int LF = L * F, LC = L * C;
+    float* my_ft = s_tile + sp * WF;
+    float* my_zt = s_ztile + sp * WZ;
     for (int l0 = 0; l0 < L; l0 += kLpFlush) {
         const int lw = min(kLpFlush, L - l0);   // levels in this flush
-        for (int l1 = 0; l1 < lw; l1 += kLpLv) {
-            Side3 sd[kLpLv];
-            float v[kLpLv][4][C];
-#pragma unroll
-            for (int q = 0; q < kLpLv; ++q)
-                if (l1 + q < lw) side3(t, lp, l0 + l1 + q, dx, sd[q]);
-#pragma unroll
-            for (int q = 0; q < kLpLv; ++q)
-                if (l1 + q < lw && live) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) load_row<C>(latents + (int64_t)sd[q].idx[j] * C, v[q][j]);
-                }
-#pragma unroll
-            for (int q = 0; q < kLpLv; ++q) {
-                if (l1 + q >= lw) continue;   // uniform
-                const int l = l0 + l1 + q;
-                const int la = per_level ? l : 0;
-                float z[C];
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) {
-                    float r[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) r[j] = live ? (round_flag ? rintf(v[q][j][ch]) : v[q][j][ch]) : 0.0f;
-                    // reference order: fma(v0,w0, v1*w1), then corners 2..7; the even lane (x) runs 0..3 and hands over
-                    float acc = __fmul_rn(r[1], sd[q].w[1]);
-                    acc = __fmaf_rn(r[0], sd[q].w[0], acc);
-                    acc = __fmaf_rn(r[2], sd[q].w[2], acc);
-                    acc = __fmaf_rn(r[3], sd[q].w[3], acc);
-                    float cont = __shfl_xor_sync(0xffffffffu, acc, 1);   // odd lane: the even lane's partial sum
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) cont = __fmaf_rn(r[j], sd[q].w[j], cont);
-                    z[ch] = cont;   // meaningful on odd lanes
-                }
-                if (dx) {
-                    float* ft = s_tile + sp * WF + (l1 + q) * F;
-#pragma unroll
-                    for (int jf = 0; jf < F; ++jf) {
-                        float acc = s_shift[la * F + jf];
-#pragma unroll
-                        for (int ch = 0; ch < C; ++ch) acc = __fmaf_rn(z[ch], s_A[(la * C + ch) * F + jf], acc);
-                        ft[jf] = acc;
-                    }
-#pragma unroll
-                    for (int ch = 0; ch < C; ++ch) s_ztile[sp * WZ + (l1 + q) * C + ch] = z[ch];
-                }
-            }
-        }
+        int l1 = 0;
+        for (; l1 + kLpLv <= lw; l1 += kLpLv)
+            lp_fwd_levels<C, F, kLpLv>(t, lp, l0 + l1, dx, per_level, round_flag, latents, s_A, s_shift, my_ft + l1 * F,
+                                       my_zt + l1 * C);
+        for (; l1 < lw; ++l1)
+            lp_fwd_levels<C, F, 1>(t, lp, l0 + l1, dx, per_level, round_flag, latents, s_A, s_shift, my_ft + l1 * F,
+                                   my_zt + l1 * C);
         __syncwarp();
         // flush `lw` levels of the live samples: consecutive lanes write consecutive 16-byte chunks of a row piece
         {
             const int wf = lw * F;
             if ((wf & 3) == 0 && (LF & 3) == 0) {
                 const int per = wf >> 2;
-                for (int u = lane; u < nlive * per; u += 32) {
-                    const int s = u / per, c4 = u - s * per;
+                int s = 0, c4 = lane;
+                while (c4 >= per) { c4 -= per; ++s; }
+                while (s < nlive) {
                     const float4 val = *reinterpret_cast<const float4*>(s_tile + s * WF + 4 * c4);
                     *reinterpret_cast<float4*>(feats + s_row[s] * LF + l0 * F + 4 * c4) = val;
+                    c4 += 32;
+                    while (c4 >= per) { c4 -= per; ++s; }
                 }
             } else {
                 for (int u = lane; u < nlive * wf; u += 32) {
@@ -559,10 +604,13 @@ latent_fwd3d_lp_kernel(const float* __restrict__ coords, const int32_t* __restri
                 float* zb = zsave + base * LC + l0 * C;
                 if ((wz & 3) == 0 && (LC & 3) == 0) {
                     const int per = wz >> 2;
-                    for (int u = lane; u < nlive * per; u += 32) {
-                        const int s = u / per, c4 = u - s * per;
+                    int s = 0, c4 = lane;
+                    while (c4 >= per) { c4 -= per; ++s; }
+                    while (s < nlive) {
                         *reinterpret_cast<float4*>(zb + (int64_t)s * LC + 4 * c4) =
                             *reinterpret_cast<const float4*>(s_ztile + s * WZ + 4 * c4);
+                        c4 += 32;
+                        while (c4 >= per) { c4 -= per; ++s; }
                     }
                 } else {
                     for (int u = lane; u < nlive * wz; u += 32) {
@@ -612,12 +660,13 @@ latent_bwd3d_lp_kernel(const float* __restrict__ coords, const int32_t* __restri
     float* s_gS = s_gA + L * C * F;                       // [L][F]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* s_g = s_gA + lp_dec_floats(L, C, F) + warp * (kLpSamples * (WG + (want_dec ? WZ : 0)));   // [16][WG]
-    float* s_z = s_g + kLpSamples * WG;                                             // [16][WZ]
+    float* s_z = s_g + kLpSamples * WG;                                                              // [16][WZ]
     for (int e = threadIdx.x; e < nA * C * F; e += kLpBlock) s_A[e] = A[e];
     for (int e = threadIdx.x; e < L * (C * F + F); e += kLpBlock) s_gA[e] = 0.0f;
     __syncthreads();
     const int dx = lane & 1, sp = lane >> 1;
     const uint32_t scatter_mask = level_mask & ~skip_mask;
+    const float* my_g = s_g + sp * WG;
     // decoder-gradient columns of this lane: col = lane + 32 k (< L*F), k < F (L <= 32)
     float accS[F], accA[F][C];
 #pragma unroll
@@ -631,24 +680,28 @@ latent_bwd3d_lp_kernel(const float* __restrict__ coords, const int32_t* __restri
         const int64_t base = chunk * kLpChunk + warp * kLpSamples;
         if (base >= n) continue;   // warp-uniform
         const int nlive = (int)min((int64_t)kLpSamples, n - base);
-        const int64_t i = base + sp;
-        const bool live = i < n;
-        double t[3] = {0.5, 0.5, 0.5};
-        if (live) load_unit_coords<3>(coords, i, t);
+        const bool live = base + sp < n;
+        const int64_t i = min(base + sp, n - 1);
+        double t[3];
+        load_unit_coords<3>(coords, i, t);
         // stage the gradient rows: lane pair s holds the row index of sample s; whole 16-byte chunks, whole lines
-        const long long my_row = live ? (perm ? (long long)__ldg(perm + i) : (long long)i) : 0;
+        const long long my_row = perm ? (long long)__ldg(perm + i) : (long long)i;
         __syncwarp();
         if ((LF & 3) == 0) {
             const int per = LF >> 2;
-            for (int u0 = 0; u0 < kLpSamples * per; u0 += 32) {
-                const int u = u0 + lane;
-                const int s = u / per, c4 = u - s * per;
-                const long long r = __shfl_sync(0xffffffffu, my_row, (s < kLpSamples ? s : 0) * 2);
-                if (s < kLpSamples) {
+            int s = 0, c4 = lane;
+            while (c4 >= per) { c4 -= per; ++s; }
+            const int iters = (kLpSamples * per + 31) >> 5;   // warp-uniform trip count (the shuffle needs every lane)
+            for (int it = 0; it < iters; ++it) {
+                const bool in = s < kLpSamples;
+                const long long r = __shfl_sync(0xffffffffu, my_row, in ? 2 * s : 0);
+                if (in) {
                     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (s < nlive) val = __ldg(reinterpret_cast<const float4*>(grad_out + r * LF) + c4);
                     *reinterpret_cast<float4*>(s_g + s * WG + 4 * c4) = val;
                 }
+                c4 += 32;
+                while (c4 >= per) { c4 -= per; ++s; }
             }
         } else {
             for (int u0 = 0; u0 < kLpSamples * LF; u0 += 32) {
@@ -672,16 +725,16 @@ latent_bwd3d_lp_kernel(const float* __restrict__ coords, const int32_t* __restri
             if (!((scatter_mask >> l) & 1u)) continue;
             Side3 sd;
             side3(t, lp, l, dx, sd);
-            const int la = per_level ? l : 0;
+            const float* Ap = s_A + (per_level ? l : 0) * C * F;
             float g[F];
 #pragma unroll
-            for (int jf = 0; jf < F; ++jf) g[jf] = s_g[sp * WG + l * F + jf];
+            for (int jf = 0; jf < F; ++jf) g[jf] = my_g[l * F + jf];
             float gz[C];
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
                 float acc = 0.0f;
 #pragma unroll
-                for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[jf], s_A[(la * C + ch) * F + jf], acc);
+                for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[jf], Ap[ch * F + jf], acc);
                 gz[ch] = acc;
             }
             if (live) {

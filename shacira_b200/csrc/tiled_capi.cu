@@ -192,13 +192,22 @@ int backward_3d(shacira_plan* p, const float* g, const float* zsave, const Level
     const int budget = smem_budget();
     const int rep = (kRepBudget / C) & ~3;
     const int ns = (num_lods_ok(lp) && grid3d_red_mode() >= 0) ? staged_prefix_3d(p, lp, (budget - rep * 4 * C) / (4 * C), &cap) : 0;
-    bool forked = false;
+    const uint32_t skip = ns >= 32 ? 0xffffffffu : ((1u << ns) - 1u);
+    const int red_w = grid3d_red_mode() < 0 ? 0 : grid3d_red_mode();
     SideStream* ss = nullptr;
     if (ns > 0) {
         if (int rc = side_stream(&ss)) return rc;
         CUDA_OK(cudaEventRecord(ss->fork, s));
         CUDA_OK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
-        int rc = SHACIRA_OK;
+    }
+    // The fine levels first: that kernel is bound by L2 reds and needs few warps (2 persistent CTAs per SM when the
+    // staged kernel runs beside it), the tile-staged kernel by shared memory and issue slots; launched in this
+    // order the two share every SM instead of queueing behind each other's CTAs.
+    int rc = launch_bwd3d(C, F, p->coords_sorted, p->sorted_io ? nullptr : p->perm, p->n, g, zsave, lp, A, per_level, skip,
+                          0xffffffffu, red_w, gl, gA, gS, s, ns > 0 ? 2 : 4);
+    if (rc) return rc;
+    bool forked = false;
+    if (ns > 0) {
         if (C == 1) {
             switch (F) {
                 case 1: rc = launch_bwd_staged3d<1, 1>(p, g, lp, A, per_level, gl, ns, cap, ss->stream); break;
@@ -218,11 +227,6 @@ int backward_3d(shacira_plan* p, const float* g, const float* zsave, const Level
         CUDA_OK(cudaEventRecord(ss->join, ss->stream));
         forked = true;
     }
-    const uint32_t skip = ns >= 32 ? 0xffffffffu : ((1u << ns) - 1u);
-    const int red_w = grid3d_red_mode() < 0 ? 0 : grid3d_red_mode();
-    int rc = launch_bwd3d(C, F, p->coords_sorted, p->sorted_io ? nullptr : p->perm, p->n, g, zsave, lp, A, per_level, skip,
-                          0xffffffffu, red_w, gl, gA, gS, s);
-    if (rc) return rc;
     if (forked) CUDA_OK(cudaStreamWaitEvent(s, ss->join, 0));
     return SHACIRA_OK;
 }

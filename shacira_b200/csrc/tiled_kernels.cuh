@@ -320,8 +320,9 @@ struct Stencil {
 __device__ __forceinline__ void locate_r(double t, const LevelRegs& r, int32_t& cell, float& f, float& g) {
     float x = __double2float_rn(__dmul_rn(r.resd, t));
     x = fmaxf(0.0f, fminf(r.hi, x));
-    cell = __float2int_rd(x);
-    f = __fsub_rn(x, (float)cell);
+    float cf;
+    floor_cell(x, cell, cf);
+    f = __fsub_rn(x, cf);
     g = __fsub_rn(1.0f, f);
 }
 
