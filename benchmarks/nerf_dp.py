@@ -95,11 +95,23 @@ def main():
             h.wait()
         return len(handles)
 
+    planned = "--unplanned" not in sys.argv
+    plan = _lib.Plan(sets[0]["coords"]) if planned else None
+
     def step(i):
         if chunks > 1:
             return step_chunked(i)
         s = sets[i % sets_n]
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if planned:
+            # the samples are new every step: re-bin them (3 small kernels, allocation reused), then the sorted kernels
+            _lib._check(lib.shacira_plan_rebuild(plan.handle, 3, P(s["coords"]), S, 0, st))
+            _lib._check(lib.shacira_latent_forward_planned_z(plan.handle, P(lat), fi, rs, L, BW, C, F, 1, P(A), P(shift), 0,
+                                                             P(feats), P(z), st))
+            arena.zero_()   # one memset: table gradient + decoder gradients
+            _lib._check(lib.shacira_latent_backward_planned_z(plan.handle, P(s["g"]), P(z), fi, rs, L, BW, C, F, P(A), 0,
+                                                              T, 0, P(glat.grad), P(gA.grad), P(gS.grad), st))
+            return arena.allreduce()
         _lib._check(lib.shacira_latent_forward(3, P(s["coords"]), S, P(lat), fi, rs, L, BW, C, F, 1, P(A), P(shift), 0,
                                                P(feats), P(z), st))
         gA.grad.zero_()
@@ -133,7 +145,9 @@ def main():
                           "ms_per_step": ms, "samples_per_s": S * world / ms * 1e3, "rays_per_s": RAYS * world / ms * 1e3,
                           "allreduce_bytes": T * C * 4, "collectives_per_step": ncoll,
                           "alg_GBs_per_gpu": (bf + bb) * S / ms / 1e6, "frac_hbm_peak": (bf + bb) * S / ms / 1e6 / peak,
-                          "backward_level_chunks": chunks, "path": "point-parallel 3D kernels"}), flush=True)
+                          "backward_level_chunks": chunks,
+                          "path": "plan re-binned per step + sorted lane-pair kernels + tile-staged coarse levels" if planned
+                          else "unsorted lane-pair kernels + whole-level shared-memory coarse path"}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

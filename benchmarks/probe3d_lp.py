@@ -56,15 +56,14 @@ us = timed(lambda i: _lib.latent_forward(sets[i % SETS]["coords"], lat, first, r
 emit(kernel="fwd", variant="lane pairs, unsorted", us=us)
 if args.bwd:
     zs = [_lib.latent_forward_planned_z(plans[k], lat, first, res, BW, A, shift, F, True, True)[1] for k in range(SETS)]
-    for staged in (None, 0, 5, 6):
-        for ctas in (None, 1, 2, 3, 4):
-            if staged is not None and ctas is not None:
-                continue
+    for staged, ctas in ((None, None), (None, 3), (5, None), (6, None), (0, None)):
+        if True:
             setenv(SHACIRA_3D_STAGED=staged, SHACIRA_3D_BWD_CTAS=ctas)
             for dec in (False, True):
                 gl, gA, gS = _lib.latent_backward_planned_z(plans[0], sets[0]["g"], zs[0] if dec else None, first, res, BW, A, C, F, T, dec)
                 us = timed(lambda i: _lib.latent_backward_planned_z(plans[i % SETS], sets[i % SETS]["g"], zs[i % SETS] if dec else None, first, res, BW, A, C, F, T, dec), iters=20)
                 rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+                lvl = max(float((gl[first[l]:first[l] + sizes[l]] - gl0[first[l]:first[l] + sizes[l]]).abs().max() / gl0[first[l]:first[l] + sizes[l]].abs().max()) for l in range(L))
                 emit(kernel="bwd+dec" if dec else "bwd", variant="sorted g=%d staged=%s ctas/sm=%s" % (info["tiles_per_axis"], staged, ctas), us=us,
-                     rel=rel(gl, gl0), rel_gA=rel(gA, gA0) if dec else None, rel_gS=rel(gS, gS0) if dec else None)
+                     rel=rel(gl, gl0), level_rel=lvl, rel_gA=rel(gA, gA0) if dec else None, rel_gS=rel(gS, gS0) if dec else None)
     setenv(SHACIRA_3D_STAGED=None, SHACIRA_3D_BWD_CTAS=None)

@@ -80,6 +80,8 @@ inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block
 template <int D, int F>
 int launch_plain_fwd(const float* coords, int64_t n, const float* table, const LevelParams& lp, float* feats,
                      cudaStream_t s) {
+    if (D == 3 && grid3d_merge_mode() >= 2 && grid3d_supported(F, F, table))   // lane pairs, identity decoder
+        return launch_fwd3d(F, F, coords, nullptr, n, table, lp, nullptr, nullptr, 0, 0, feats, nullptr, s);
     hashgrid_fwd_kernel<D, F><<<grid_for(n, kBlock), kBlock, 0, s>>>(coords, n, table, lp, feats);
     LAUNCHED();
     return SHACIRA_OK;
@@ -157,6 +159,11 @@ int launch_plain_bwd(const float* coords, int64_t n, const float* g, const Level
     bool join = false;
     int rc = launch_coarse_bwd<D, F, F, false>(coords, n, g, lp, nullptr, 0, gt, s, skip, join);
     if (rc) return rc;
+    if (D == 3 && grid3d_red_mode() >= 8 && grid3d_supported(F, F, gt)) {   // lane pairs, identity decoder
+        rc = launch_bwd3d(F, F, coords, nullptr, n, g, nullptr, lp, nullptr, 0, skip, 0xffffffffu, 8, gt, nullptr, nullptr, s);
+        if (rc) return rc;
+        return join ? join_side(s) : SHACIRA_OK;
+    }
     hashgrid_bwd_kernel<D, F><<<grid_for(n, kBlock), kBlock, 0, s>>>(coords, n, g, lp, skip, gt);
     LAUNCHED();
     return join ? join_side(s) : SHACIRA_OK;

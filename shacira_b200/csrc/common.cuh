@@ -191,6 +191,11 @@ __device__ __forceinline__ void red_add_row(float* p, const float (&v)[N]) {
     }
 }
 
+// max that PROPAGATES NaN (fmaxf returns the non-NaN operand): a NaN upstream gradient has to reach the fixed-point
+// scale logic, where it poisons the level like the reference's float atomics would. As an unsigned bit pattern a
+// positive NaN compares above +Inf, so REDUX / atomicMax on the bits keep it.
+__device__ __forceinline__ float nan_max(float m, float a) { return (a != a) ? a : ((m != m) ? m : fmaxf(m, a)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

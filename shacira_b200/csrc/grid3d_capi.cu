@@ -37,6 +37,7 @@ template <int C, int F>
 int fwd3d(const float* coords, const int32_t* perm, int64_t n, const float* lat, const LevelParams& lp, const float* A,
           const float* shift, int per_level, int round_flag, float* feats, float* zsave, cudaStream_t s) {
     const int nA = per_level ? lp.num_lods : 1;
+    if (!A && (C != F || grid3d_merge_mode() < 2)) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "3D forward: A is NULL");
     if (grid3d_merge_mode() >= 2) {   // lane pairs
         const size_t smem = LpFwdLayout<C, F>::bytes(nA);
         static unsigned long long configured = 0ull;
@@ -59,6 +60,7 @@ int bwd3d(const float* coords, const int32_t* perm, int64_t n, const float* g, c
           const float* A, int per_level, uint32_t skip_mask, uint32_t level_mask, int red_w, float* gl, float* gA,
           float* gS, cudaStream_t s, int ctas_per_sm) {
     const int nA = per_level ? lp.num_lods : 1;
+    if (!A && (C != F || red_w < 8)) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "3D backward: A is NULL");
     if (red_w >= 8) {   // lane pairs, persistent CTAs
         const bool dec = gA != nullptr || gS != nullptr;
         const size_t smem = LpBwdLayout<C, F>::bytes(lp.num_lods, nA, dec);

@@ -522,13 +522,18 @@ __device__ __forceinline__ void lp_fwd_levels(const double (&t)[3], const LevelP
         }
         if (dx) {
             float o[F];
-            const float* Ap = s_A + la * C * F;
+            if (C == F && s_A == nullptr) {   // plain table (wisp._C.ops entry points): features = interpolated rows
 #pragma unroll
-            for (int jf = 0; jf < F; ++jf) {
-                float acc = s_shift[la * F + jf];
+                for (int jf = 0; jf < F; ++jf) o[jf] = z[jf < C ? jf : 0];
+            } else {
+                const float* Ap = s_A + la * C * F;
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) acc = __fmaf_rn(z[ch], Ap[ch * F + jf], acc);
-                o[jf] = acc;
+                for (int jf = 0; jf < F; ++jf) {
+                    float acc = s_shift[la * F + jf];
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) acc = __fmaf_rn(z[ch], Ap[ch * F + jf], acc);
+                    o[jf] = acc;
+                }
             }
             sts_row<F>(ft + q * F, o);
             sts_row<C>(zt + q * C, z);
@@ -549,12 +554,14 @@ latent_fwd3d_lp_kernel(const float* __restrict__ coords, const int32_t* __restri
     const int nA = per_level ? L : 1;
     float* s_A = s_dyn;                       // [nA][C][F]
     float* s_shift = s_A + nA * C * F;        // [nA][F]
+    const float* dec_A = A ? s_A : nullptr;   // A == NULL (C == F only): identity decoder, the plain hash grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* s_warp = s_dyn + lp_dec_floats(nA, C, F) + warp * LY::kWarpFloats;
     long long* s_row = reinterpret_cast<long long*>(s_warp);   // [16] output row of each sample
     float* s_tile = s_warp + 2 * kLpSamples;                     // [16][WF]
     float* s_ztile = s_tile + kLpSamples * WF;                   // [16][WZ]
-    for (int e = threadIdx.x; e < nA * C * F; e += kLpBlock) s_A[e] = A[e];
+    if (A)
+        for (int e = threadIdx.x; e < nA * C * F; e += kLpBlock) s_A[e] = A[e];
     for (int e = threadIdx.x; e < nA * F; e += kLpBlock) s_shift[e] = shift ? shift[e] : 0.0f;
     __syncthreads();
     const int dx = lane & 1, sp = lane >> 1;
@@ -574,10 +581,10 @@ latent_fwd3d_lp_kernel(const float* __restrict__ coords, const int32_t* __restri
         const int lw = min(kLpFlush, L - l0);   // levels in this flush
         int l1 = 0;
         for (; l1 + kLpLv <= lw; l1 += kLpLv)
-            lp_fwd_levels<C, F, kLpLv>(t, lp, l0 + l1, dx, per_level, round_flag, latents, s_A, s_shift, my_ft + l1 * F,
+            lp_fwd_levels<C, F, kLpLv>(t, lp, l0 + l1, dx, per_level, round_flag, latents, dec_A, s_shift, my_ft + l1 * F,
                                        my_zt + l1 * C);
         for (; l1 < lw; ++l1)
-            lp_fwd_levels<C, F, 1>(t, lp, l0 + l1, dx, per_level, round_flag, latents, s_A, s_shift, my_ft + l1 * F,
+            lp_fwd_levels<C, F, 1>(t, lp, l0 + l1, dx, per_level, round_flag, latents, dec_A, s_shift, my_ft + l1 * F,
                                    my_zt + l1 * C);
         __syncwarp();
         // flush `lw` levels of the live samples: consecutive lanes write consecutive 16-byte chunks of a row piece
@@ -661,7 +668,8 @@ latent_bwd3d_lp_kernel(const float* __restrict__ coords, const int32_t* __restri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* s_g = s_gA + lp_dec_floats(L, C, F) + warp * (kLpSamples * (WG + (want_dec ? WZ : 0)));   // [16][WG]
     float* s_z = s_g + kLpSamples * WG;                                                              // [16][WZ]
-    for (int e = threadIdx.x; e < nA * C * F; e += kLpBlock) s_A[e] = A[e];
+    if (A)
+        for (int e = threadIdx.x; e < nA * C * F; e += kLpBlock) s_A[e] = A[e];
     for (int e = threadIdx.x; e < L * (C * F + F); e += kLpBlock) s_gA[e] = 0.0f;
     __syncthreads();
     const int dx = lane & 1, sp = lane >> 1;
@@ -730,12 +738,17 @@ latent_bwd3d_lp_kernel(const float* __restrict__ coords, const int32_t* __restri
 #pragma unroll
             for (int jf = 0; jf < F; ++jf) g[jf] = my_g[l * F + jf];
             float gz[C];
+            if (C == F && A == nullptr) {   // plain table: the gradient rows are the row gradients (2d_cuda.cu:203-205)
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-                float acc = 0.0f;
+                for (int ch = 0; ch < C; ++ch) gz[ch] = g[ch < F ? ch : 0];
+            } else {
 #pragma unroll
-                for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[jf], Ap[ch * F + jf], acc);
-                gz[ch] = acc;
+                for (int ch = 0; ch < C; ++ch) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[jf], Ap[ch * F + jf], acc);
+                    gz[ch] = acc;
+                }
             }
             if (live) {
 #pragma unroll

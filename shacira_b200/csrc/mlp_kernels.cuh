@@ -863,8 +863,8 @@ mlp16_tc_step_kernel(const float* __restrict__ x, const float* __restrict__ gt, 
                     for (int nt = 0; nt < 2; ++nt) {
                         *reinterpret_cast<float2*>(gx + row * 16 + 8 * nt + 2 * t) =
                             make_float2(D[mt][nt][2 * hh], D[mt][nt][2 * hh + 1]);
-                        cmax[nt][0] = fmaxf(cmax[nt][0], fabsf(D[mt][nt][2 * hh]));
-                        cmax[nt][1] = fmaxf(cmax[nt][1], fabsf(D[mt][nt][2 * hh + 1]));
+                        cmax[nt][0] = nan_max(cmax[nt][0], fabsf(D[mt][nt][2 * hh]));
+                        cmax[nt][1] = nan_max(cmax[nt][1], fabsf(D[mt][nt][2 * hh + 1]));
                     }
                 }
             }

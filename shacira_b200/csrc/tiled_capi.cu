@@ -186,12 +186,13 @@ int launch_bwd_staged3d(shacira_plan* p, const float* g, const LevelParams& lp, 
     return SHACIRA_OK;
 }
 
-int backward_3d(shacira_plan* p, const float* g, const float* zsave, const LevelParams& lp, int C, int F, const float* A,
-                int per_level, float* gl, float* gA, float* gS, cudaStream_t s) {
-    int cap = 32;
-    const int budget = smem_budget();
-    const int rep = (kRepBudget / C) & ~3;
-    const int ns = (num_lods_ok(lp) && grid3d_red_mode() >= 0) ? staged_prefix_3d(p, lp, (budget - rep * 4 * C) / (4 * C), &cap) : 0;
+// Two kernels side by side: the tiled kernel accumulates the staged (coarse / middle) levels per tile in shared memory,
+// the lane-pair kernel sends the fine levels' reds and reduces the decoder gradients. Measured alternative, dropped:
+// both regimes in ONE persistent tile-walking kernel (rows staged once, no second read) -- 306 / 384 us against
+// 209 / 243 us for this form at the NeRF shape (profiles/r02e_probe3d_fused_ab.jsonl): five CTA-wide barriers per
+// 128-sample tile serialise staging, scale, accumulation and flush, and with 3 resident CTAs per SM nothing hides them.
+int backward_3d_two(shacira_plan* p, const float* g, const float* zsave, const LevelParams& lp, int C, int F, const float* A,
+                    int per_level, float* gl, float* gA, float* gS, int ns, int cap, cudaStream_t s) {
     const uint32_t skip = ns >= 32 ? 0xffffffffu : ((1u << ns) - 1u);
     const int red_w = grid3d_red_mode() < 0 ? 0 : grid3d_red_mode();
     SideStream* ss = nullptr;
@@ -231,6 +232,17 @@ int backward_3d(shacira_plan* p, const float* g, const float* zsave, const Level
     return SHACIRA_OK;
 }
 
+int backward_3d(shacira_plan* p, const float* g, const float* zsave, const LevelParams& lp, int C, int F, const float* A,
+                int per_level, float* gl, float* gA, float* gS, cudaStream_t s) {
+    int cap = 32;
+    const int budget = smem_budget();
+    const int rep = (kRepBudget / C) & ~3;
+    const int ns = (grid3d_red_mode() >= 0) ? staged_prefix_3d(p, lp, (budget - rep * 4 * C) / (4 * C), &cap) : 0;
+    if (!num_lods_ok(lp)) cap = 32;
+    const int ns_two = num_lods_ok(lp) ? ns : 0;   // the two-kernel form: the tiled kernel unrolls 4 levels
+    return backward_3d_two(p, g, zsave, lp, C, F, A, per_level, gl, gA, gS, ns_two, cap, s);
+}
+
 #define T_DISPATCH_F(F_, CALL)                                                                     \
     switch (F_) {                                                                                  \
         case 1: { constexpr int kF = 1; return CALL; }                                             \
@@ -253,9 +265,12 @@ namespace {
 
 int choose_tiles_per_axis(int dim, int64_t n, int tile_points) {
     if (tile_points <= 0) {
-        const char* env = getenv("SHACIRA_TILE_POINTS");
-        tile_points = env ? atoi(env) : 384;
-        if (tile_points <= 0) tile_points = 384;
+        // 2D: ~384 points per tile (tuned round 1). 3D: ~128 samples, i.e. 16 tiles per axis at the NeRF batch: the
+        // middle levels' node boxes stay small enough to live in L1 / shared memory (profiles/r02b_probe3d.jsonl)
+        const char* env = getenv(dim == 3 ? "SHACIRA_TILE_POINTS_3D" : "SHACIRA_TILE_POINTS");
+        const int dflt = dim == 3 ? 128 : 384;
+        tile_points = env ? atoi(env) : dflt;
+        if (tile_points <= 0) tile_points = dflt;
     }
     // power of two per axis, about tile_points points per tile, at most kMaxTiles tiles
     int g = 1;

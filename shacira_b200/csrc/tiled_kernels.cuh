@@ -118,8 +118,8 @@ template <int D>
 __global__ void __launch_bounds__(1024)
 plan_scatter_kernel(const float* __restrict__ coords, int64_t n, int ntiles, const int32_t* __restrict__ tile_id,
                     int32_t* __restrict__ cursor, int32_t* __restrict__ perm, float* __restrict__ coords_sorted) {
-    extern __shared__ int s_mem[];
-    int* s_hist = s_mem;            // local count per tile, then global base of this block's run
+    extern __shared__ int s_plan_mem[];
+    int* s_hist = s_plan_mem;            // local count per tile, then global base of this block's run
     for (int e = threadIdx.x; e < ntiles; e += blockDim.x) s_hist[e] = 0;
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -711,9 +711,9 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
             // (a second read of every row) is skipped. The bound of the accumulated quantity is |g| itself in
             // scatter-g mode, else |A^T g| <= max|g| * max_c sum_f |A[c][f]|.
             if (threadIdx.x < L) {
-                float m = __ldg(level_max + threadIdx.x * F);
+                float m = fabsf(__ldg(level_max + threadIdx.x * F));
 #pragma unroll
-                for (int jf = 1; jf < F; ++jf) m = fmaxf(m, __ldg(level_max + threadIdx.x * F + jf));
+                for (int jf = 1; jf < F; ++jf) m = nan_max(m, fabsf(__ldg(level_max + threadIdx.x * F + jf)));
                 if (!SG) {
                     const int la = per_level ? threadIdx.x : 0;
                     float amax = 0.0f;
@@ -762,7 +762,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                             for (int k = 0; k < KP1; ++k) {
                                 if (SG) {
 #pragma unroll
-                                    for (int jf = 0; jf < F; ++jf) m = fmaxf(m, fabsf(g[k][h][q * F + jf]));
+                                    for (int jf = 0; jf < F; ++jf) m = nan_max(m, fabsf(g[k][h][q * F + jf]));
                                 } else {
                                     const int la = per_level ? min(l, L - 1) : 0;
 #pragma unroll
@@ -771,7 +771,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
 #pragma unroll
                                         for (int jf = 0; jf < F; ++jf)
                                             acc = __fmaf_rn(g[k][h][q * F + jf], s_A[(la * C + ch) * F + jf], acc);
-                                        m = fmaxf(m, fabsf(acc));
+                                        m = nan_max(m, fabsf(acc));
                                     }
                                 }
                             }

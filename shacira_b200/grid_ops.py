@@ -29,13 +29,32 @@ _plans = OrderedDict()
 plan_stats = {"hits": 0, "builds": 0}
 
 
+PLAN_MIN_POINTS_3D = int(os.environ.get("SHACIRA_PLAN_MIN_POINTS_3D", "65536"))
+
+
+class _PlanLease:
+    """Held by an autograd ctx for as long as its graph lives: the plan cache does not re-bin a leased plan for other
+    coordinates (a second backward under retain_graph, or a backward that never runs, keep the lease -- it is released
+    when the ctx is collected, not when backward() happens to be called)."""
+
+    def __init__(self, plan):
+        self.plan = plan
+        plan.users += 1
+
+    def __del__(self):
+        try:
+            self.plan.users = max(0, self.plan.users - 1)
+        except Exception:
+            pass
+
+
 def plan_for(coords):
-    """Tile plan for `coords` ([N, 2|3] float32 contiguous CUDA) or None when planning is disabled / not worth it."""
+    """Tile plan for `coords` ([N, 2|3] float32 contiguous CUDA) or None when planning is disabled / not worth it.
+    3D sample sets (new coordinates every step) re-bin a recycled plan: ~40 us at the NeRF batch, paid back by the
+    sorted kernels from ~2^16 samples on (profiles/r02b_probe3d.jsonl)."""
     if os.environ.get("SHACIRA_DISABLE_PLAN") or coords.shape[0] < PLAN_MIN_POINTS:
         return None
-    if coords.shape[1] == 3 and not os.environ.get("SHACIRA_PLAN_3D"):
-        # measured (benchmarks/sweep.py, cfg4 shape): most 3D levels do not fit a tile's shared-memory box and
-        # the point-parallel kernels are faster there today
+    if coords.shape[1] == 3 and (os.environ.get("SHACIRA_DISABLE_PLAN_3D") or coords.shape[0] < PLAN_MIN_POINTS_3D):
         return None
     key = (coords.data_ptr(), coords._version, tuple(coords.shape), coords.device.index)
     plan = _plans.get(key)
@@ -160,8 +179,16 @@ class LatentHashGrid(torch.autograd.Function):
     def forward(ctx, coords, latents, A, shift, first_idx, resolutions, bitwidth, round_flag):
         F = A.shape[2]
         need_dec = bool(ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
-        plan = plan_for(coords) if len(resolutions) % 4 == 0 else None  # tiled kernels unroll 4 levels
-        if plan is not None:
+        dim3 = coords.shape[1] == 3
+        if dim3:  # sorted lane-pair kernels: any level count, latent_dim 1 or 2
+            plan = plan_for(coords) if latents.shape[1] in (1, 2) and latents.data_ptr() % 16 == 0 else None
+        else:
+            plan = plan_for(coords) if len(resolutions) % 4 == 0 else None  # tiled kernels unroll 4 levels
+        if plan is not None and dim3:
+            feats, z = _lib.latent_forward_planned_z(plan, latents, first_idx, resolutions, bitwidth, A, shift, F,
+                                                     round_flag, save_z=need_dec)
+            ctx.save_for_backward(coords, A.detach(), z if z is not None else coords.new_empty(0))
+        elif plan is not None:
             feats = _lib.latent_forward_planned(plan, latents, first_idx, resolutions, bitwidth, A, shift, F, round_flag)
             # the tiled backward recomputes the interpolation from the latents: nothing extra is written here
             ctx.save_for_backward(coords, A.detach(), latents.detach() if need_dec else coords.new_empty(0))
@@ -170,8 +197,7 @@ class LatentHashGrid(torch.autograd.Function):
                                            save_z=need_dec)
             ctx.save_for_backward(coords, A.detach(), z if z is not None else coords.new_empty(0))
         ctx.plan = plan
-        if plan is not None and any(ctx.needs_input_grad):
-            plan.users += 1  # released in backward; keeps the cache from recycling it under a live graph
+        ctx.lease = _PlanLease(plan) if (plan is not None and any(ctx.needs_input_grad)) else None
         ctx.round_flag = round_flag
         ctx.meta = (first_idx, tuple(resolutions), bitwidth, tuple(latents.shape), F, need_dec, shift is not None,
                     A.shape[0])
@@ -182,11 +208,13 @@ class LatentHashGrid(torch.autograd.Function):
     def backward(ctx, grad_output):
         coords, A, z = ctx.saved_tensors
         first_idx, resolutions, bitwidth, (rows, C), F, need_dec, has_shift, nA = ctx.meta
-        if ctx.plan is not None:
+        if ctx.plan is not None and coords.shape[1] == 3:
+            gl, gA, gS = _lib.latent_backward_planned_z(ctx.plan, grad_output.contiguous(), z if need_dec else None,
+                                                        first_idx, resolutions, bitwidth, A, C, F, rows, need_dec)
+        elif ctx.plan is not None:
             gl, gA, gS = _lib.latent_backward_planned(ctx.plan, grad_output.contiguous(), z if need_dec else None,
                                                       first_idx, resolutions, bitwidth, A, C, F, rows,
                                                       ctx.round_flag, need_dec)
-            ctx.plan.users = max(0, ctx.plan.users - 1)
         else:
             gl, gA, gS = _lib.latent_backward(coords, grad_output.contiguous(), z if need_dec else None, first_idx,
                                               resolutions, bitwidth, A, C, F, rows, need_dec)

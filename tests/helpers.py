@@ -73,3 +73,26 @@ def make_case(dim, L, bw, rmin, rmax, n, F, seed, coord_kind="uniform"):
     gout = rng.standard_normal((coords.shape[0], L * F)).astype(np.float32)
     return dict(dim=dim, L=L, bw=bw, resolutions=res, first_idx=first, sizes=sizes, T=T, coords=coords, table=table,
                 grad_out=gout, F=F)
+
+
+def level_rel_err(a, b, first_idx, sizes):
+    """max over levels of (max |a-b| over the level's rows) / (max |b| over the level's rows): a small gradient on a
+    fine level is not allowed to hide behind a large one on a coarse level."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    worst = 0.0
+    for f, s in zip(first_idx, sizes):
+        da, db = a[f:f + s], b[f:f + s]
+        worst = max(worst, float(np.max(np.abs(da - db)) / max(float(np.max(np.abs(db))), 1e-30)))
+    return worst
+
+
+def level_rms_err(a, b, first_idx, sizes):
+    """max over levels of rms(a-b) / rms(b)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    worst = 0.0
+    for f, s in zip(first_idx, sizes):
+        da, db = a[f:f + s], b[f:f + s]
+        worst = max(worst, float(np.sqrt(np.mean((da - db) ** 2)) / max(float(np.sqrt(np.mean(db ** 2))), 1e-30)))
+    return worst

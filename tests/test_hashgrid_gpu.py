@@ -65,7 +65,6 @@ def test_plain_forward_matches_oracle(lib, dim, L, bw, rmin, rmax, n, F):
 
 
 @pytest.mark.parametrize("dim,L,bw,rmin,rmax,n,F", PLAIN_CASES[:6])
-@pytest.mark.xfail(strict=False, reason="bit-exactness is stronger than the 1e-5 gate; reported, not required")
 def test_plain_forward_bit_exact(lib, dim, L, bw, rmin, rmax, n, F):
     c = make_case(dim, L, bw, rmin, rmax, n, F, seed=dim * 100 + F, coord_kind="arbitrary")
     want = oracle.forward(c["coords"], c["table"], c["first_idx"], c["resolutions"], bw)

@@ -164,15 +164,20 @@ def test_gradient_magnitude_extremes(lib):
     plan.close()
 
 
-def test_non_finite_upstream_gradient_propagates(lib):
+@pytest.mark.parametrize("bad", [np.inf, -np.inf, np.nan])
+@pytest.mark.parametrize("bounded", [False, True])
+def test_non_finite_upstream_gradient_propagates(lib, bad, bounded):
     """Fixed-point accumulation cannot represent Inf/NaN: the affected tile/level is poisoned with NaN, as the
-    reference's float atomics would do, instead of silently dropping the gradient."""
+    reference's float atomics would do, instead of silently dropping the gradient. NaN needs care: fmaxf() returns
+    the non-NaN operand, so the max pass (and a caller's bound) must carry it explicitly."""
     c = _case(2, 8, 12, 16, 128, 20000, 1, 1, seed=12, kind="uniform")
     coords, lat, A = _dev(c["coords"]), _dev(c["lat"]), _dev(c["A"])
     g = c["g"].copy()
-    g[123, 2] = np.inf
+    g[123, 2] = bad
     plan = lib.Plan(coords)
-    gl, _, _ = lib.latent_backward_planned(plan, _dev(g), None, c["first"], c["res"], 12, A, 1, 1, c["T"], True, False)
+    level_max = _dev(np.abs(g).max(0).astype(np.float32)) if bounded else None   # np max propagates NaN
+    gl, _, _ = lib.latent_backward_planned(plan, _dev(g), None, c["first"], c["res"], 12, A, 1, 1, c["T"], True, False,
+                                           level_max=level_max)
     a, b = c["first"][2], c["first"][3]
     assert bool(torch.isnan(gl[a:b]).any())                   # level 2 carries the poison
     assert bool(torch.isfinite(gl[:a]).all()) and bool(torch.isfinite(gl[b:]).all())
