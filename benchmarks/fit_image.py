@@ -111,13 +111,21 @@ def clamped_psnr(pred, gt):
     return 20 * np.log10(255.0) - 10 * np.log10(max(mse, 1e-12))
 
 
-def _native_setup(seed, dev, device_noise=False):
+def sga_temperature(epoch, num_epochs, end=0.1, decay_period=0.9):
+    """DecayScheduler('exp', start 1.0, end `temperature`) of the reference (utils/schedulers.py:21-23,
+    base_trainer.py:155-157): max(end, exp(-ln(1 / end) * epoch / num_epochs / decay_period))."""
+    return max(end, math.exp(-math.log(1.0 / end) * epoch / num_epochs / decay_period))
+
+
+def _native_setup(seed, dev, device_noise=False, sga=False):
     from shacira_b200.grids import LatentGrid
     from shacira_b200.image_fit import ImageFitStep
     torch.manual_seed(seed)
+    dec = dict(DEC)
+    dec["use_sga"] = bool(sga)    # kodak.yaml:43: the reference's recipe; off after decay_period (image_trainer.py:136)
     grid = LatentGrid.from_geometric(feature_dim=1, num_lods=16, latent_dim=1, multiscale_type="cat", resolution_dim=2,
                                      feature_std=0.1, codebook_bitwidth=16, min_grid_res=16, max_grid_res=512,
-                                     init_grid="uniform", conf_latent_decoder=dict(DEC), conf_entropy_reg=dict(ENT))
+                                     init_grid="uniform", conf_latent_decoder=dec, conf_entropy_reg=dict(ENT))
     mlp = nn.Sequential(nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 3))
     with torch.no_grad():
         grid.codebook.mul_(LATENT_SCALE)
@@ -141,6 +149,66 @@ def _native_metrics(seed, grid, mlp, coords, gt, fs, ms_per_step):
         n_other = sum(p.numel() for p in mlp.parameters()) + sum(p.numel() for p in grid.latent_dec.parameters())
         bpp = (latent_bits + 32 * n_other) / (H * W)
     return dict(seed=seed, psnr=psnr, bpp=bpp, latent_bits=latent_bits, ms_per_step=ms_per_step, rgb_loss=rgb_loss)
+
+
+def fit_native_recipe(seeds, steps, dev, decay_period=0.9, temperature=0.1):
+    """The reference's recipe (kodak.yaml:43-52): SGA with the exponential temperature schedule while
+    epoch / max_epochs <= decay_period, straight-through rounding afterwards; len(seeds) independent fits in flight, one
+    stream and one CUDA graph per image and PHASE (a captured graph holds its quantiser). The two phases are timed
+    separately: fits/hour weights them decay_period : 1 - decay_period."""
+    fits = [_native_setup(s, dev, device_noise=True, sga=True) for s in seeds]
+    streams = [torch.cuda.Stream(device=dev) for _ in seeds]
+    switch = int(math.floor(decay_period * steps))      # epochs 1..switch sample with SGA (epoch = it + 1)
+
+    def host_side(k, it):
+        fs = fits[k][4]
+        fs.set_lambda(1e-4 + 0.5 * (1e-3 - 1e-4) * (1 + math.cos(math.pi * it / steps)))
+        if fs.sga:
+            fs.set_temperature(sga_temperature(it + 1, steps, temperature, decay_period))
+        if it + 1 in (1, 2, 5, 10):
+            fs.update_div()
+
+    def capture():
+        graphs = []
+        for k in range(len(seeds)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=streams[k]):
+                fits[k][4].step()
+            graphs.append(g)
+        return graphs
+
+    def run(graphs, a, b):
+        for it in range(a, b):
+            for k in range(len(seeds)):
+                with torch.cuda.stream(streams[k]):
+                    host_side(k, it)
+                    graphs[k].replay()
+
+    def timed(graphs, a, b):
+        warm = min(20, max(0, (b - a) // 4))
+        run(graphs, a, a + warm)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run(graphs, a + warm, b)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / max(1, b - a - warm) * 1e3 / len(seeds)
+
+    for k in range(len(seeds)):                         # eager warm-up (allocator, plan, Adam state)
+        with torch.cuda.stream(streams[k]):
+            for it in range(3):
+                host_side(k, it)
+                fits[k][4].step()
+    torch.cuda.synchronize()
+    ms_sga = timed(capture(), 3, switch)
+    for f in fits:
+        f[4].set_sga(False)
+    ms_ste = timed(capture(), switch, steps)
+    out = []
+    for s, f in zip(seeds, fits):
+        m = _native_metrics(s, *f, decay_period * ms_sga + (1 - decay_period) * ms_ste)
+        m.update(ms_per_step_sga=ms_sga, ms_per_step_ste=ms_ste, sga_steps=switch, ste_steps=steps - switch)
+        out.append(m)
+    return out
 
 
 def fit_native_many(seeds, steps, dev, use_graph, noise_cpu):

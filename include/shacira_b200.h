@@ -272,6 +272,26 @@ int shacira_adam_step_sum(float* param, const float* grad, const float* grad2, c
                           float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
                           float weight_decay, float* step, int32_t advance, int32_t zero_grad, shacira_stream_t stream);
 
+/* The same with the grid gradient multiplied element-wise by grad_mul first (NULL: 1): the chain rule of a table-side
+ * quantiser, i.e. d w_hat / d w of shacira_sga_quantize -- the SGA backward costs no pass of its own. */
+int shacira_adam_step_sum_mul(float* param, const float* grad, const float* grad_mul, const float* grad2,
+                              const float* scale2, float scale2_mul, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
+                              int32_t advance, int32_t zero_grad, shacira_stream_t stream);
+
+/* ---- stochastic Gumbel annealing (SGA): the reference's quantiser for the first `decay_period` of training -------- */
+/* LatentDecoder.forward with use_sga (wisp/models/latent_decoders/basic_latent_decoder.py:183-191, torch's
+ * RelaxedOneHotCategorical): w_hat = floor(w) * s_0 + (floor(w) + 1) * s_1 with (s_0, s_1) a Gumbel-softmax sample at
+ * `temperature` (device float: the trainer's schedule changes it every epoch, image_trainer.py:131-133) over the
+ * logits -tanh(w - floor w) / T, -tanh(floor w + 1 - w) / T. Element-wise over `count` = rows * latent_dim values.
+ * uniforms [count, 2]: the U(0,1) draws (parity runs inject the reference's torch.rand); NULL = drawn in the kernel
+ * from a counter-based hash of (element, *rng_step, seed), *rng_step (device uint64, may be NULL) advanced by the call.
+ * w_hat feeds shacira_latent_forward* with round_flag = 0. dw (nullable) receives d w_hat / d w: the rsample
+ * derivative when diff_sampling != 0, else s_0 + s_1 (straight-through floor, sample() not differentiated). */
+int shacira_sga_quantize(const float* latents, const float* uniforms, int64_t count, const float* temperature,
+                         int32_t diff_sampling, uint64_t seed, uint64_t* rng_step, float* w_hat, float* dw,
+                         shacira_stream_t stream);
+
 /* Adam over MANY small tensors in ONE single-CTA launch (the reference's trainer steps ~20 tensors of 1..256
  * elements: decoder MLP, latent-decoder scale/shift, density-model h/b/a; wisp/trainers/base_trainer.py:206-266
  * builds their parameter groups). Per segment the gradient is

@@ -11,6 +11,9 @@ Restates, operation by operation and in the reference's order:
   size_bits                      wisp/models/grids/latent_grid.py:138-153 (use_torchac=False branch)
   symbol_stream / float_cdf      wisp/models/grids/latent_grid.py:160-169 (what is handed to torchac)
   latent_interpolate             wisp/models/grids/latent_grid.py:355-370 (decode -> repeat -> hashgrid -> [::2])
+  sga_quantize                   wisp/models/latent_decoders/basic_latent_decoder.py:183-191 with torch's
+                                 RelaxedOneHotCategorical written out (ExpRelaxedCategorical.rsample + exp), the
+                                 uniform draws passed in; pinned by tests/golden/sga_ref.npz (make_golden_sga.py)
 
 Pinned against the reference's own Python modules imported under stubs: tests/golden/make_golden.py
 writes tests/golden/latent_ref.npz, tests/test_oracle_golden.py compares.
@@ -24,6 +27,26 @@ import oracle as _o
 
 def ste_round(w):
     return torch.round(w)
+
+
+def sga_quantize(w, u, temperature, diff_sampling=True):
+    """w [T, C] (requires_grad for the derivative), u [T, C, 2] uniform draws in [0, 1). Returns w_hat [T, C];
+    autograd through it gives the reference's gradient (rsample when diff_sampling, else straight-through floor)."""
+    eps6 = 1e-6
+    wf = torch.floor(w) if diff_sampling else (w + (torch.floor(w) - w).detach())
+    wc = wf + 1
+    lf = -torch.tanh(torch.clamp(w - wf, min=-1 + eps6, max=1 - eps6)).unsqueeze(-1) / temperature
+    lc = -torch.tanh(torch.clamp(wc - w, min=-1 + eps6, max=1 - eps6)).unsqueeze(-1) / temperature
+    logits = torch.cat((lf, lc), dim=-1)
+    logits = logits - logits.logsumexp(dim=-1, keepdim=True)          # Categorical(logits=...) normalises
+    fe = torch.finfo(u.dtype).eps
+    uni = u.clamp(min=fe, max=1 - fe)                                  # clamp_probs
+    gumbels = -((-(uni.log())).log())
+    scores = (logits + gumbels) / temperature
+    sample = (scores - scores.logsumexp(dim=-1, keepdim=True)).exp()   # ExpTransform of the log-sample
+    if not diff_sampling:
+        sample = sample.detach()
+    return wf * sample[..., 0] + wc * sample[..., 1]
 
 
 def decode_single(w_hat, div, scale, shift):

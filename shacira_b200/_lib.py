@@ -69,6 +69,8 @@ SIGNATURES = {
     "shacira_mlp_mse_step_bounded": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "shacira_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _i32, _vp]),
     "shacira_adam_step_sum": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_float, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _i32, _i32, _vp]),
+    "shacira_adam_step_sum_mul": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_float, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _i32, _i32, _vp]),
+    "shacira_sga_quantize": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i32, ctypes.c_uint64, _vp, _vp, _vp, _vp]),
     "shacira_multi_adam_step": (ctypes.c_int, [_vp, _i32, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "shacira_integrate_forward": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "shacira_integrate_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -506,6 +508,28 @@ def entropy_bits_rng(latents, seed, rng_step, params, num_layers, first_idx=None
                                             _ptr(params), num_layers, fi, L, _ptr(bits), _ptr(gl), _ptr(gp),
                                             _ptr(scratch), scratch.numel(), _stream()))
     return bits, gl, gp
+
+
+def sga_quantize(latents, temperature, diff_sampling, uniforms=None, seed=0, rng_step=None, want_dw=True):
+    """SGA sample of the latents (shacira_sga_quantize): returns (w_hat, d w_hat / d w | None). `temperature`: python
+    float or device float32 scalar tensor; `uniforms` [T, C, 2] (optional): the U(0,1) draws, else drawn in the kernel."""
+    lib = load()
+    latents = _f32c(latents, "latents")
+    dev = latents.device
+    if not isinstance(temperature, torch.Tensor):
+        temperature = torch.tensor(float(temperature), dtype=torch.float32, device=dev)
+    temperature = _f32c(temperature, "temperature")
+    if uniforms is not None:
+        uniforms = _f32c(uniforms, "uniforms")
+        if uniforms.numel() != 2 * latents.numel():
+            raise ShaciraError(ERR_INVALID_ARGUMENT, "uniforms must be [T, C, 2]")
+    w_hat = torch.empty_like(latents)
+    dw = torch.empty_like(latents) if want_dw else None
+    with torch.cuda.device(dev):
+        _check(lib.shacira_sga_quantize(_ptr(latents), _ptr(uniforms), latents.numel(), _ptr(temperature),
+                                        1 if diff_sampling else 0, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(rng_step),
+                                        _ptr(w_hat), _ptr(dw), _stream()))
+    return w_hat, dw
 
 
 def mlp_mse_step(features, target, W1, b1, W2, b2, W3, b3, want_pred=False, absmax_out=None):

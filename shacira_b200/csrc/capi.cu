@@ -9,6 +9,7 @@
 #include "hashgrid_kernels.cuh"
 #include "mlp_kernels.cuh"
 #include "render_kernels.cuh"
+#include "sga_kernels.cuh"
 
 using namespace shacira;
 
@@ -566,16 +567,45 @@ int shacira_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_
 int shacira_adam_step_sum(float* param, const float* grad, const float* grad2, const float* scale2, float scale2_mul,
                           float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
                           float weight_decay, float* step, int32_t advance, int32_t zero_grad, shacira_stream_t stream) {
+    return shacira_adam_step_sum_mul(param, grad, nullptr, grad2, scale2, scale2_mul, exp_avg, exp_avg_sq, n, lr, beta1,
+                                     beta2, eps, weight_decay, step, advance, zero_grad, stream);
+}
+
+int shacira_adam_step_sum_mul(float* param, const float* grad, const float* grad_mul, const float* grad2,
+                              const float* scale2, float scale2_mul, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
+                              int32_t advance, int32_t zero_grad, shacira_stream_t stream) {
     if (!param || !grad || !exp_avg || !exp_avg_sq || !step)
         return fail(SHACIRA_ERR_INVALID_ARGUMENT, "adam_step_sum: NULL argument");
     if (n <= 0) return SHACIRA_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t blocks = (n + 1023) / 1024;
-    adam_step_sum_kernel<<<(int)blocks, 256, 0, s>>>(param, grad, grad2, scale2, scale2_mul, exp_avg, exp_avg_sq, n, lr,
-                                                     beta1, beta2, eps, weight_decay, step, zero_grad);
+    adam_step_sum_kernel<<<(int)blocks, 256, 0, s>>>(param, grad, grad_mul, grad2, scale2, scale2_mul, exp_avg, exp_avg_sq,
+                                                     n, lr, beta1, beta2, eps, weight_decay, step, zero_grad);
     LAUNCHED();
     if (advance) {
         adam_advance_kernel<<<1, 1, 0, s>>>(step);
+        LAUNCHED();
+    }
+    return SHACIRA_OK;
+}
+
+int shacira_sga_quantize(const float* latents, const float* uniforms, int64_t count, const float* temperature,
+                         int32_t diff_sampling, uint64_t seed, uint64_t* rng_step, float* w_hat, float* dw,
+                         shacira_stream_t stream) {
+    if (count < 0) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "sga_quantize: count is negative");
+    if (count == 0) return SHACIRA_OK;
+    if (!latents || !temperature || !w_hat) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "sga_quantize: NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t blocks = (count + kSgaBlock - 1) / kSgaBlock;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    sga_quantize_kernel<<<(int)blocks, kSgaBlock, 0, s>>>(latents, uniforms, count, temperature, diff_sampling,
+                                                          (unsigned long long)seed, (const unsigned long long*)rng_step,
+                                                          w_hat, dw);
+    LAUNCHED();
+    if (!uniforms && rng_step) {
+        sga_advance_kernel<<<1, 1, 0, s>>>((unsigned long long*)rng_step);
         LAUNCHED();
     }
     return SHACIRA_OK;

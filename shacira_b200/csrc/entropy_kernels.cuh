@@ -280,7 +280,8 @@ __global__ void adam_advance_kernel(float* step) { *step += 1.0f; }
 
 // grad = g + (*scale2 * mul2) * g2: the bit-rate gradient rides on the grid gradient (no pass of its own)
 __global__ void __launch_bounds__(256)
-adam_step_sum_kernel(float* __restrict__ p, const float* __restrict__ g, const float* __restrict__ g2,
+adam_step_sum_kernel(float* __restrict__ p, const float* __restrict__ g, const float* __restrict__ gmul,
+                     const float* __restrict__ g2,
                      const float* __restrict__ scale2, float mul2, float* __restrict__ m, float* __restrict__ v,
                      int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                      const float* __restrict__ step, int zero_grad) {
@@ -291,11 +292,15 @@ adam_step_sum_kernel(float* __restrict__ p, const float* __restrict__ g, const f
     const int64_t i4 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
     const bool vec = i4 + 3 < n && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
                                      reinterpret_cast<uintptr_t>(g2) | reinterpret_cast<uintptr_t>(m) |
-                                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+                                     reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(gmul)) & 15) == 0;
     if (vec) {
         float4 pp = *reinterpret_cast<float4*>(p + i4), mm = *reinterpret_cast<float4*>(m + i4);
         float4 vv = *reinterpret_cast<float4*>(v + i4);
         float4 gg = *reinterpret_cast<const float4*>(g + i4);
+        if (gmul) {   // chain rule of a table-side quantiser (SGA): grid gradient times d w_hat / d w
+            const float4 qq = *reinterpret_cast<const float4*>(gmul + i4);
+            gg.x *= qq.x; gg.y *= qq.y; gg.z *= qq.z; gg.w *= qq.w;
+        }
         if (g2) {
             const float4 hh = *reinterpret_cast<const float4*>(g2 + i4);
             gg.x = fmaf(s2, hh.x, gg.x); gg.y = fmaf(s2, hh.y, gg.y); gg.z = fmaf(s2, hh.z, gg.z); gg.w = fmaf(s2, hh.w, gg.w);
@@ -314,7 +319,8 @@ adam_step_sum_kernel(float* __restrict__ p, const float* __restrict__ g, const f
         if (zero_grad) *reinterpret_cast<float4*>(const_cast<float*>(g) + i4) = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
         for (int64_t i = i4; i < min(n, i4 + 4); ++i) {
-            const float gi = g2 ? fmaf(s2, g2[i], g[i]) : g[i];
+            const float g0 = gmul ? g[i] * gmul[i] : g[i];
+            const float gi = g2 ? fmaf(s2, g2[i], g0) : g0;
             if (zero_grad) const_cast<float*>(g)[i] = 0.0f;
             const float gk = fmaf(weight_decay, p[i], gi);
             const float mk = fmaf(beta1, m[i], (1.0f - beta1) * gk);

@@ -232,6 +232,33 @@ def latent_hashgrid(coords, latents, A, shift, first_idx, resolutions, bitwidth,
                                 list(resolutions), int(bitwidth), bool(round_flag))
 
 
+class SGAQuantize(torch.autograd.Function):
+    """Fused SGA sample of the latents (basic_latent_decoder.py:183-191): one table-side kernel produces w_hat and
+    d w_hat / d w; backward is one multiply."""
+
+    @staticmethod
+    def forward(ctx, latents, temperature, diff_sampling, uniforms, seed):
+        w_hat, dw = _lib.sga_quantize(latents, temperature, diff_sampling, uniforms=uniforms, seed=seed,
+                                      want_dw=ctx.needs_input_grad[0])
+        if dw is not None:
+            ctx.save_for_backward(dw)
+        return w_hat
+
+    @staticmethod
+    def backward(ctx, grad):
+        (dw,) = ctx.saved_tensors
+        return grad * dw, None, None, None, None
+
+
+def sga_quantize(latents, temperature, diff_sampling, uniforms=None, seed=None):
+    """latents [T, C] (CUDA) -> SGA sample w_hat [T, C]. `uniforms` [T, C, 2]: injected U(0,1) draws (parity runs);
+    otherwise the noise is drawn inside the kernel from `seed` (default: taken from torch's CPU generator, so
+    torch.manual_seed makes runs repeatable)."""
+    if seed is None and uniforms is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return SGAQuantize.apply(latents, temperature, bool(diff_sampling), uniforms, seed or 0)
+
+
 class EntropyBits(torch.autograd.Function):
     """Fused LatentGrid.ent_loss body (latent_grid.py:132-135): total bits of the factorized density.
     The kernel produces value and gradients in one pass; backward only scales them."""

@@ -36,14 +36,13 @@ class ImageFitStep:
     def __init__(self, grid, mlp, coords, target, lr=1e-3, grid_lr=2e-2, ldec_lr=1e-2, prob_lr=1e-4,
                  weight_decay=0.0, weight_decay_decoder=1e-2, betas=(0.9, 0.999), eps=1e-8, device_noise=False,
                  noise_seed=0):
-        """`grid`: shacira_b200.grids.LatentGrid (2D, single affine decoder, STE rounding); `mlp`:
+        """`grid`: shacira_b200.grids.LatentGrid (2D, single affine decoder; SGA sampling or STE rounding as the decoder's
+        `use_sga` says -- see set_sga / set_temperature); `mlp`:
         nn.Sequential(Linear(L*F,16), ReLU, Linear(16,16), ReLU, Linear(16,3)); coords [N,2], target [N,3].
         Learning rates / weight decays: the reference's parameter groups (base_trainer.py:219-239; kodak.yaml:61-70).
         device_noise=True draws the bit-rate noise inside the kernel (fresh on every step, also under graph replay:
         `draw_noise` is then unnecessary); False reads `self.noise`, which `draw_noise` fills (parity runs)."""
         dec = grid.latent_dec
-        if getattr(dec, "use_sga", False):
-            raise _lib.ShaciraError(_lib.ERR_UNSUPPORTED, "ImageFitStep: SGA sampling runs on the PyTorch path")
         amap = dec.affine_map() if hasattr(dec, "affine_map") else None
         if amap is None or amap[0].shape[0] != 1 or "dft" in dec.layers[0].ldecode_matrix:
             raise _lib.ShaciraError(_lib.ERR_UNSUPPORTED, "ImageFitStep: needs ONE affine 'sq' latent decoder")
@@ -108,6 +107,16 @@ class ImageFitStep:
         self.lam = torch.zeros((), **f32)
         self.device_noise, self.noise_seed = bool(device_noise), int(noise_seed)
         self.rng_step = torch.zeros((), dtype=torch.int64, device=dev)
+        # SGA (basic_latent_decoder.py:183-191): the reference's quantiser until epoch / max_epochs > decay_period
+        # (image_trainer.py:136-137). One table-side kernel per step writes w_hat (what the grid kernels interpolate,
+        # rounding off) and d w_hat / d w (multiplied into the grid gradient inside the table's Adam kernel).
+        self.sga = bool(getattr(dec, "use_sga", False))
+        self.diff_sampling = bool(getattr(dec, "diff_sampling", True))
+        self.temperature = torch.full((), float(getattr(dec, "temperature", 1.0)), **f32)
+        self.w_hat = torch.empty((self.T, self.C), **f32)
+        self.dw = torch.empty((self.T, self.C), **f32)
+        self.sga_uniforms = None     # [T, C, 2]: injected draws (parity runs); None = drawn in the kernel
+        self.sga_rng_step = torch.zeros((), dtype=torch.int64, device=dev)
         self.ent_scratch = torch.zeros(int(_lib.load().shacira_entropy_scratch_bytes(self.C, self.L)),
                                        dtype=torch.uint8, device=dev)
         # Adam state
@@ -179,6 +188,17 @@ class ImageFitStep:
     def set_lambda(self, value):
         self.lam.fill_(float(value))
 
+    def set_temperature(self, value):
+        """SGA temperature of this epoch (image_trainer.py:131-133; base_trainer.py:155-157 builds the schedule)."""
+        self.temperature.fill_(float(value))
+        self.grid.latent_dec.temperature = float(value)
+
+    def set_sga(self, flag):
+        """Switch between SGA and straight-through rounding (the trainer turns SGA off once epoch / max_epochs >
+        decay_period). A captured CUDA graph holds the mode it was captured with: re-capture after switching."""
+        self.sga = bool(flag)
+        self.grid.latent_dec.use_sga = bool(flag)
+
     def draw_noise(self, generator=None):
         """U(-0.5, 0.5) per latent (latent_grid.py:128); with a CPU generator the reference's stream."""
         if generator is not None:
@@ -215,8 +235,14 @@ class ImageFitStep:
                                                  self.num_prob_layers, self.fi, self.L, P(self.bits), P(self.g_ent),
                                                  P(self.g_prob), P(self.ent_scratch), self.ent_scratch.numel(),
                                                  _lib._stream()))
-            chk(lib.shacira_latent_forward_planned(self.plan.handle, P(lat), self.fi, self.rs, self.L, self.bw, self.C,
-                                                   self.F, 1, P(self.A), P(shift), 0, P(self.feats), st))
+            q_lat, rflag, gmul = lat, 1, None
+            if self.sga:
+                chk(lib.shacira_sga_quantize(P(lat), P(self.sga_uniforms), self.T * self.C, P(self.temperature),
+                                             1 if self.diff_sampling else 0, self.noise_seed + 0x5A17,
+                                             P(self.sga_rng_step), P(self.w_hat), P(self.dw), st))
+                q_lat, rflag, gmul = self.w_hat, 0, self.dw
+            chk(lib.shacira_latent_forward_planned(self.plan.handle, P(q_lat), self.fi, self.rs, self.L, self.bw, self.C,
+                                                   self.F, rflag, P(self.A), P(shift), 0, P(self.feats), st))
             # the MLP kernel reduces max |feature gradient| per column on the way; the tiled backward takes its
             # fixed-point scales from that bound and skips its own pass over the gradient rows
             bound = P(self.gfeat_max) if self.use_bound else None
@@ -227,15 +253,15 @@ class ImageFitStep:
             if not self.has_shift:
                 self.g_dec[self.L * self.C * self.F:].zero_()   # no segment consumes (and clears) the shift rows
             CF = self.C * self.F
-            chk(lib.shacira_latent_backward_planned_bounded(self.plan.handle, P(self.gfeat), P(lat), self.fi, self.rs,
-                                                            self.L, self.bw, self.C, self.F, 1, P(self.A), 0, self.T, 0,
+            chk(lib.shacira_latent_backward_planned_bounded(self.plan.handle, P(self.gfeat), P(q_lat), self.fi, self.rs,
+                                                            self.L, self.bw, self.C, self.F, rflag, P(self.A), 0, self.T, 0,
                                                             P(self.g_grid), P(self.g_dec), P(self.g_dec[self.L * CF:]),
                                                             bound, st))
             cur.wait_stream(self.side)
-            chk(lib.shacira_adam_step_sum(P(lat), P(self.g_grid), P(self.g_ent), P(self.lam), 1.0 / self.T,
-                                          P(self.m_table), P(self.v_table), self.T * self.C, self.grid_lr,
-                                          self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                          P(self.step_table), 0, 1, st))
+            chk(lib.shacira_adam_step_sum_mul(P(lat), P(self.g_grid), P(gmul), P(self.g_ent), P(self.lam), 1.0 / self.T,
+                                              P(self.m_table), P(self.v_table), self.T * self.C, self.grid_lr,
+                                              self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                              P(self.step_table), 0, 1, st))
             chk(lib.shacira_multi_adam_step(ctypes.cast(self.segs, ctypes.c_void_p), self.nseg, self.betas[0],
                                             self.betas[1], self.eps, P(self.step_small), P(self.step_table),
                                             P(self.layer.scale.data), P(dec.div.data), P(self.A), self.C, self.F,

@@ -66,10 +66,15 @@ def _activation(name):
     return table[name]()
 
 
-def sga_quantize(weight, temperature, diff_sampling):
-    """Stochastic Gumbel annealing between floor and ceil (basic_latent_decoder.py:183-191).
-    Table-side PyTorch pre-pass: it is RNG-bound and only active for the first `decay_period`
-    of training; its output feeds the fused kernel with rounding disabled."""
+def sga_quantize(weight, temperature, diff_sampling, uniforms=None):
+    """Stochastic Gumbel annealing between floor and ceil (basic_latent_decoder.py:183-191), active for the first
+    `decay_period` of training (every shipped yaml: use_sga True, decay_period 0.9). CUDA tensors take the fused
+    table-side kernel (shacira_sga_quantize: value + derivative in one pass, noise drawn in the kernel or injected
+    through `uniforms` [T, C, 2]); its output feeds the fused grid kernels with rounding disabled. The torch
+    expression below is the definition (host tensors, multi decoder)."""
+    if weight.is_cuda and weight.dtype == torch.float32:
+        from . import grid_ops
+        return grid_ops.sga_quantize(weight, temperature, diff_sampling, uniforms=uniforms)
     wf = torch.floor(weight) if diff_sampling else StraightThroughFloor.apply(weight)
     wc = wf + 1
     lo, hi = -1 + epsilon, 1 - epsilon
@@ -166,6 +171,7 @@ class LatentDecoder(nn.Module):
         layers.append(DecoderLayer(width, feature_dim, ldecode_matrix, bias=use_shift))
         self.use_sga = use_sga
         self.temperature = 1.0
+        self.sga_uniforms = None   # [T, C, 2] U(0,1) draws to use instead of fresh noise (parity tests)
         self.layers = nn.Sequential(*layers)
         self.reset_parameters("normal", ldec_std)
         self.diff_sampling = diff_sampling
@@ -215,7 +221,7 @@ class LatentDecoder(nn.Module):
     def quantize(self, weight):
         """Latents as the decoder sees them: SGA mix or straight-through round."""
         if self.use_sga:
-            return sga_quantize(weight, self.temperature, self.diff_sampling)
+            return sga_quantize(weight, self.temperature, self.diff_sampling, getattr(self, "sga_uniforms", None))
         return StraightThrough.apply(weight)
 
     def forward(self, weight):

@@ -1,5 +1,7 @@
 """The CPU oracle against the golden vectors produced by the reference's own Python modules
 (tests/golden/make_golden.py). CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -226,3 +228,21 @@ def test_voxel_sample_oracle_matches_the_reference_sampling_helpers():
         # deltas telescope back to the depths; samples lie on their rays
         assert np.allclose(depth[:, 0] + deltas.reshape(-1, K).sum(1), ds.reshape(-1, K)[:, -1], rtol=1e-5)
         assert np.allclose(samples, o[ridx_out] + d[ridx_out] * ds[:, None], rtol=1e-6, atol=1e-6)
+
+
+def _sga_golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sga_ref.npz"))
+
+
+@pytest.mark.parametrize("name", ["t1.0_diff", "t0.37_diff_c2", "t0.1_diff", "t0.5_nodiff", "t0.05_diff_c4"])
+def test_sga_oracle_matches_the_reference_decoder(name):
+    """oracle.sga_quantize on the recorded uniform draws == the reference's LatentDecoder.forward(use_sga) output and
+    its autograd gradient (same torch CPU ops in the same order: bit for bit)."""
+    g = _sga_golden()
+    p = "dec/" + name + "/"
+    T, C, diff = [int(v) for v in g[p + "meta"]]
+    w = torch.from_numpy(g[p + "w"]).clone().requires_grad_(True)
+    w_hat = lo.sga_quantize(w, torch.from_numpy(g[p + "u"]), float(g[p + "tau"][0]), bool(diff))
+    assert np.array_equal(w_hat.detach().numpy(), g[p + "w_hat"])
+    (w_hat * torch.from_numpy(g[p + "gout"])).sum().backward()
+    assert np.allclose(w.grad.numpy(), g[p + "grad_w"], rtol=1e-6, atol=1e-7 * np.abs(g[p + "grad_w"]).max())
