@@ -1,12 +1,15 @@
 """NeRF-shape ray-batch data parallel step (BASELINE cfg4): 3D LatentGrid, 16 levels 16->2048, 2^19-row tables,
 C=1 -> F=4; 4096 rays x 128 samples (8 cells x 16 steps, synthetic sampler: kaolin's raymarcher is out of scope)
-per rank and step; forward + backward of the grid, then the ONE exchange step of the path: NCCL SUM all-reduce of
-grad(latents) (24 MB fp32) plus a flat bucket with the decoder gradients.
+per rank and step. One step = re-bin this step's samples (plan rebuild) -> forward -> backward (latents + decoder
+gradients), then the ONE exchange step of the path: NCCL SUM all-reduce of one flat gradient arena (grad(latents)
+24 MB fp32 + the decoder gradients).
 
     python benchmarks/nerf_dp.py                                   # 1 GPU
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 benchmarks/nerf_dp.py
 
-Weak scaling (4096 rays per rank). Device timing (CUDA events), barrier on both sides, max over ranks."""
+Weak scaling (4096 rays per rank). Device timing (CUDA events), barrier on both sides, max over ranks. The samples of
+step i+1 do not depend on step i's parameters, so their binning runs on a side stream while step i's gradients are
+exchanged (two plans, double buffered): the all-reduce hides it. `run()` is what bench.py calls."""
 import ctypes
 import json
 import os
@@ -17,7 +20,6 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench  # noqa: E402
 from shacira_b200 import _lib, dp  # noqa: E402
 from shacira_b200.grids import geometric_resolutions  # noqa: E402
 
@@ -25,18 +27,13 @@ RAYS, SAMPLES_PER_RAY = 4096, 128
 L, BW, C, F = 16, 19, 1, 4
 
 
-def main():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    steps, warmup, sets_n = 30, 5, 4
-    chunks = 1
-    if "--chunks" in sys.argv:
-        chunks = int(sys.argv[sys.argv.index("--chunks") + 1])
+def algorithmic_bytes_per_sample():
+    """fwd [4D + 2^D L C 4 + 4 L F] + bwd [same] for D = 3."""
+    one = 4 * 3 + 8 * L * C * 4 + 4 * L * F
+    return 2 * one
+
+
+def run(dev, rank, world, steps=30, warmup=5, planned=True, overlap_binning=True, sets_n=4):
     res = geometric_resolutions(16, 2048, L)
     sizes = [min(2 ** BW, r ** 3) for r in res]
     first = [0]
@@ -60,94 +57,103 @@ def main():
     fi, _ = _lib._i32_array(first)
     rs, _ = _lib._i32_array(res)
     P = _lib._ptr
+    plans = [_lib.Plan(sets[0]["coords"]), _lib.Plan(sets[1 % sets_n]["coords"])] if planned else None
+    side = torch.cuda.Stream(device=dev)
+    binned = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    # level chunks with about equal numbers of rows: [level_lo, level_hi), flat range of the rows in the arena
-    bounds = [0]
-    for k in range(1, chunks):
-        tgt = T * k // chunks
-        l = min(range(1, L), key=lambda l_: abs(first[l_] - tgt))
-        bounds.append(max(l, bounds[-1] + 1))
-    bounds.append(L)
-    spans = []
-    for k in range(chunks):
-        lo, hi = bounds[k], bounds[k + 1]
-        mask = sum(1 << l for l in range(lo, hi))
-        r0 = first[lo] * C
-        r1 = (first[hi] * C) if hi < L else arena.flat.numel()      # the last chunk carries the decoder gradients too
-        spans.append((mask, r0, r1))
+    def bin_samples(i, stream):
+        """Re-bin the samples of step i into plan i % 2 on `stream` (3 small kernels, allocation reused)."""
+        st = ctypes.c_void_p(stream.cuda_stream)
+        _lib._check(lib.shacira_plan_rebuild(plans[i % 2].handle, 3, P(sets[i % sets_n]["coords"]), S, 0, st))
 
-    def step_chunked(i):
-        """Backward in level chunks; the all-reduce of a chunk's rows is in flight while the next chunk computes."""
+    def step(i, exchange=True):
         s = sets[i % sets_n]
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib._check(lib.shacira_latent_forward(3, P(s["coords"]), S, P(lat), fi, rs, L, BW, C, F, 1, P(A), P(shift), 0,
-                                               P(feats), P(z), st))
-        gA.grad.zero_()
-        gS.grad.zero_()
-        handles = []
-        for k, (mask, r0, r1) in enumerate(spans):
-            _lib._check(lib.shacira_latent_backward_levels(3, P(s["coords"]), S, P(s["g"]), P(z), fi, rs, L, BW, C, F, P(A),
-                                                           0, T, 1 if k == 0 else 0, mask, P(glat.grad), P(gA.grad),
-                                                           P(gS.grad), st))
-            if world > 1:
-                handles.append(dist.all_reduce(arena.flat[r0:r1], op=dist.ReduceOp.SUM, async_op=True))
-        for h in handles:
-            h.wait()
-        return len(handles)
-
-    planned = "--unplanned" not in sys.argv
-    plan = _lib.Plan(sets[0]["coords"]) if planned else None
-
-    def step(i):
-        if chunks > 1:
-            return step_chunked(i)
-        s = sets[i % sets_n]
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        cur = torch.cuda.current_stream(dev)
+        st = ctypes.c_void_p(cur.cuda_stream)
         if planned:
-            # the samples are new every step: re-bin them (3 small kernels, allocation reused), then the sorted kernels
-            _lib._check(lib.shacira_plan_rebuild(plan.handle, 3, P(s["coords"]), S, 0, st))
+            plan = plans[i % 2]
+            if overlap_binning and i > 0 and step.prebinned == i:
+                cur.wait_event(binned[i % 2])           # binned on the side stream during the previous exchange
+            else:
+                bin_samples(i, cur)
             _lib._check(lib.shacira_latent_forward_planned_z(plan.handle, P(lat), fi, rs, L, BW, C, F, 1, P(A), P(shift), 0,
                                                              P(feats), P(z), st))
             arena.zero_()   # one memset: table gradient + decoder gradients
             _lib._check(lib.shacira_latent_backward_planned_z(plan.handle, P(s["g"]), P(z), fi, rs, L, BW, C, F, P(A), 0,
                                                               T, 0, P(glat.grad), P(gA.grad), P(gS.grad), st))
-            return arena.allreduce()
-        _lib._check(lib.shacira_latent_forward(3, P(s["coords"]), S, P(lat), fi, rs, L, BW, C, F, 1, P(A), P(shift), 0,
-                                               P(feats), P(z), st))
-        gA.grad.zero_()
-        gS.grad.zero_()
-        _lib._check(lib.shacira_latent_backward(3, P(s["coords"]), S, P(s["g"]), P(z), fi, rs, L, BW, C, F, P(A), 0, T, 1,
-                                                P(glat.grad), P(gA.grad), P(gS.grad), st))
-        return arena.allreduce()
+            if overlap_binning:
+                # step i + 1's samples do not depend on this step's parameters: bin them beside the exchange. The other
+                # plan was last used by step i - 1, whose kernels are ordered before this point on `cur`.
+                freed[(i + 1) % 2].record(cur)
+                side.wait_event(freed[(i + 1) % 2])
+                bin_samples(i + 1, side)
+                binned[(i + 1) % 2].record(side)
+                step.prebinned = i + 1
+        else:
+            _lib._check(lib.shacira_latent_forward(3, P(s["coords"]), S, P(lat), fi, rs, L, BW, C, F, 1, P(A), P(shift), 0,
+                                                   P(feats), P(z), st))
+            arena.zero_()
+            _lib._check(lib.shacira_latent_backward(3, P(s["coords"]), S, P(s["g"]), P(z), fi, rs, L, BW, C, F, P(A), 0, T, 0,
+                                                    P(glat.grad), P(gA.grad), P(gS.grad), st))
+        return arena.allreduce() if exchange else 0
 
-    for i in range(warmup):
-        ncoll = step(i)
-    torch.cuda.synchronize()
+    step.prebinned = -1
+
+    def timed(exchange):
+        step.prebinned = -1
+        for i in range(warmup):
+            step(i, exchange)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(warmup, warmup + steps):
+            ncoll = step(i, exchange)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps, ncoll
+
+    ms, ncoll = timed(True)
+    ms_compute = ms
     if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        step(i)
-    e1.record()
-    torch.cuda.synchronize()
+        ms_compute, _ = timed(False)      # the same step without the exchange: the difference is the exposed collective
+    if planned:
+        for p in plans:
+            p.close()
+    bps = algorithmic_bytes_per_sample()
+    return {"workload": "BASELINE cfg4 NeRF-shape ray-batch DP step (re-bin + grid fwd + bwd + grad all-reduce)",
+            "n_gpus": world, "scaling": "weak", "rays_per_rank": RAYS, "samples_per_rank": S,
+            "ms_per_step": ms, "samples_per_s": S * world / ms * 1e3, "rays_per_s": RAYS * world / ms * 1e3,
+            "allreduce_bytes": arena.flat.numel() * 4, "collectives_per_step": ncoll,
+            "ms_per_step_without_exchange": ms_compute, "exposed_collective_us": max(0.0, (ms - ms_compute) * 1e3),
+            "bytes_per_sample": bps, "alg_GBs_per_gpu": bps * S / ms / 1e6,
+            "binning": ("next step's samples binned beside the exchange (side stream)" if (planned and overlap_binning)
+                        else ("in line" if planned else "none")),
+            "path": "plan re-binned per step + sorted lane-pair kernels + tile-staged coarse levels" if planned
+                    else "unsorted lane-pair kernels + whole-level shared-memory coarse path"}
+
+
+def main():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item()) / steps
+        dist.init_process_group("nccl", device_id=dev)
+    r = run(dev, rank, world, planned="--unplanned" not in sys.argv, overlap_binning="--no-overlap" not in sys.argv)
     if rank == 0:
-        bf, bb = bench.algorithmic_bytes_per_point(3, L, C, F)
+        import bench
         peak, _ = bench.measured_peaks()
-        print(json.dumps({"workload": "BASELINE cfg4 NeRF-shape ray-batch DP step (grid fwd+bwd + grad all-reduce)",
-                          "n_gpus": world, "scaling": "weak", "rays_per_rank": RAYS, "samples_per_rank": S,
-                          "ms_per_step": ms, "samples_per_s": S * world / ms * 1e3, "rays_per_s": RAYS * world / ms * 1e3,
-                          "allreduce_bytes": T * C * 4, "collectives_per_step": ncoll,
-                          "alg_GBs_per_gpu": (bf + bb) * S / ms / 1e6, "frac_hbm_peak": (bf + bb) * S / ms / 1e6 / peak,
-                          "backward_level_chunks": chunks,
-                          "path": "plan re-binned per step + sorted lane-pair kernels + tile-staged coarse levels" if planned
-                          else "unsorted lane-pair kernels + whole-level shared-memory coarse path"}), flush=True)
+        r["frac_hbm_peak"] = r["alg_GBs_per_gpu"] / peak
+        print(json.dumps(r), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -398,6 +398,29 @@ int shacira_latent_step_host(int32_t dim, const float* coords, int64_t n, const 
                              const float* A, const float* shift, int32_t per_level, const float* grad_output,
                              float* feats, float* grad_latents);
 
+/* Host-buffer SESSION: the same step for a caller that runs many steps over ONE coordinate set (an image fit:
+ * static coordinates, image_trainer.py:234-266), pipelined two steps deep. The coordinates and their spatial plan stay
+ * on the device (set_coords: upload + binning, once); the table and decoder are uploaded when the host changed them
+ * (set_table, ordered after the kernels in flight that read the old values); step_async enqueues
+ *   upload(grad_output) | forward -> download(feats) | backward -> download(grad_latents, grad_A, grad_shift)
+ * on three streams over two slots of device buffers and returns at once with the slot it used: the upload of step
+ * i+1 and the downloads of step i use both PCIe directions at the same time. The host buffers of a slot (ideally
+ * pinned) are complete after session_wait(slot) and must not be reused before. grad_A [L, C, F] / grad_shift [L, F]
+ * (nullable) as in shacira_latent_backward_planned (2D tiled path; with one shared decoder only the sum over the L
+ * rows is defined). */
+typedef struct shacira_host_session shacira_host_session_t;
+int shacira_host_session_create(int32_t dim, int64_t n, int64_t table_rows, const int32_t* first_idx,
+                                const int32_t* resolutions, int32_t num_lods, int32_t codebook_bitwidth,
+                                int32_t latent_dim, int32_t feature_dim, int32_t per_level,
+                                shacira_host_session_t** session);
+int shacira_host_session_destroy(shacira_host_session_t* session);
+int shacira_host_session_set_coords(shacira_host_session_t* session, const float* coords);
+int shacira_host_session_set_table(shacira_host_session_t* session, const float* latents, const float* A,
+                                   const float* shift, int32_t round_flag);
+int shacira_host_session_step_async(shacira_host_session_t* session, const float* grad_output, float* feats,
+                                    float* grad_latents, float* grad_A, float* grad_shift, int32_t* slot);
+int shacira_host_session_wait(shacira_host_session_t* session, int32_t slot);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,12 @@ SIGNATURES = {
     "shacira_ac_encode": (_i64, [_vp, _i64, _vp, _i32, _vp, _i64]),
     "shacira_ac_decode": (ctypes.c_int, [_vp, _i64, _vp, _i32, _vp, _i64]),
     "shacira_latent_step_host": (ctypes.c_int, [_i32, _vp, _i64, _vp, _i64, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "shacira_host_session_create": (ctypes.c_int, [_i32, _i64, _i64, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _i32, _i32, ctypes.POINTER(_vp)]),
+    "shacira_host_session_destroy": (ctypes.c_int, [_vp]),
+    "shacira_host_session_set_coords": (ctypes.c_int, [_vp, _vp]),
+    "shacira_host_session_set_table": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32]),
+    "shacira_host_session_step_async": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int32_p]),
+    "shacira_host_session_wait": (ctypes.c_int, [_vp, _i32]),
 }
 
 _lib = None
@@ -606,6 +612,69 @@ def latent_step_host(coords, latents, first_idx, resolutions, bitwidth, A, shift
                                         1 if round_flag else 0, _ptr(A), _ptr(shift), per_level, _ptr(grad_output),
                                         _ptr(feats_out), _ptr(grad_latents_out)))
     return feats_out, grad_latents_out
+
+
+class HostSession:
+    """Host-buffer session (shacira_host_session_*): fused latent fwd + bwd steps over one coordinate set with every
+    array in (pinned) host memory, pipelined two steps deep. `step()` returns the slot whose host buffers it will fill;
+    `wait(slot)` blocks until they are complete."""
+
+    def __init__(self, coords, table_rows, first_idx, resolutions, bitwidth, latent_dim, feature_dim, per_level=False,
+                 device=None):
+        lib = load()
+        self._check_host(coords, "coords")
+        self.dim = _dim_of(coords)
+        self.n, self.T, self.C, self.F = coords.shape[0], int(table_rows), int(latent_dim), int(feature_dim)
+        fi, self.L = _i32_array(first_idx)
+        rs, _ = _i32_array(resolutions)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        handle = ctypes.c_void_p(0)
+        with torch.cuda.device(self.device):
+            _check(lib.shacira_host_session_create(self.dim, self.n, self.T, fi, rs, self.L, int(bitwidth), self.C, self.F,
+                                                   1 if per_level else 0, ctypes.byref(handle)))
+            self.handle = handle
+            _check(lib.shacira_host_session_set_coords(self.handle, _ptr(coords)))
+        self._keep = [coords]
+
+    @staticmethod
+    def _check_host(t, name):
+        if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
+            raise ShaciraError(ERR_INVALID_ARGUMENT, "%s must be a contiguous float32 HOST tensor" % name)
+
+    def set_table(self, latents, A, shift=None, round_flag=True):
+        for name, t in (("latents", latents), ("A", A), ("shift", shift)):
+            self._check_host(t, name)
+        with torch.cuda.device(self.device):
+            _check(load().shacira_host_session_set_table(self.handle, _ptr(latents), _ptr(A), _ptr(shift),
+                                                         1 if round_flag else 0))
+        self._keep_table = (latents, A, shift)
+
+    def step(self, grad_output, feats_out, grad_latents_out, grad_A_out=None, grad_shift_out=None):
+        for name, t in (("grad_output", grad_output), ("feats_out", feats_out), ("grad_latents_out", grad_latents_out),
+                        ("grad_A_out", grad_A_out), ("grad_shift_out", grad_shift_out)):
+            self._check_host(t, name)
+        slot = ctypes.c_int32(-1)
+        with torch.cuda.device(self.device):
+            _check(load().shacira_host_session_step_async(self.handle, _ptr(grad_output), _ptr(feats_out),
+                                                          _ptr(grad_latents_out), _ptr(grad_A_out), _ptr(grad_shift_out),
+                                                          ctypes.byref(slot)))
+        return slot.value
+
+    def wait(self, slot):
+        with torch.cuda.device(self.device):
+            _check(load().shacira_host_session_wait(self.handle, int(slot)))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            with torch.cuda.device(self.device):
+                load().shacira_host_session_destroy(self.handle)
+            self.handle = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def ac_encode(symbols, cdf):

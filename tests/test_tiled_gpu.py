@@ -344,3 +344,41 @@ def test_drop_in_entry_points_take_the_tiled_path_for_large_2d_batches(lib):
     builds = grid_ops.plan_stats["builds"]
     small = ops.hashgrid_interpolate2d_cuda(coords[:1000].contiguous(), table, first, c["res"], 16)
     assert grid_ops.plan_stats["builds"] == builds and torch.equal(small, want[:1000])
+
+
+def test_host_session_pipelined_steps_match_device_calls(lib):
+    """shacira_host_session_*: host buffers in and out, two steps in flight, tables that change between steps: every
+    step's features, table gradient and decoder gradients equal the device-tensor calls on the same inputs."""
+    c = _case(2, 16, 16, 16, 512, 40000, 1, 1, seed=21, kind="uniform")
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    coords = pin(c["coords"])
+    sess = lib.HostSession(coords, c["T"], c["first"], c["res"], 16, 1, 1)
+    rng = np.random.default_rng(0)
+    K = 5
+    lats = [pin(c["lat"] + rng.standard_normal(c["lat"].shape).astype(np.float32) * k) for k in range(K)]
+    gouts = [pin(rng.standard_normal(c["g"].shape).astype(np.float32)) for _ in range(K)]
+    A, S = pin(c["A"]), pin(c["S"])
+    feats = [torch.empty(c["g"].shape, dtype=torch.float32).pin_memory() for _ in range(K)]
+    gls = [torch.empty(c["lat"].shape, dtype=torch.float32).pin_memory() for _ in range(K)]
+    gAs = [torch.empty((16, 1, 1), dtype=torch.float32).pin_memory() for _ in range(K)]
+    gSs = [torch.empty((16, 1), dtype=torch.float32).pin_memory() for _ in range(K)]
+    slots = []
+    for k in range(K):
+        sess.set_table(lats[k], A, S, True)
+        slots.append(sess.step(gouts[k], feats[k], gls[k], gAs[k], gSs[k]))
+        if k >= 1:
+            sess.wait(slots[k - 1])
+    sess.wait(slots[-1])
+    assert slots == [0, 1, 0, 1, 0]
+    dcoords, dA, dS = coords.cuda(), A.cuda(), S.cuda()
+    plan = lib.Plan(dcoords)
+    for k in range(K):
+        f = lib.latent_forward_planned(plan, lats[k].cuda(), c["first"], c["res"], 16, dA, dS, 1, True)
+        gl, gA, gS = lib.latent_backward_planned(plan, gouts[k].cuda(), lats[k].cuda(), c["first"], c["res"], 16, dA, 1, 1,
+                                                 c["T"], True, True)
+        assert torch.equal(feats[k], f.cpu())
+        assert rel_err(gls[k].numpy(), gl.cpu().numpy()) <= 1e-6   # nodes shared by two tiles: float reds in either order
+        assert rel_err(gAs[k].numpy().sum(0), gA.cpu().numpy().sum(0)) <= 1e-5
+        assert rel_err(gSs[k].numpy().sum(0), gS.cpu().numpy().sum(0)) <= 1e-5
+    plan.close()
+    sess.close()
