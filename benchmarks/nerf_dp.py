@@ -33,7 +33,7 @@ def algorithmic_bytes_per_sample():
     return 2 * one
 
 
-def run(dev, rank, world, steps=30, warmup=5, planned=True, overlap_binning=True, sets_n=4):
+def run(dev, rank, world, steps=30, warmup=5, planned=True, overlap_binning=True, sets_n=4, entropy=True):
     res = geometric_resolutions(16, 2048, L)
     sizes = [min(2 ** BW, r ** 3) for r in res]
     first = [0]
@@ -52,7 +52,16 @@ def run(dev, rank, world, steps=30, warmup=5, planned=True, overlap_binning=True
     glat = torch.nn.Parameter(torch.zeros((T, C), device=dev))
     gA = torch.nn.Parameter(torch.zeros((L, C, F), device=dev))
     gS = torch.nn.Parameter(torch.zeros((L, F), device=dev))
-    arena = dp.GradArena([glat, gA, gS])     # one flat gradient buffer: the exchange step is ONE all-reduce
+    # bit-rate loss (multiview_trainer.py:110 calls ent_loss with is_val = pipeline.training, SURVEY Q8: the NeRF recipe
+    # evaluates it on round(w), so only the density model receives a gradient). It is a sum over table rows: every rank
+    # takes a slice (dp.shard_rows), its bits and density-model gradients ride in the same arena and the all-reduce adds
+    # the slices -- no second collective, and 1/N of the table-side work per rank.
+    gprob = torch.nn.Parameter(torch.zeros((4, 3, C), device=dev))
+    gbits = torch.nn.Parameter(torch.zeros((1,), device=dev))
+    prob = torch.randn((4, 3, C), device=dev) * 0.3
+    r0, r1 = dp.shard_rows(T, rank, world)
+    ent_stream = torch.cuda.Stream(device=dev)
+    arena = dp.GradArena([glat, gA, gS, gprob, gbits])     # one flat gradient buffer: the exchange step is ONE all-reduce
     lib = _lib.load()
     fi, _ = _lib._i32_array(first)
     rs, _ = _lib._i32_array(res)
@@ -71,6 +80,14 @@ def run(dev, rank, world, steps=30, warmup=5, planned=True, overlap_binning=True
         s = sets[i % sets_n]
         cur = torch.cuda.current_stream(dev)
         st = ctypes.c_void_p(cur.cuda_stream)
+        arena.zero_()   # one memset: table gradient + decoder / density-model gradients + the bits
+        if entropy and r1 > r0:
+            # this rank's slice of the table on its own stream, beside the grid kernels (it only reads the table)
+            ent_stream.wait_stream(cur)
+            with torch.cuda.stream(ent_stream):
+                bits, _, gp = _lib.entropy_bits(lat[r0:r1], None, prob, 1, None, want_grads=True)
+                gprob.grad.copy_(gp)
+                gbits.grad.copy_(bits[:1].to(torch.float32))
         if planned:
             plan = plans[i % 2]
             if overlap_binning and i > 0 and step.prebinned == i:
@@ -79,7 +96,6 @@ def run(dev, rank, world, steps=30, warmup=5, planned=True, overlap_binning=True
                 bin_samples(i, cur)
             _lib._check(lib.shacira_latent_forward_planned_z(plan.handle, P(lat), fi, rs, L, BW, C, F, 1, P(A), P(shift), 0,
                                                              P(feats), P(z), st))
-            arena.zero_()   # one memset: table gradient + decoder gradients
             _lib._check(lib.shacira_latent_backward_planned_z(plan.handle, P(s["g"]), P(z), fi, rs, L, BW, C, F, P(A), 0,
                                                               T, 0, P(glat.grad), P(gA.grad), P(gS.grad), st))
             if overlap_binning:
@@ -93,9 +109,10 @@ def run(dev, rank, world, steps=30, warmup=5, planned=True, overlap_binning=True
         else:
             _lib._check(lib.shacira_latent_forward(3, P(s["coords"]), S, P(lat), fi, rs, L, BW, C, F, 1, P(A), P(shift), 0,
                                                    P(feats), P(z), st))
-            arena.zero_()
             _lib._check(lib.shacira_latent_backward(3, P(s["coords"]), S, P(s["g"]), P(z), fi, rs, L, BW, C, F, P(A), 0, T, 0,
                                                     P(glat.grad), P(gA.grad), P(gS.grad), st))
+        if entropy and r1 > r0:
+            cur.wait_stream(ent_stream)
         return arena.allreduce() if exchange else 0
 
     step.prebinned = -1
@@ -131,7 +148,8 @@ def run(dev, rank, world, steps=30, warmup=5, planned=True, overlap_binning=True
     return {"workload": "BASELINE cfg4 NeRF-shape ray-batch DP step (re-bin + grid fwd + bwd + grad all-reduce)",
             "n_gpus": world, "scaling": "weak", "rays_per_rank": RAYS, "samples_per_rank": S,
             "ms_per_step": ms, "samples_per_s": S * world / ms * 1e3, "rays_per_s": RAYS * world / ms * 1e3,
-            "allreduce_bytes": arena.flat.numel() * 4, "collectives_per_step": ncoll,
+            "allreduce_bytes": arena.flat.numel() * 4,
+            "bit_rate_rows_per_rank": (r1 - r0) if entropy else 0, "collectives_per_step": ncoll,
             "ms_per_step_without_exchange": ms_compute, "exposed_collective_us": max(0.0, (ms - ms_compute) * 1e3),
             "bytes_per_sample": bps, "alg_GBs_per_gpu": bps * S / ms / 1e6,
             "binning": ("next step's samples binned beside the exchange (side stream)" if (planned and overlap_binning)

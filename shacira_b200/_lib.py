@@ -180,6 +180,13 @@ def _dim_of(coords):
     return coords.shape[1]
 
 
+def _check_table_rows(rows, first_idx, resolutions, bitwidth, dim, what):
+    """The forward ABI carries no table size: make sure here that every level ends inside the table."""
+    need = max(int(f) + min(1 << int(bitwidth), int(r) ** dim) for f, r in zip(first_idx, resolutions))
+    if rows < need:
+        raise ShaciraError(ERR_INVALID_ARGUMENT, "%s has %d rows, the levels need %d" % (what, rows, need))
+
+
 def hashgrid_forward(coords, codebook, first_idx, resolutions, bitwidth):
     """feats[N, L*F]; first_idx / resolutions are host int sequences."""
     lib = load()
@@ -190,6 +197,7 @@ def hashgrid_forward(coords, codebook, first_idx, resolutions, bitwidth):
     rs, L2 = _i32_array(resolutions)
     if L != L2:
         raise ShaciraError(ERR_INVALID_ARGUMENT, "first_idx and resolutions differ in length")
+    _check_table_rows(codebook.shape[0], first_idx, resolutions, bitwidth, dim, "codebook")
     n, F = coords.shape[0], codebook.shape[1]
     feats = torch.empty((n, L * F), dtype=torch.float32, device=coords.device)
     with torch.cuda.device(coords.device):
@@ -206,6 +214,8 @@ def hashgrid_backward(coords, grad_output, first_idx, resolutions, bitwidth, fea
     fi, L = _i32_array(first_idx)
     rs, _ = _i32_array(resolutions)
     n = coords.shape[0]
+    if tuple(grad_output.shape) != (n, L * feature_dim):
+        raise ShaciraError(ERR_INVALID_ARGUMENT, "grad_output must be [N, L*F] = %s, got %s" % ((n, L * feature_dim), tuple(grad_output.shape)))
     zero_first = 1
     if out is None:
         out = torch.empty((table_rows, feature_dim), dtype=torch.float32, device=coords.device)
@@ -244,6 +254,7 @@ def latent_forward(coords, latents, first_idx, resolutions, bitwidth, A, shift, 
     per_level = 1 if A.shape[0] == L and L > 1 else 0
     if A.shape[0] not in (1, L) or tuple(A.shape[1:]) != (C, feature_dim):
         raise ShaciraError(ERR_INVALID_ARGUMENT, "A must be [1|L, C, F], got %s" % (tuple(A.shape),))
+    _check_table_rows(latents.shape[0], first_idx, resolutions, bitwidth, dim, "latents")
     feats = torch.empty((n, L * feature_dim), dtype=torch.float32, device=coords.device)
     z = torch.empty((n, L * C), dtype=torch.float32, device=coords.device) if save_z else None
     with torch.cuda.device(coords.device):
@@ -267,6 +278,10 @@ def latent_backward(coords, grad_output, z, first_idx, resolutions, bitwidth, A,
     n = coords.shape[0]
     per_level = 1 if A.shape[0] == L and L > 1 else 0
     dev = coords.device
+    if tuple(grad_output.shape) != (n, L * feature_dim):
+        raise ShaciraError(ERR_INVALID_ARGUMENT, "grad_output must be [N, L*F] = %s, got %s" % ((n, L * feature_dim), tuple(grad_output.shape)))
+    if z is not None and tuple(z.shape) != (n, L * latent_dim):
+        raise ShaciraError(ERR_INVALID_ARGUMENT, "z must be [N, L*C], got %s" % (tuple(z.shape),))
     gl = torch.empty((table_rows, latent_dim), dtype=torch.float32, device=dev)
     gA = gS = None
     if want_decoder_grads:

@@ -1,8 +1,10 @@
 """Entropy-coded latent bitstream: what `size(use_torchac=True)` measures in the reference
 (wisp/models/grids/latent_grid.py:155-172, multi_latent_decoder.py:174-186).
 
-Bit-exactly pinned against the reference (tests/test_size_bitstream.py): the int16 symbol
-stream (dense ranks), the per-channel histogram and the float32 CDF table handed to the coder.
+Pinned against the restatement of latent_grid.py:160-169 in oracle/latent_oracle.symbol_stream
+(tests/test_host_logic.py::test_symbol_stream_and_cdf_match_the_oracle, tests/test_oracle_golden.py::
+test_symbol_stream_round_trip): the int16 symbol stream (dense ranks), the per-channel histogram and the
+float32 CDF table handed to the coder.
 NOT pinned: the coded bytes themselves -- `torchac` is absent, unvendored and unpinned, and the
 reference never decodes its stream. The coder here (csrc/arith_coder.inl) is verified by
 decode round trip and by its length against the empirical entropy.
@@ -31,6 +33,22 @@ def quantize_cdf(cdf_float):
     return q.numpy().astype(np.uint32)
 
 
+def integer_cdf(counts):
+    """The coding model of the stored container (codec.py): the 16-bit CDF from the INTEGER histogram in exact
+    integer arithmetic, floor(cum * (2^16 - K) / total) + arange(K + 1). Writer and reader derive it from the same
+    stored counts, so -- unlike the float32 cumsum of float_cdf, whose last bit depends on summation order, torch build
+    and device -- it is identical everywhere and the arithmetic decoder cannot desynchronise."""
+    c = np.asarray(counts.cpu() if isinstance(counts, torch.Tensor) else counts, dtype=np.int64)
+    K = int(c.size)
+    if K + 1 > (1 << 16):
+        raise ValueError("too many distinct symbols for a 16-bit CDF")
+    if K == 0 or (c <= 0).any():
+        raise ValueError("integer_cdf needs positive counts")
+    cum = np.concatenate((np.zeros(1, dtype=np.int64), np.cumsum(c)))
+    q = (cum * ((1 << 16) - K)) // cum[-1] + np.arange(K + 1, dtype=np.int64)
+    return q.astype(np.uint32)
+
+
 def dense_ranks(column, unique_vals):
     """Rounded latents -> rank of each value among the sorted unique values, int16
     (the reference's `mapping[weight]`, latent_grid.py:161-165)."""
@@ -38,9 +56,10 @@ def dense_ranks(column, unique_vals):
     return torch.searchsorted(unique_vals, q).to(torch.int16)
 
 
-def encode_column(column, unique_vals, counts):
-    """Returns (stream bytes, cdf uint32[K+1])."""
-    cdf = quantize_cdf(float_cdf(counts))
+def encode_column(column, unique_vals, counts, exact=False):
+    """Returns (stream bytes, cdf uint32[K+1]). exact: the integer coding model of the container (integer_cdf);
+    otherwise the reference's float32 CDF (what size(use_torchac=True) measures)."""
+    cdf = integer_cdf(counts) if exact else quantize_cdf(float_cdf(counts))
     ranks = dense_ranks(column, unique_vals).cpu().numpy()
     return _lib.ac_encode(ranks, cdf), cdf
 

@@ -25,6 +25,7 @@ histogram is taken on the host from the very symbols that are coded.
 """
 import json
 import struct
+import zlib
 
 import numpy as np
 import torch
@@ -32,7 +33,7 @@ import torch
 from . import _lib, bitstream
 
 MAGIC = b"SHCR"
-VERSION = 1
+VERSION = 2   # 2: integer coding model + CRC32 of every channel's symbols
 
 
 def _channel_stats(grid):
@@ -77,10 +78,12 @@ def encode_model(grid, mlp=None, extra_meta=None):
         if K > (1 << 15):
             raise ValueError("latent range %d..%d too wide for int16 symbols" % (lo, hi))
         # the reference's coding model: dense ranks over the OBSERVED values (latent_grid.py:161-165)
-        stream, _ = bitstream.encode_column(w[:, c].cpu(), uniq, counts)
+        # coding model from the integer counts in exact integer arithmetic: the reader rebuilds the identical CDF
+        stream, _ = bitstream.encode_column(w[:, c].cpu(), uniq, counts, exact=True)
         dense = np.zeros(K, dtype="<u4")
         dense[(uniq - lo).numpy()] = counts.numpy().astype("<u4")
-        out += [struct.pack("<iI", lo, K), dense.tobytes(), struct.pack("<Q", len(stream)), stream]
+        crc = zlib.crc32(torch.round(w[:, c]).to(torch.int32).cpu().numpy().astype("<i4").tobytes()) & 0xFFFFFFFF
+        out += [struct.pack("<iI", lo, K), dense.tobytes(), struct.pack("<QI", len(stream), crc), stream]
     out += payload
     return b"".join(out)
 
@@ -102,13 +105,18 @@ def decode_model(blob):
         pos += 8
         dense = np.frombuffer(blob, dtype="<u4", count=K, offset=pos).astype(np.int64)
         pos += 4 * K
-        (slen,) = struct.unpack_from("<Q", blob, pos)
-        pos += 8
+        slen, crc = struct.unpack_from("<QI", blob, pos)
+        pos += 12
         nz = np.nonzero(dense)[0]
+        if int(dense.sum()) != T:
+            raise ValueError("SHCR stream: histogram of channel %d does not sum to the row count" % len(cols))
         uniq = torch.from_numpy(nz + lo)
         counts = torch.from_numpy(dense[nz])
-        cdf = bitstream.quantize_cdf(bitstream.float_cdf(counts))
-        cols.append(bitstream.decode_column(blob[pos:pos + slen], cdf, T, uniq))
+        cdf = bitstream.integer_cdf(counts)
+        col = bitstream.decode_column(blob[pos:pos + slen], cdf, T, uniq)
+        if (zlib.crc32(col.to(torch.int32).numpy().astype("<i4").tobytes()) & 0xFFFFFFFF) != crc:
+            raise ValueError("SHCR stream: checksum mismatch in channel %d (corrupt stream or coding model)" % len(cols))
+        cols.append(col)
         pos += slen
     tensors = {}
     for sec in header["sections"]:
@@ -148,7 +156,7 @@ def size_report(grid, mlp, blob, pixels):
         p = counts.double() / counts.sum()
         entropy_bits += float((torch.clamp(-torch.log2(p + 1e-10), 0, 1000) * counts).sum())   # latent_grid.py:150-153
         stream_bits += bitstream.coded_bits_from_table(grid.codebook.detach()[:, c].cpu(), uniq, counts)
-        hist_bits += 32 * (int(uniq[-1]) - int(uniq[0]) + 1) + 64 + 64
+        hist_bits += 32 * (int(uniq[-1]) - int(uniq[0]) + 1) + 64 + 64 + 32
     ref_formula_bits = stream_bits + dec_bits + mlp_bits
     return {
         "file_bytes": len(blob), "file_bpp": len(blob) * 8.0 / pixels,

@@ -389,6 +389,7 @@ int shacira_hashgrid_backward(int32_t dim, const float* coords, int64_t n, const
     if (rc) return rc;
     if ((rc = check_points(coords, n))) return rc;
     if (!grad_codebook) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "grad_codebook is NULL");
+    if ((rc = check_table(lp, table_rows))) return rc;
     if (feature_dim != 1 && feature_dim != 2 && feature_dim != 4 && feature_dim != 8)
         return fail(SHACIRA_ERR_UNSUPPORTED, "feature_dim %d not in {1,2,4,8}", feature_dim);
     cudaStream_t s = (cudaStream_t)stream;
@@ -448,6 +449,7 @@ int shacira_latent_backward_levels(int32_t dim, const float* coords, int64_t n, 
     if (rc) return rc;
     if ((rc = check_points(coords, n))) return rc;
     if (!grad_latents || !A) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "grad_latents/A is NULL");
+    if ((rc = check_table(lp, table_rows))) return rc;
     if (grad_A && !zsave) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "grad_A requested without zsave");
     if (latent_dim != 1 && latent_dim != 2 && latent_dim != 4)
         return fail(SHACIRA_ERR_UNSUPPORTED, "latent_dim %d not in {1,2,4}", latent_dim);

@@ -41,6 +41,14 @@ inline int fail(int code, const char* fmt, ...) {
 int build_levels(int32_t dim, const int32_t* first_idx, const int32_t* resolutions, int32_t num_lods,
                  int32_t bitwidth, LevelParams& lp);
 int check_points(const float* coords, int64_t n);
+// every level must end inside a table of `table_rows` rows (a mismatched first_idx / bitwidth would scatter out of bounds)
+inline int check_table(const LevelParams& lp, int64_t table_rows) {
+    for (int l = 0; l < lp.num_lods; ++l)
+        if ((int64_t)lp.first[l] + lp.rows[l] > table_rows)
+            return fail(SHACIRA_ERR_INVALID_ARGUMENT, "level %d ends at row %lld, past table_rows %lld", l,
+                        (long long)lp.first[l] + lp.rows[l], (long long)table_rows);
+    return SHACIRA_OK;
+}
 
 // SM count of the CURRENT device (cached per device ordinal).
 inline int sm_count() {

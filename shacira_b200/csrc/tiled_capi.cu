@@ -439,6 +439,7 @@ int shacira_latent_backward_planned_bounded(const shacira_plan_t* plan, const fl
     int rc = build_levels(plan->dim, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
     if (rc) return rc;
     if (!grad_latents || !A || !grad_output) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "grad_latents/A/grad_output is NULL");
+    if ((rc = check_table(lp, table_rows))) return rc;
     if ((grad_A || grad_shift) && !latents)
         return fail(SHACIRA_ERR_INVALID_ARGUMENT, "decoder gradients need the latents (the interpolation is recomputed)");
     if (latent_dim != 1 && latent_dim != 2 && latent_dim != 4)
@@ -494,10 +495,7 @@ int shacira_latent_backward_planned_z(const shacira_plan_t* plan, const float* g
     if (grad_A && !zsave) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "grad_A requested without zsave");
     if (!grid3d_supported(latent_dim, feature_dim, grad_latents))
         return fail(SHACIRA_ERR_UNSUPPORTED, "backward_planned_z: latent_dim %d / feature_dim %d / table alignment", latent_dim, feature_dim);
-    for (int l = 0; l < num_lods; ++l)
-        if ((int64_t)lp.first[l] + lp.rows[l] > table_rows)
-            return fail(SHACIRA_ERR_INVALID_ARGUMENT, "level %d ends at row %lld, past table_rows %lld", l,
-                        (long long)lp.first[l] + lp.rows[l], (long long)table_rows);
+    if ((rc = check_table(lp, table_rows))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     if (zero_first) CUDA_OK(cudaMemsetAsync(grad_latents, 0, sizeof(float) * (size_t)table_rows * latent_dim, s));
     return backward_3d(const_cast<shacira_plan*>(plan), grad_output, zsave, lp, latent_dim, feature_dim, A, per_level,

@@ -36,6 +36,19 @@ def split_rays(num_rays, rank=None, world_size=None):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def shard_rows(num_rows, rank=None, world_size=None, align=4):
+    """[begin, end) of this rank's contiguous slice of the latent table for table-wise work (the bit-rate loss is a sum
+    over rows: each rank evaluates its slice, the all-reduce of the gradient arena adds the pieces -- SURVEY 8e).
+    Slice starts are multiples of `align` rows (16-byte aligned float rows for the vectorised kernels)."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    per = -(-num_rows // world_size)
+    per = -(-per // align) * align
+    begin = min(num_rows, rank * per)
+    return begin, min(num_rows, begin + per)
+
+
 def allreduce_grads(params, average=False, small_numel=1 << 16, group=None):
     """SUM all-reduce of .grad over ranks. Large gradients (the latent table) are reduced in
     place, each as its own collective launched in parameter order; everything smaller than

@@ -31,6 +31,18 @@ def _worker(rank, world, port, out):
     ok &= bool((small[0].grad == 21.0).all()) and bool((small[1].grad == 41.0).all())
     b, e = dp.split_rays(4096, rank, world)
     ok &= (e - b) == 2048
+    # table rows for table-wise work (bit-rate loss): aligned, disjoint, covering slices; summing the slices' partial
+    # results over the ranks gives the whole-table value
+    r0, r1 = dp.shard_rows(6098925)
+    ok &= r0 % 4 == 0 and (r1 == 6098925 or r1 % 4 == 0)
+    spans = dp.gather_results((r0, r1))
+    ok &= spans[0][0] == 0 and spans[0][1] == spans[1][0] and spans[1][1] == 6098925
+    w = torch.arange(1000, dtype=torch.float64)
+    q0, q1 = dp.shard_rows(1000)
+    part = torch.nn.Parameter(torch.zeros(1, dtype=torch.float64))
+    part.grad = w[q0:q1].sum().reshape(1)
+    dp.allreduce_grads([part], small_numel=0)
+    ok &= float(part.grad) == float(w.sum())
     res = dp.gather_results({"rank": rank, "units": dp.shard_units(5)})
     ok &= [r["units"] for r in res] == [[0, 2, 4], [1, 3]]
     table.grad = torch.full_like(table, float(rank + 1))

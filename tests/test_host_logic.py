@@ -137,6 +137,15 @@ def test_bitstream_round_trip_and_length(lib):
     sym, cdf_f, _, _ = lo.symbol_stream(col)
     assert torch.equal(bitstream.dense_ranks(col, uniq), sym)
     assert torch.equal(bitstream.float_cdf(counts), cdf_f)
+    # the container's coding model: exact integer arithmetic on the counts, strictly increasing, total 2^16; it does
+    # not depend on float summation order (a permuted cumsum of the float CDF may differ in the last bit)
+    icdf = bitstream.integer_cdf(counts)
+    assert icdf[0] == 0 and icdf[-1] == 65536 and (np.diff(icdf.astype(np.int64)) > 0).all()
+    total = int(counts.sum())
+    want = [(int(c) * (65536 - len(counts))) // total + k for k, c in enumerate([0] + np.cumsum(counts.numpy()).tolist())]
+    assert icdf.tolist() == want
+    s2, cdf2 = bitstream.encode_column(col, uniq, counts, exact=True)
+    assert np.array_equal(cdf2, icdf) and torch.equal(bitstream.decode_column(s2, icdf, col.numel(), uniq), col.long())
     # degenerate: a single symbol
     one = torch.zeros(100)
     u1, c1 = torch.unique(one.long(), return_counts=True)
@@ -220,3 +229,14 @@ def test_codec_container_round_trip_and_size_accounting(lib):
         codec.decode_model(b"XXXX" + blob[4:])
     with pytest.raises(ValueError):
         codec.decode_model(blob + b"\0")
+    # a flipped bit inside the coded latents: the per-channel CRC (or the decoder itself) refuses the stream
+    import json
+    import struct
+    hlen = struct.unpack_from("<HI", blob, 4)[1]
+    pos = 10 + hlen
+    lo0, K0 = struct.unpack_from("<iI", blob, pos)
+    first_stream = pos + 8 + 4 * K0 + 12
+    bad = bytearray(blob)
+    bad[first_stream + 40] ^= 0x10
+    with pytest.raises((ValueError, lib.ShaciraError)):
+        codec.decode_model(bytes(bad))

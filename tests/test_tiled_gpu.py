@@ -382,3 +382,55 @@ def test_host_session_pipelined_steps_match_device_calls(lib):
         assert rel_err(gSs[k].numpy().sum(0), gS.cpu().numpy().sum(0)) <= 1e-5
     plan.close()
     sess.close()
+
+
+@pytest.mark.parametrize("L,bw,n", [(16, 16, 768 * 512), (24, 11, 768 * 512)])
+def test_self_scaled_backward_per_level_and_per_tile(lib, L, bw, n):
+    """The tiled backward accumulates in fixed point with a step of 2^-19 of each TILE's and LEVEL's own max |gradient|.
+    A gate normalised by the whole table's maximum would let a small gradient next to a large one be wrong by far more
+    than 1e-4 of itself, so: upstream gradients whose magnitude varies by 10^6 across the image, and the error
+    normalised (a) per level and (b) per level AND spatial tile (dense levels: a row is a grid node, a node lies in a
+    tile), plus RMS per level. BASELINE cfg2 and the reference's kodak.yaml grid (24 levels, 2^11 rows)."""
+    from helpers import level_rel_err, level_rms_err
+    c = _case(2, L, bw, 16, 512, n, 1, 1, seed=77, kind="pixels")
+    # gradient magnitude: 10^-3 ... 10^3 across the image, smooth in space (whole tiles are small or large)
+    mag = 10.0 ** (3.0 * np.sin(2.5 * c["coords"][:, 0]) * np.cos(1.7 * c["coords"][:, 1]))
+    c["g"] = (c["g"] * mag[:, None]).astype(np.float32)
+    coords, lat, A, g = _dev(c["coords"]), _dev(c["lat"]), _dev(c["A"]), _dev(c["g"])
+    plan = lib.Plan(coords)
+    G = plan.info()["tiles_per_axis"]
+    gl, _, _ = lib.latent_backward_planned(plan, g, None, c["first"], c["res"], bw, A, 1, 1, c["T"], True, False)
+    gl = gl.cpu().numpy().astype(np.float64)
+    _, want_gl, _, _ = _oracle_fwd_bwd(c)
+    sizes = oracle.level_layout(c["res"], bw, 2)[0]
+    assert level_rel_err(gl, want_gl, c["first"], sizes) <= BWD_TOL
+    assert level_rms_err(gl, want_gl, c["first"], sizes) <= BWD_TOL
+    checked = 0
+    for l, (f0, rows, res) in enumerate(zip(c["first"], sizes, c["res"])):
+        if res * res != rows:          # hashed level: rows are not spatial
+            continue
+        a = gl[f0:f0 + rows, 0].reshape(res, res)            # row = x + y * res  ->  [y, x]
+        b = want_gl[f0:f0 + rows, 0].reshape(res, res)
+        # node i along an axis lies at coordinate i / res in [0, 1): tile = floor(i * G / res)
+        tile_of = np.minimum((np.arange(res) * G) // res, G - 1)
+        for ty in range(G):
+            ys = np.nonzero(tile_of == ty)[0]
+            for tx in range(G):
+                xs = np.nonzero(tile_of == tx)[0]
+                if ys.size == 0 or xs.size == 0:
+                    continue
+                ba = b[np.ix_(ys, xs)]
+                m = np.abs(ba).max()
+                if m == 0.0:
+                    continue
+                # a node on a tile border also receives the neighbour tile's contribution, quantised with THAT tile's
+                # scale: normalise by the largest gradient of the tile and its 8 neighbours (magnitudes vary by ~3x
+                # from one tile to the next here, by 10^6 across the image)
+                ny = np.nonzero((tile_of >= ty - 1) & (tile_of <= ty + 1))[0]
+                nx = np.nonzero((tile_of >= tx - 1) & (tile_of <= tx + 1))[0]
+                m = np.abs(b[np.ix_(ny, nx)]).max()
+                err = np.abs(a[np.ix_(ys, xs)] - ba).max() / m
+                assert err <= BWD_TOL, "level %d tile (%d, %d): %.3g" % (l, tx, ty, err)
+                checked += 1
+    assert checked > 100
+    plan.close()
