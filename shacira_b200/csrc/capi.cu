@@ -926,7 +926,7 @@ int shacira_latent_step_host(int32_t dim, const float* coords, int64_t n, const 
     CUDA_OK(cudaMemcpyAsync(d_gout, grad_output, sizeof(float) * n * LF, cudaMemcpyHostToDevice, s1));
     // the coordinates are new to the device every call: bin them (3 small kernels, allocation reused),
     // then run the tiled kernels; configurations the tiled path does not cover use the point-parallel ones
-    const bool tiled = (num_lods % 4 == 0) && n >= 16384;
+    const bool tiled = (num_lods % 4 == 0) && n >= 65536;   // crossover measured: profiles/r02h_crossover.jsonl
     int rc = SHACIRA_OK;
     if (tiled) {
         rc = sc.plan ? shacira_plan_rebuild(sc.plan, dim, d_coords, n, 0, s0)

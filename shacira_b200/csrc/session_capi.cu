@@ -122,7 +122,7 @@ int shacira_host_session_set_coords(shacira_host_session_t* s, const float* coor
     if (!s || !coords) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "session / coords is NULL");
     // ordered after every step in flight: the compute stream owns the plan
     CUDA_OK(cudaMemcpyAsync(s->coords, coords, 4 * (size_t)s->n * s->dim, cudaMemcpyHostToDevice, s->comp));
-    const bool tiled = (s->dim == 2 && s->L % 4 == 0 && s->n >= 16384) || (s->dim == 3 && s->n >= 65536 && s->C <= 2);
+    const bool tiled = (s->dim == 2 && s->L % 4 == 0 && s->n >= 32768) || (s->dim == 3 && s->n >= 393216 && s->C <= 2);   // static coordinates: the plan is built once
     int rc = SHACIRA_OK;
     if (tiled)
         rc = s->plan ? shacira_plan_rebuild(s->plan, s->dim, s->coords, s->n, 0, s->comp)

@@ -23,13 +23,17 @@ from collections import OrderedDict
 # An image fit calls interpolate() with the same coords tensor for every step (static coordinates,
 # image_trainer.py:234-266): one plan for the whole fit. A workload with fresh coordinates every
 # step (NeRF samples) misses the cache and pays the ~3-kernel plan build each step.
-PLAN_MIN_POINTS = int(os.environ.get("SHACIRA_PLAN_MIN_POINTS", "16384"))
+# Crossovers measured on the B200 (benchmarks/crossover.py, profiles/r02h_crossover.jsonl). 2D, cfg2 grid: fwd + bwd tiled
+# 67 us against 90 us point-parallel at 2^16 points (83 us when the plan is re-binned every step), but 115 / 147 us
+# against 94 us at 2^14 / 2^15 -- a 64-tile plan leaves most SMs idle. 3D, cfg4 grid: sorted 376 us (415 us with the
+# per-step re-binning) against 436 us unsorted at 2^19 samples; below that the re-binning costs more than the sort saves.
+PLAN_MIN_POINTS = int(os.environ.get("SHACIRA_PLAN_MIN_POINTS", "65536"))
 PLAN_CACHE_SIZE = int(os.environ.get("SHACIRA_PLAN_CACHE", "8"))
 _plans = OrderedDict()
 plan_stats = {"hits": 0, "builds": 0}
 
 
-PLAN_MIN_POINTS_3D = int(os.environ.get("SHACIRA_PLAN_MIN_POINTS_3D", "65536"))
+PLAN_MIN_POINTS_3D = int(os.environ.get("SHACIRA_PLAN_MIN_POINTS_3D", "393216"))
 
 
 class _PlanLease:

@@ -67,7 +67,7 @@ class ImageFitStep:
         self.IN, self.H, self.OUT = self.lin[0].in_features, self.lin[0].out_features, self.lin[2].out_features
         if self.IN != self.L * self.F:
             raise _lib.ShaciraError(_lib.ERR_INVALID_ARGUMENT, "MLP input width must be num_lods * feature_dim")
-        if self.n < grid_ops.PLAN_MIN_POINTS or self.L % 4:
+        if self.n < 4096 or self.L % 4:
             raise _lib.ShaciraError(_lib.ERR_UNSUPPORTED, "ImageFitStep: coordinate set / level count outside the tiled path")
         # A plan of its own, in sorted-I/O mode: the step's consumers of the feature rows (per-point MLP, mean loss)
         # do not care about the order of the points, so grid and MLP exchange rows in the plan's tile order (targets

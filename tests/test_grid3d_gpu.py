@@ -103,6 +103,7 @@ def test_latent_grid_3d_autograd_uses_the_sorted_path(lib, monkeypatch):
     S = _dev(c["S"]).requires_grad_(True)
     coords, g = _dev(c["coords"]), _dev(c["g"])
     grid_ops.clear_plans()
+    monkeypatch.setattr(grid_ops, "PLAN_MIN_POINTS_3D", 1)   # the mechanism, not the crossover, is under test
     builds = grid_ops.plan_stats["builds"]
     feats = grid_ops.latent_hashgrid(coords, lat, A, S, c["first"], c["res"], 19, True)
     assert grid_ops.plan_stats["builds"] == builds + 1
