@@ -297,7 +297,7 @@ struct LevelRegs {
 
 template <int D>
 __device__ __forceinline__ void load_level_regs(const LevelParams& lp, const TileGeom<D>& tg, int l, LevelRegs& r) {
-    r.resd = (double)lp.res[l];
+    r.resd = lp.resd[l];
     r.hi = lp.hi[l];
     r.w0 = tg.w[l][0];
     r.w01 = (D > 2) ? tg.w[l][0] * tg.w[l][1] : 0;
@@ -636,12 +636,15 @@ __device__ __forceinline__ float fixed_scale(float m, int k, float& inv) {
         inv = (m != m || m > 3.0e38f) ? __int_as_float(0x7fc00000) : 0.0f;
         return 0.0f;
     }
-    int ex;
-    frexpf(m, &ex);  // m < 2^ex
-    const int e = 30 - k - ex;
-    inv = ldexpf(1.0f, -e);
-    return ldexpf(1.0f, e);
+    const int ex = (int)((__float_as_uint(m) >> 23) & 0xffu) - 126;   // m < 2^ex (exponent field; subnormals: 2^-126)
+    // sums of 2^k terms below 2^30, and every single term below 2^21 so that fixed_rn() can convert without the XU pipe
+    const int e = max(-126, min(min(30 - k, 21) - ex, 126));
+    inv = __int_as_float((127 - e) << 23);   // 2^-e, exact
+    return __int_as_float((127 + e) << 23);  // 2^e
 }
+// round-to-nearest-even float -> int for |v| <= 2^22 as one FADD + one IADD (v + 1.5 * 2^23 lands in [2^23, 2^24), where
+// floats are the integers): F2I sits on the quarter-rate conversion pipe with scoreboard latency, 64 of them per point.
+__device__ __forceinline__ int fixed_rn(float v) { return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000; }
 
 // Two formulations, chosen at compile time:
 //   scatter-gz (SG = false): accumulate w_k * (A^T g) per node (C channels). Decoder gradients, when wanted,
@@ -694,8 +697,13 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
     // levels this launch touches: all of them, or the staged prefix rounded up to the level blocking
     const int Lrun = skip_direct ? min(L, ((__popc(tg.staged) + kLv - 1) / kLv) * kLv) : L;
 
-    for (int b0 = beg; b0 < end; b0 += kBatch) {
-        const int b1 = min(end, b0 + kBatch);
+    // Points per thread held in registers for a whole batch: each 16-byte piece of a gradient row is read ONCE, its
+    // levels' maxima (the fixed-point scales) are reduced from the registers, and after one barrier the same registers
+    // feed the accumulation -- no separate max pass over the rows (round 1: a second, latency-bound read of every row).
+    constexpr int KB = (F == 1) ? 3 : ((F == 2) ? 2 : 1);
+    constexpr int kBatchPts = kTileThreads * KB;
+    for (int b0 = beg; b0 < end; b0 += kBatchPts) {
+        const int b1 = min(end, b0 + kBatchPts);
         int kbits = 0;
         while ((1 << kbits) < (b1 - b0)) ++kbits;
         {
@@ -703,14 +711,12 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
             int4* z4 = reinterpret_cast<int4*>(s_acc);
             for (int e = threadIdx.x; e < n4; e += kTileThreads) z4[e] = make_int4(0, 0, 0, 0);
         }
-        if (threadIdx.x < SHACIRA_MAX_LEVELS) s_gmax[threadIdx.x] = 0u;
-        __syncthreads();
-        if (level_max) {
-            // The caller knows an upper bound of |grad_output| per level (e.g. the kernel that produced the rows
-            // reduced it on the way): the fixed-point scales come from it and the pass over the tile's gradient rows
-            // (a second read of every row) is skipped. The bound of the accumulated quantity is |g| itself in
-            // scatter-g mode, else |A^T g| <= max|g| * max_c sum_f |A[c][f]|.
-            if (threadIdx.x < L) {
+        if (threadIdx.x < SHACIRA_MAX_LEVELS) {
+            unsigned bound = 0u;
+            if (level_max && threadIdx.x < L) {
+                // The caller knows an upper bound of |grad_output| per level (e.g. the kernel that produced the rows
+                // reduced it on the way). The bound of the accumulated quantity is |g| itself in scatter-g mode, else
+                // |A^T g| <= max|g| * max_c sum_f |A[c][f]|.
                 float m = fabsf(__ldg(level_max + threadIdx.x * F));
 #pragma unroll
                 for (int jf = 1; jf < F; ++jf) m = nan_max(m, fabsf(__ldg(level_max + threadIdx.x * F + jf)));
@@ -721,81 +727,75 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                     for (int ch = 0; ch < C; ++ch) {
                         float sum = 0.0f;
 #pragma unroll
-                        for (int jf = 0; jf < F; ++jf) sum += fabsf(s_A[(la * C + ch) * F + jf]);
+                        for (int jf = 0; jf < F; ++jf) sum += fabsf(__ldg(A + (la * C + ch) * F + jf));
                         amax = fmaxf(amax, sum);
                     }
                     m *= amax;
                 }
-                s_gmax[threadIdx.x] = __float_as_uint(m);
+                bound = __float_as_uint(m);
             }
-        } else
-        // pass 1: per-level maxima of what will be accumulated (they fix the fixed-point scales).
-        // Points outer, whole gradient row (all levels) in flight per point: one round trip to memory per
-        // group of KP1 points instead of one per level chunk. Per-level running maxima live in shared memory
-        // (REDUX over the warp, then one shared atomicMax per warp, level and group).
-        {
-            constexpr int KP1 = (F == 1) ? SHACIRA_KP1 : 1;
-            for (int base = b0; base < b1; base += kTileThreads * KP1) {
-                const float* rows[KP1];
+            s_gmax[threadIdx.x] = bound;
+        }
+        // this thread's points of the batch: row index, coordinates
+        int64_t rowk[KB];
+        float ck[KB][D];
+        bool livek[KB];
 #pragma unroll
-                for (int k = 0; k < KP1; ++k) {
-                    const int j = base + k * kTileThreads + threadIdx.x;
-                    rows[k] = (j < b1) ? grad_out + (int64_t)(pv.perm ? __ldg(pv.perm + j) : j) * L * F : nullptr;
-                }
-                for (int l0 = 0; l0 < Lrun; l0 += 8) {  // 8 levels = two 16-byte vectors per point in flight
-                    float g[KP1][2][4 * F];
+        for (int k = 0; k < KB; ++k) {
+            const int j = b0 + k * kTileThreads + threadIdx.x;
+            livek[k] = j < b1;
+            rowk[k] = 0;
 #pragma unroll
-                    for (int k = 0; k < KP1; ++k)
+            for (int d = 0; d < D; ++d) ck[k][d] = 0.0f;
+            if (livek[k]) {
+                rowk[k] = (int64_t)(pv.perm ? __ldg(pv.perm + j) : j) * L * F;
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                            for (int e = 0; e < 4 * F; ++e) g[k][h][e] = 0.0f;
-                            if (rows[k] && l0 + 4 * h < Lrun) load_row<4 * F>(rows[k] + (l0 + 4 * h) * F, g[k][h]);
-                        }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int l = l0 + 4 * h + q;
-                            float m = 0.0f;
-#pragma unroll
-                            for (int k = 0; k < KP1; ++k) {
-                                if (SG) {
-#pragma unroll
-                                    for (int jf = 0; jf < F; ++jf) m = nan_max(m, fabsf(g[k][h][q * F + jf]));
-                                } else {
-                                    const int la = per_level ? min(l, L - 1) : 0;
-#pragma unroll
-                                    for (int ch = 0; ch < C; ++ch) {
-                                        float acc = 0.0f;
-#pragma unroll
-                                        for (int jf = 0; jf < F; ++jf)
-                                            acc = __fmaf_rn(g[k][h][q * F + jf], s_A[(la * C + ch) * F + jf], acc);
-                                        m = nan_max(m, fabsf(acc));
-                                    }
-                                }
-                            }
-                            const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
-                            if (lane == 0 && wm && l < L) atomicMax(&s_gmax[l], wm);
-                        }
-                }
+                for (int d = 0; d < D; ++d) ck[k][d] = __ldg(pv.coords_sorted + (int64_t)j * D + d);
             }
         }
-        // latents for the decoder gradients (ZP: per-point z in pass 2; SG: q[node] at flush). Staged here, behind
-        // pass 1, so that their gather latency overlaps the other warps' work instead of the kernel prologue.
+        // latents for the decoder gradients (ZP: per-point z; SG: q[node] at flush), staged once, behind the loads above
         if (DEC && !staged_lat) {
             stage_nodes<D, C>(tg, pv.node_tab + (size_t)tile * pv.node_stride, latents, round_flag, s_lat);
             staged_lat = true;
         }
         __syncthreads();
-        if (threadIdx.x < L) {
-            float inv;
-            s_scale[threadIdx.x] = fixed_scale(__uint_as_float(s_gmax[threadIdx.x]), kbits, inv);
-            s_inv[threadIdx.x] = inv;
-        }
-        __syncthreads();
-        // pass 2: accumulate
         for (int l0 = 0; l0 < Lrun; l0 += kLv) {
+            float gk[KB][kLv * F];
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+#pragma unroll
+                for (int e = 0; e < kLv * F; ++e) gk[k][e] = 0.0f;
+                if (livek[k]) load_row<kLv * F>(grad_out + rowk[k] + l0 * F, gk[k]);
+            }
+            if (!level_max) {
+                // maxima of what this chunk of levels will accumulate, over the batch: REDUX over the warp, one shared
+                // atomicMax per warp and level; NaN propagates (nan_max; its bit pattern compares above +Inf)
+#pragma unroll
+                for (int q = 0; q < kLv; ++q) {
+                    const int l = l0 + q;
+                    float m = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < KB; ++k) {
+                        if (SG) {
+#pragma unroll
+                            for (int jf = 0; jf < F; ++jf) m = nan_max(m, fabsf(gk[k][q * F + jf]));
+                        } else {
+                            const int la = per_level ? l : 0;
+#pragma unroll
+                            for (int ch = 0; ch < C; ++ch) {
+                                float acc = 0.0f;
+#pragma unroll
+                                for (int jf = 0; jf < F; ++jf)
+                                    acc = __fmaf_rn(gk[k][q * F + jf], s_A[(la * C + ch) * F + jf], acc);
+                                m = nan_max(m, fabsf(acc));
+                            }
+                        }
+                    }
+                    const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+                    if (lane == 0 && wm) atomicMax(&s_gmax[l], wm);
+                }
+                __syncthreads();
+            }
             float accS[ZP ? kLv * F : 1], accA[ZP ? kLv * C * F : 1];
             if (ZP) {
 #pragma unroll
@@ -808,7 +808,8 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
 #pragma unroll
             for (int q = 0; q < kLv; ++q) {
                 load_level_regs<D>(lp, tg, l0 + q, lr[q]);
-                scq[q] = s_scale[l0 + q];
+                float inv_unused;
+                scq[q] = fixed_scale(__uint_as_float(s_gmax[l0 + q]), kbits, inv_unused);
                 if (!SG) {
                     const int la = per_level ? (l0 + q) : 0;
 #pragma unroll
@@ -818,27 +819,14 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
             bool all_staged = true;
 #pragma unroll
             for (int q = 0; q < kLv; ++q) all_staged &= lr[q].staged;
-            for (int base = b0; base < b1; base += kTileThreads * KP) {
-                float gk[KP][kLv * F];
-                double tk[KP][D];
-                bool livek[KP];
+            {
 #pragma unroll
-                for (int k = 0; k < KP; ++k) {
-                    const int j = base + k * kTileThreads + threadIdx.x;
-                    livek[k] = j < b1;
-#pragma unroll
-                    for (int e = 0; e < kLv * F; ++e) gk[k][e] = 0.0f;
-#pragma unroll
-                    for (int d = 0; d < D; ++d) tk[k][d] = 0.5;
-                    if (livek[k]) {
-                        load_row<kLv * F>(grad_out + (int64_t)(pv.perm ? __ldg(pv.perm + j) : j) * L * F + l0 * F, gk[k]);
-                        load_unit_coords<D>(pv.coords_sorted, j, tk[k]);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < KP; ++k) {
+                for (int k = 0; k < KB; ++k) {
                     if (!livek[k]) continue;
-                    const double (&t)[D] = tk[k];
+                    double tk1[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) tk1[d] = unit_coord(ck[k][d]);
+                    const double (&t)[D] = tk1;
                     const float (&g)[kLv * F] = gk[k];
                     if (all_staged) {
                         // every level of the chunk is staged (uniform): stencils first, as one basic block, so the
@@ -867,7 +855,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
 #pragma unroll
                                 for (int kk = 0; kk < NC; ++kk)
                                     atomicAdd(&s_acc[(size_t)((st[q].slot[kk] + lr[q].accd) * lr[q].amul + lr[q].alane) * CA + ch],
-                                              __float2int_rn(__fmul_rn(gs, st[q].w[kk])));
+                                              fixed_rn(__fmul_rn(gs, st[q].w[kk])));
                             }
                             if (ZP) {
                                 float v[NC][C], z[C];
@@ -914,7 +902,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
 #pragma unroll
                                 for (int kk = 0; kk < NC; ++kk)
                                     atomicAdd(&s_acc[(size_t)((st.slot[kk] + lr[q].accd) * lr[q].amul + lr[q].alane) * CA + ch],
-                                              __float2int_rn(__fmul_rn(gs, st.w[kk])));
+                                              fixed_rn(__fmul_rn(gs, st.w[kk])));
                             }
                             if (ZP) {
                                 float v[NC][C];
@@ -993,6 +981,11 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                     if (lane == 0) s_gA[(warp * L + l0) * C * F + e] += v;  // e = (q*C + ch)*F + jf
                 }
             }
+        }
+        if (threadIdx.x < L) {
+            float inv;
+            fixed_scale(__uint_as_float(s_gmax[threadIdx.x]), kbits, inv);
+            s_inv[threadIdx.x] = inv;
         }
         __syncthreads();
         // flush: one float REDG per touched node (+ the per-node decoder gradients in scatter-g mode)
