@@ -449,6 +449,9 @@ constexpr int kStageUnroll = SHACIRA_STAGE_UNROLL;
 #ifndef SHACIRA_LV
 #define SHACIRA_LV 4
 #endif
+#ifndef SHACIRA_BWD_PREFETCH
+#define SHACIRA_BWD_PREFETCH 0   // measured: the extra row registers spill at the 72-register cap (38.1 vs 36.7 us)
+#endif
 constexpr int kLv = SHACIRA_LV;  // levels per inner iteration (register blocking of the level loop): 4 or 2
 template <int D, int C>
 __device__ __forceinline__ void stage_nodes(const TileGeom<D>& tg, const int2* __restrict__ tab,
@@ -758,15 +761,24 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
             stage_nodes<D, C>(tg, pv.node_tab + (size_t)tile * pv.node_stride, latents, round_flag, s_lat);
             staged_lat = true;
         }
+        // the first chunk's gradient pieces are requested before the barrier, every later chunk's while the previous one
+        // is being accumulated (SHACIRA_BWD_PREFETCH: one more set of row registers)
+        float gk[KB][kLv * F];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+#pragma unroll
+            for (int e = 0; e < kLv * F; ++e) gk[k][e] = 0.0f;
+            if (livek[k] && Lrun > 0) load_row<kLv * F>(grad_out + rowk[k], gk[k]);
+        }
         __syncthreads();
         for (int l0 = 0; l0 < Lrun; l0 += kLv) {
-            float gk[KB][kLv * F];
+#if !SHACIRA_BWD_PREFETCH
+            if (l0 > 0) {
 #pragma unroll
-            for (int k = 0; k < KB; ++k) {
-#pragma unroll
-                for (int e = 0; e < kLv * F; ++e) gk[k][e] = 0.0f;
-                if (livek[k]) load_row<kLv * F>(grad_out + rowk[k] + l0 * F, gk[k]);
+                for (int k = 0; k < KB; ++k)
+                    if (livek[k]) load_row<kLv * F>(grad_out + rowk[k] + l0 * F, gk[k]);
             }
+#endif
             if (!level_max) {
                 // maxima of what this chunk of levels will accumulate, over the batch: REDUX over the warp, one shared
                 // atomicMax per warp and level; NaN propagates (nan_max; its bit pattern compares above +Inf)
@@ -796,6 +808,15 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                 }
                 __syncthreads();
             }
+#if SHACIRA_BWD_PREFETCH
+            float gn[KB][kLv * F];
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+#pragma unroll
+                for (int e = 0; e < kLv * F; ++e) gn[k][e] = 0.0f;
+                if (livek[k] && l0 + kLv < Lrun) load_row<kLv * F>(grad_out + rowk[k] + (l0 + kLv) * F, gn[k]);
+            }
+#endif
             float accS[ZP ? kLv * F : 1], accA[ZP ? kLv * C * F : 1];
             if (ZP) {
 #pragma unroll
@@ -981,11 +1002,29 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                     if (lane == 0) s_gA[(warp * L + l0) * C * F + e] += v;  // e = (q*C + ch)*F + jf
                 }
             }
+#if SHACIRA_BWD_PREFETCH
+#pragma unroll
+            for (int k = 0; k < KB; ++k)
+#pragma unroll
+                for (int e = 0; e < kLv * F; ++e) gk[k][e] = gn[k][e];
+#endif
         }
         if (threadIdx.x < L) {
             float inv;
             fixed_scale(__uint_as_float(s_gmax[threadIdx.x]), kbits, inv);
             s_inv[threadIdx.x] = inv;
+        }
+        // the flush's node-table entries (absolute row, level) are requested now, ahead of the barrier: the flush is
+        // the tail of the CTA, nothing else would hide their latency
+        constexpr int kFlushPre = 9;
+        int2 pre[kFlushPre];
+        {
+            const int2* tab_p = pv.node_tab ? pv.node_tab + (size_t)tile * pv.node_stride : nullptr;
+#pragma unroll
+            for (int u = 0; u < kFlushPre; ++u) {
+                const int e = threadIdx.x + u * kTileThreads;
+                pre[u] = (tab_p && e < tg.total) ? __ldg(tab_p + e) : make_int2(0, 0);
+            }
         }
         __syncthreads();
         // flush: one float REDG per touched node (+ the per-node decoder gradients in scatter-g mode)
@@ -1003,69 +1042,78 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
         // plan's node table): full lanes on the small coarse levels, no per-node index math. With per-level
         // decoders in scatter-g mode the partial sums must be kept per level, so that (rare) case walks level by level.
         const bool by_level = SG && per_level;
+        // one node: fixed-point sums -> float, one REDG (+ the per-node decoder gradients in scatter-g mode)
+        auto flush_node = [&](int e, int2 ent) {
+            const int l = ent.y & 0xff;
+            const int nloc = e - tg.off[l];
+            const float inv = s_inv[l];
+            const bool rep = tg.acc_mul[l] == 32;
+            const int abase = tg.acc_off[l];
+            bool any = false;
+            float gv[CA];
+#pragma unroll
+            for (int ch = 0; ch < CA; ++ch) {
+                int qv = 0;
+                if (rep) {
+                    // the node's 32 lane copies, read starting at this thread's lane: 32 different banks per warp
+#pragma unroll 8
+                    for (int jj = 0; jj < 32; ++jj) qv += s_acc[(size_t)(abase + nloc * 32 + ((lane + jj) & 31)) * CA + ch];
+                } else {
+                    qv = s_acc[(size_t)(abase + nloc) * CA + ch];
+                }
+                any |= (qv != 0);
+                gv[ch] = (float)qv * inv;
+            }
+            if (inv != inv) {  // non-finite upstream gradient in this tile/level (see fixed_scale)
+                any = true;
+#pragma unroll
+                for (int ch = 0; ch < CA; ++ch) gv[ch] = inv;
+            }
+            if (!any || (ent.y & kNodeInvalid)) return;
+            float* dst = grad_latents + (int64_t)ent.x * C;
+            if constexpr (SG) {
+                const int la = per_level ? l : 0;
+                float qn[C], gl[C];
+                lds_row<C>(s_lat + (size_t)e * C, qn);  // staged (already rounded)
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int jf = 0; jf < F; ++jf) {
+                        acc = __fmaf_rn(gv[jf], s_A[(la * C + ch) * F + jf], acc);
+                        pA[ch * F + jf] = __fmaf_rn(qn[ch], gv[jf], pA[ch * F + jf]);
+                    }
+                    gl[ch] = acc;
+                }
+#pragma unroll
+                for (int jf = 0; jf < F; ++jf) pS[jf] += gv[jf];
+                red_add_row<C>(dst, gl);
+            } else {
+                red_add_row<C>(dst, gv);
+            }
+        };
+        auto node_entry = [&](int e) -> int2 {
+            if (pv.node_tab) return __ldg(&tab[e]);
+            // no node table (3D: it would be tens of MB): level and table row from the tile geometry
+            const int le = level_of_slot<D>(tg, num_staged, e);
+            const int r = node_row<D>(tg, lp, le, e - tg.off[le], false);
+            return make_int2(lp.first[le] + max(r, 0), le | (r >= 0 ? 0 : kNodeInvalid));
+        };
         for (int lvl = 0; lvl < (by_level ? num_staged : 1); ++lvl) {
             const int e_begin = by_level ? tg.off[lvl] : 0;
             const int e_end = by_level ? ((lvl + 1 < num_staged) ? tg.off[lvl + 1] : total_nodes) : total_nodes;
-            for (int e = e_begin + threadIdx.x; e < e_end; e += kTileThreads) {
-                int2 ent;
-                if (pv.node_tab) {
-                    ent = __ldg(&tab[e]);
-                } else {   // no node table (3D: it would be tens of MB): level and table row from the tile geometry
-                    const int le = level_of_slot<D>(tg, num_staged, e);
-                    const int r = node_row<D>(tg, lp, le, e - tg.off[le], false);
-                    ent = make_int2(lp.first[le] + max(r, 0), le | (r >= 0 ? 0 : kNodeInvalid));
-                }
-                const int l = ent.y & 0xff;
-                const int nloc = e - tg.off[l];
-                const float inv = s_inv[l];
-                const bool rep = tg.acc_mul[l] == 32;
-                const int abase = tg.acc_off[l];
-                bool any = false;
-                float gv[CA];
+            int e = e_begin + threadIdx.x;
+            if (!by_level && pv.node_tab) {
+                // the first kFlushPre entries of this thread were requested before the barrier (see `pre`)
 #pragma unroll
-                for (int ch = 0; ch < CA; ++ch) {
-                    int qv = 0;
-                    if (rep) {
-                        // the node's 32 lane copies, read starting at this thread's lane: 32 different banks per warp
-#pragma unroll 8
-                        for (int jj = 0; jj < 32; ++jj) qv += s_acc[(size_t)(abase + nloc * 32 + ((lane + jj) & 31)) * CA + ch];
-                    } else {
-                        qv = s_acc[(size_t)(abase + nloc) * CA + ch];
-                    }
-                    any |= (qv != 0);
-                    gv[ch] = (float)qv * inv;
-                }
-                if (inv != inv) {  // non-finite upstream gradient in this tile/level (see fixed_scale)
-                    any = true;
-#pragma unroll
-                    for (int ch = 0; ch < CA; ++ch) gv[ch] = inv;
-                }
-                if (!any || (ent.y & kNodeInvalid)) continue;
-                float* dst = grad_latents + (int64_t)ent.x * C;
-                if constexpr (SG) {
-                    const int la = per_level ? l : 0;
-                    float qn[C], gl[C];
-                    lds_row<C>(s_lat + (size_t)e * C, qn);  // staged (already rounded)
-#pragma unroll
-                    for (int ch = 0; ch < C; ++ch) {
-                        float acc = 0.0f;
-#pragma unroll
-                        for (int jf = 0; jf < F; ++jf) {
-                            acc = __fmaf_rn(gv[jf], s_A[(la * C + ch) * F + jf], acc);
-                            pA[ch * F + jf] = __fmaf_rn(qn[ch], gv[jf], pA[ch * F + jf]);
-                        }
-                        gl[ch] = acc;
-                    }
-#pragma unroll
-                    for (int jf = 0; jf < F; ++jf) pS[jf] += gv[jf];
-                    red_add_row<C>(dst, gl);
-                } else {
-                    red_add_row<C>(dst, gv);
-                }
+                for (int u = 0; u < kFlushPre; ++u, e += kTileThreads)
+                    if (e < e_end) flush_node(e, pre[u]);
             }
+            for (; e < e_end; e += kTileThreads) flush_node(e, node_entry(e));
             if (SG) {
-                // one shared decoder: everything rides in level slot 0 (the caller sums grad_A over levels anyway)
-                const int dl = by_level ? lvl : 0;
+                // one shared decoder: only the SUM over the L rows is defined (the caller adds them), so every tile
+                // puts its share in row (tile mod L): 1024 CTAs adding into ONE address serialise in L2
+                const int dl = by_level ? lvl : (tile % L);
 #pragma unroll
                 for (int e = 0; e < F; ++e) {
                     const float v = warp_sum(pS[e]);

@@ -378,7 +378,7 @@ def test_host_session_pipelined_steps_match_device_calls(lib):
         gl, gA, gS = lib.latent_backward_planned(plan, gouts[k].cuda(), lats[k].cuda(), c["first"], c["res"], 16, dA, 1, 1,
                                                  c["T"], True, True)
         assert torch.equal(feats[k], f.cpu())
-        assert rel_err(gls[k].numpy(), gl.cpu().numpy()) <= 1e-5   # another plan object: other point order inside a tile, other batches
+        assert rel_err(gls[k].numpy(), gl.cpu().numpy()) <= BWD_TOL   # another plan object: other point order inside a tile, other batches and scales
         assert rel_err(gAs[k].numpy().sum(0), gA.cpu().numpy().sum(0)) <= BWD_TOL
         assert rel_err(gSs[k].numpy().sum(0), gS.cpu().numpy().sum(0)) <= BWD_TOL
     plan.close()
