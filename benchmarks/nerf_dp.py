@@ -85,7 +85,7 @@ def run(dev, rank, world, steps=30, warmup=5, planned=True, overlap_binning=True
             # this rank's slice of the table on its own stream, beside the grid kernels (it only reads the table)
             ent_stream.wait_stream(cur)
             with torch.cuda.stream(ent_stream):
-                bits, _, gp = _lib.entropy_bits(lat[r0:r1], None, prob, 1, None, want_grads=True)
+                bits, _, gp = _lib.entropy_bits(lat[r0:r1], None, prob, 1, None, want_grads=True, want_latent_grads=False)
                 gprob.grad.copy_(gp)
                 gbits.grad.copy_(bits[:1].to(torch.float32))
         if planned:

@@ -488,8 +488,10 @@ def _entropy_scratch(device, C, L):
     return buf
 
 
-def entropy_bits(latents, noise, params, num_layers, first_idx=None, want_grads=True):
-    """params [4, 3, C]. Returns (bits[1+L] float64, grad_latents[T, C] | None, grad_params[4,3,C] | None)."""
+def entropy_bits(latents, noise, params, num_layers, first_idx=None, want_grads=True, want_latent_grads=True):
+    """params [4, 3, C]. Returns (bits[1+L] float64, grad_latents[T, C] | None, grad_params[4,3,C] | None).
+    noise None = validation mode (x = rint(w)): the latents' gradient is zero there (want_latent_grads=False skips
+    writing it) and the kernel counts integers instead of evaluating every element."""
     lib = load()
     latents = _f32c(latents, "latents")
     noise = _f32c(noise, "noise") if noise is not None else None
@@ -501,7 +503,7 @@ def entropy_bits(latents, noise, params, num_layers, first_idx=None, want_grads=
         fi, L = None, 0
     dev = latents.device
     bits = torch.empty((1 + L,), dtype=torch.float64, device=dev)
-    gl = torch.empty_like(latents) if want_grads else None
+    gl = torch.empty_like(latents) if (want_grads and want_latent_grads) else None
     gp = torch.empty((4, 3, C), dtype=torch.float32, device=dev) if want_grads else None
     with torch.cuda.device(dev):
         scratch = _entropy_scratch(dev, C, L)

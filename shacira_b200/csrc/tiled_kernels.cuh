@@ -703,12 +703,18 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
     // Points per thread held in registers for a whole batch: each 16-byte piece of a gradient row is read ONCE, its
     // levels' maxima (the fixed-point scales) are reduced from the registers, and after one barrier the same registers
     // feed the accumulation -- no separate max pass over the rows (round 1: a second, latency-bound read of every row).
+    // A tile with more points than one register batch (uneven sample sets; the test suite's clustered case) runs the
+    // max pass of round 1 over up to kBatch points first and then several register batches into the SAME accumulators:
+    // one zero-fill and one flush per kBatch points either way.
     constexpr int KB = (F == 1) ? 3 : ((F == 2) ? 2 : 1);
     constexpr int kBatchPts = kTileThreads * KB;
-    for (int b0 = beg; b0 < end; b0 += kBatchPts) {
-        const int b1 = min(end, b0 + kBatchPts);
+    for (int s0 = beg; s0 < end; s0 += kBatch) {
+        const int s1 = min(end, s0 + kBatch);
+        // (the 3D staged-prefix launches always take this form: their tiles average 128 samples around a batch of 128,
+        // measured 206 / 243 us against 220 / 253 us with per-batch maxima and 263 us with two samples per thread)
+        const bool multi = skip_direct || (s1 - s0) > kBatchPts;
         int kbits = 0;
-        while ((1 << kbits) < (b1 - b0)) ++kbits;
+        while ((1 << kbits) < (s1 - s0)) ++kbits;
         {
             const int n4 = (tg.acc_total * CA + 3) >> 2;  // capacities are multiples of 4 slots: whole int4 stores
             int4* z4 = reinterpret_cast<int4*>(s_acc);
@@ -739,9 +745,48 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
             }
             s_gmax[threadIdx.x] = bound;
         }
+        if (multi && !level_max) {
+            __syncthreads();   // s_gmax cleared
+            for (int base = s0; base < s1; base += kTileThreads) {
+                const int j = base + threadIdx.x;
+                const float* rowp = (j < s1) ? grad_out + (int64_t)(pv.perm ? __ldg(pv.perm + j) : j) * L * F : nullptr;
+                for (int l0 = 0; l0 < Lrun; l0 += kLv) {
+                    float g[kLv * F];
+#pragma unroll
+                    for (int e = 0; e < kLv * F; ++e) g[e] = 0.0f;
+                    if (rowp) load_row<kLv * F>(rowp + l0 * F, g);
+#pragma unroll
+                    for (int q = 0; q < kLv; ++q) {
+                        float m = 0.0f;
+                        if (SG) {
+#pragma unroll
+                            for (int jf = 0; jf < F; ++jf) m = nan_max(m, fabsf(g[q * F + jf]));
+                        } else {
+                            const int la = per_level ? (l0 + q) : 0;
+#pragma unroll
+                            for (int ch = 0; ch < C; ++ch) {
+                                float acc = 0.0f;
+#pragma unroll
+                                for (int jf = 0; jf < F; ++jf) acc = __fmaf_rn(g[q * F + jf], s_A[(la * C + ch) * F + jf], acc);
+                                m = nan_max(m, fabsf(acc));
+                            }
+                        }
+                        const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+                        if (lane == 0 && wm) atomicMax(&s_gmax[l0 + q], wm);
+                    }
+                }
+            }
+        }
+        const bool own_max = !level_max && !multi;   // the chunk loop reduces the maxima itself (one register batch)
+      for (int b0 = s0; b0 < s1; b0 += kBatchPts) {
+        const int b1 = min(s1, b0 + kBatchPts);
         // this thread's points of the batch: row index, coordinates
+        // (coordinates as floats when a thread holds several points -- the double unit coordinate is then rebuilt per
+        // level chunk, 6 registers instead of 12 at the image shape -- and as doubles when it holds one)
+        constexpr bool kKeepUnit = KB * D <= 4;
         int64_t rowk[KB];
         float ck[KB][D];
+        double tu[kKeepUnit ? KB : 1][D];
         bool livek[KB];
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
@@ -754,6 +799,10 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                 rowk[k] = (int64_t)(pv.perm ? __ldg(pv.perm + j) : j) * L * F;
 #pragma unroll
                 for (int d = 0; d < D; ++d) ck[k][d] = __ldg(pv.coords_sorted + (int64_t)j * D + d);
+            }
+            if (kKeepUnit) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) tu[k][d] = unit_coord(ck[k][d]);
             }
         }
         // latents for the decoder gradients (ZP: per-point z; SG: q[node] at flush), staged once, behind the loads above
@@ -779,7 +828,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                     if (livek[k]) load_row<kLv * F>(grad_out + rowk[k] + l0 * F, gk[k]);
             }
 #endif
-            if (!level_max) {
+            if (own_max) {
                 // maxima of what this chunk of levels will accumulate, over the batch: REDUX over the warp, one shared
                 // atomicMax per warp and level; NaN propagates (nan_max; its bit pattern compares above +Inf)
 #pragma unroll
@@ -846,7 +895,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                     if (!livek[k]) continue;
                     double tk1[D];
 #pragma unroll
-                    for (int d = 0; d < D; ++d) tk1[d] = unit_coord(ck[k][d]);
+                    for (int d = 0; d < D; ++d) tk1[d] = kKeepUnit ? tu[k][d] : unit_coord(ck[k][d]);
                     const double (&t)[D] = tk1;
                     const float (&g)[kLv * F] = gk[k];
                     if (all_staged) {
@@ -1009,6 +1058,7 @@ latent_bwd_tiled_kernel(const PlanView pv, const float* __restrict__ grad_out, c
                 for (int e = 0; e < kLv * F; ++e) gk[k][e] = gn[k][e];
 #endif
         }
+      }   // register batches of this span
         if (threadIdx.x < L) {
             float inv;
             fixed_scale(__uint_as_float(s_gmax[threadIdx.x]), kbits, inv);

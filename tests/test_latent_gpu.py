@@ -172,6 +172,42 @@ def test_entropy_kernel_matches_reference(lib, golden, name, mode):
         assert not gp[fi].any()                                    # unused layers get no gradient
 
 
+@pytest.mark.parametrize("C,L", [(1, 16), (2, 6), (4, 0)])
+def test_entropy_validation_mode_histogram_and_per_element_paths(lib, C, L):
+    """Validation mode counts integers per (level, channel) and evaluates each distinct integer once; integers outside
+    the histogram's range (|q| >= 128) take the per-element path in the same launch. Both against the torch
+    restatement of ent_loss (oracle), at a NeRF-size table, called twice on the same scratch (it must come back clean)."""
+    torch.manual_seed(5 + C)
+    T = 600000
+    w = torch.randn(T, C) * 9.0
+    w[::1000] *= 40.0                                   # a sprinkle of integers far outside [-128, 127]
+    w[5, 0], w[6, 0] = -128.0, 127.4                      # the histogram's edges
+    first = [int(v) for v in torch.linspace(0, T, L + 1)[:-1]] if L else None
+    packed = (torch.randn(4, 3, C) * 0.3).numpy()
+    params = {"f%d" % (i + 1): (torch.from_numpy(packed[i, 0:1]), torch.from_numpy(packed[i, 1:2]),
+                                torch.from_numpy(packed[i, 2:3]) if i < 3 else None) for i in range(4)}
+    wd = w.cuda()
+    for layers in (1, 3):
+        want = lo.ent_loss(w, None, params, layers, is_val=True)[1].item()
+        for _ in range(2):
+            bits, gl, gp = lib.entropy_bits(wd, None, torch.from_numpy(packed).cuda(), layers, first, want_grads=True,
+                                            want_latent_grads=False)
+            assert gl is None
+            assert abs(float(bits[0]) - want) <= 1e-5 * want
+            if L:
+                assert abs(float(bits[1:].sum()) - float(bits[0])) <= 1e-6 * float(bits[0])
+        # parameter gradients: autograd through the restatement
+        ps = [torch.from_numpy(packed[i].copy()).requires_grad_(True) for i in range(4)]
+        pd = {"f%d" % (i + 1): (ps[i][0:1], ps[i][1:2], ps[i][2:3] if i < 3 else None) for i in range(4)}
+        lo.ent_loss(w, None, pd, layers, is_val=True)[1].backward()
+        got = gp.cpu().numpy()
+        for i in list(range(layers - 1)) + [3]:
+            g = ps[i].grad.numpy()
+            assert rel_err(got[i, :2], g[:2]) <= BWD_TOL
+            if i < 3:
+                assert rel_err(got[i, 2], g[2]) <= BWD_TOL
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_ent_loss_api_and_autograd(lib, golden, name):
     c = case_from_golden(golden, name)
