@@ -276,7 +276,9 @@ class LatentGrid(_HashGridBase):
         if self.prob_model is None:
             return 0.0, 0.0
         noise = self.noise
-        if self.noise_freq == 1:
+        if is_val:
+            noise = None                      # round(w): no draw needed (the reference draws and discards it)
+        elif self.noise_freq == 1:
             noise = self._draw_noise()
         elif idx % self.noise_freq == 0:
             self.noise = self._draw_noise()
