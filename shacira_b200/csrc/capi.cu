@@ -505,37 +505,21 @@ static int entropy_bits_impl(const float* latents, const float* noise, int64_t t
     static const int per_sm = [] { const char* e = getenv("SHACIRA_ENT_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
     const int64_t cap = (int64_t)sms * per_sm;  // per-block prologue/epilogue (~500 instructions) vs parallelism: tuned on B200
     if (blocks > cap) blocks = cap;
-    // scratch for the block partials (+ one row for the histogram's contribution) + arrival ticket + the validation-mode
-    // histogram: the caller's (zero-initialised once, reusable: the kernel leaves ticket and histogram at 0), else a
-    // stream-ordered pool allocation (more graph nodes per call)
+    // scratch for the block partials + arrival ticket: the caller's (zero-initialised once, reusable: the kernel
+    // leaves the ticket at 0), else a stream-ordered pool allocation (3 more graph nodes per call)
     const int P = 1 + num_lods + 12 * latent_dim;
-    const size_t part_bytes = ((sizeof(float) * (size_t)(blocks + 1) * P) + 255) & ~(size_t)255;
-    const int HL = num_lods > 0 ? num_lods : 1;
-    const size_t hist_bytes = sizeof(unsigned) * (size_t)HL * latent_dim * kEntBins;
-    const bool val_mode = !noise && !rng_step;
-    static const bool hist_on = [] { const char* e = getenv("SHACIRA_ENT_HIST"); return !e || atoi(e) != 0; }();
-    // measured (benchmarks/entropy_times.py, profiles/r02k_entropy_times.txt): counting pays on big tables without the
-    // per-level breakdown (6.1 M rows: 73 us against 86 us); with 16 levels of bins per CTA (138 vs 131 us) or on the
-    // image table (54 vs 24 us) the per-CTA histogram traffic and the last CTA's evaluation cost more than they save
-    const bool use_hist = hist_on && val_mode && num_lods == 0 && total >= (1 << 20) && hist_bytes <= 96 * 1024;
-    const size_t need = part_bytes + 256 + (use_hist ? hist_bytes : 0);
+    const size_t part_bytes = ((sizeof(float) * (size_t)blocks * P) + 255) & ~(size_t)255;
     char* buf = (char*)scratch;
-    const bool own = !buf || (size_t)scratch_bytes < need;
+    const bool own = !buf || (size_t)scratch_bytes < part_bytes + 256;
     if (own) {
         buf = nullptr;
-        CUDA_OK(cudaMallocAsync((void**)&buf, need, s));
-        CUDA_OK(cudaMemsetAsync(buf + part_bytes, 0, need - part_bytes, s));
+        CUDA_OK(cudaMallocAsync((void**)&buf, part_bytes + 256, s));
+        CUDA_OK(cudaMemsetAsync(buf + part_bytes, 0, sizeof(unsigned), s));
     }
     unsigned* ticket = (unsigned*)(buf + part_bytes);
-    unsigned* hist = use_hist ? (unsigned*)(buf + part_bytes + 256) : nullptr;
-    if (use_hist && hist_bytes > 48 * 1024) {
-        static unsigned long long configured = 0ull;
-        if (needs_config(configured))
-            CUDA_OK(cudaFuncSetAttribute(entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    }
-    entropy_kernel<<<(int)blocks, kEntBlock, use_hist ? hist_bytes : 0, s>>>(
-        latents, noise, total, latent_dim, params, num_layers, lb, bits, grad_latents, grad_params, (float*)buf, ticket,
-        (unsigned long long)rng_seed, (unsigned long long*)rng_step, hist);
+    entropy_kernel<<<(int)blocks, kEntBlock, 0, s>>>(latents, noise, total, latent_dim, params, num_layers, lb, bits,
+                                                     grad_latents, grad_params, (float*)buf, ticket,
+                                                     (unsigned long long)rng_seed, (unsigned long long*)rng_step);
     launch_counter().fetch_add(1);
     const cudaError_t le = cudaGetLastError();
     if (own) cudaFreeAsync(buf, s);
@@ -564,8 +548,7 @@ int shacira_entropy_bits_rng(const float* latents, uint64_t seed, uint64_t* rng_
 int64_t shacira_entropy_scratch_bytes(int32_t latent_dim, int32_t num_lods) {
     const int64_t blocks = (int64_t)sm_count() * 8;  // upper bound of the launch grid
     const int64_t P = 1 + num_lods + 12 * (int64_t)latent_dim;
-    const int64_t hist = 4 * (int64_t)(num_lods > 0 ? num_lods : 1) * latent_dim * kEntBins;   // validation-mode histogram
-    return ((4 * (blocks + 1) * P + 255) & ~(int64_t)255) + 256 + hist;
+    return ((4 * blocks * P + 255) & ~(int64_t)255) + 256;
 }
 
 int shacira_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,

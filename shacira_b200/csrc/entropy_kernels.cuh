@@ -11,7 +11,6 @@ namespace shacira {
 
 constexpr int kEntBlock = 256;
 constexpr int kMaxEntC = 16;
-constexpr int kEntBins = 256;   // integers -128 .. 127 per (level, channel) in the validation-mode histogram
 
 struct LevelBounds {
     int32_t first[SHACIRA_MAX_LEVELS + 1];  // first row of each level, then total rows
@@ -85,23 +84,13 @@ entropy_kernel(const float* __restrict__ latents, const float* __restrict__ nois
                const float* __restrict__ params, int num_layers, const __grid_constant__ LevelBounds lb,
                double* __restrict__ bits, float* __restrict__ grad_latents, float* __restrict__ grad_params,
                float* __restrict__ partials, unsigned* __restrict__ ticket, unsigned long long rng_seed,
-               unsigned long long* __restrict__ rng_step, unsigned* __restrict__ hist) {
+               unsigned long long* __restrict__ rng_step) {
     __shared__ float s_sp[4 * kMaxEntC], s_b[4 * kMaxEntC], s_ta[4 * kMaxEntC];
     __shared__ float s_dsp[4 * kMaxEntC], s_dta[4 * kMaxEntC];  // chain-rule factors
     __shared__ float s_lvl[SHACIRA_MAX_LEVELS];
     __shared__ float s_acc[3 * 4 * kMaxEntC];
     __shared__ double s_total;
-    // Validation mode (x = rint(w): the is_val branch, which is also what the NeRF trainer evaluates every training
-    // step -- SURVEY Q8) only ever sees a handful of distinct integers: the bits and their parameter gradients depend
-    // on the integer alone. With `hist` (global, [max(L,1)][C][kEntBins] counters, zero on entry, left zero) the
-    // elements are only COUNTED per (level, channel, integer) -- shared-memory histogram per CTA, flushed with one
-    // atomic per non-empty bin -- and the last CTA evaluates the CDF chain once per non-empty bin, weighted by its
-    // count. Integers outside [-kEntBins/2, kEntBins/2) take the per-element path below. 6.1 M rows: 65 -> ~8 us.
-    extern __shared__ unsigned s_hist[];   // [max(L,1)][C][kEntBins] when hist != NULL
     const int tid = threadIdx.x;
-    const int HL = lb.num_lods > 0 ? lb.num_lods : 1;
-    if (hist)
-        for (int e = tid; e < HL * C * kEntBins; e += kEntBlock) s_hist[e] = 0u;
     if (tid < 4 * C) {
         const int k = tid / C, ch = tid % C;
         const float h = params[(k * 3 + 0) * C + ch];
@@ -142,32 +131,9 @@ entropy_kernel(const float* __restrict__ latents, const float* __restrict__ nois
         const bool live = e < total;
         float bval = 0.0f;
         int lvl = 0;
-        bool continue_flag = false;
-        int hkey = -1;
         if (live) {
             const float w = __ldg(latents + e);
             float x;
-            if (hist) {   // count, do not evaluate
-                const float q = rintf(w);
-                if (q >= -(float)(kEntBins / 2) && q < (float)(kEntBins / 2)) {
-                    int hl = 0;
-                    if (lb.num_lods > 0) {
-                        const int32_t row = (int32_t)(e / C);
-                        int a = 0, bnd = lb.num_lods;
-                        while (bnd - a > 1) {
-                            const int mid = (a + bnd) >> 1;
-                            if (lb.first[mid] <= row) a = mid; else bnd = mid;
-                        }
-                        hl = a;
-                    }
-                    hkey = (hl * C + ch) * kEntBins + (int)q + kEntBins / 2;
-                    if (grad_latents) grad_latents[e] = 0.0f;
-                    continue_flag = true;
-                }
-            }
-            if (continue_flag) {
-                // nothing: this element is represented by its histogram bin
-            } else {
             if (rng) {
                 uint32_t h = (uint32_t)e + rng_base;      // lowbias32 finaliser, two multiply-xorshift rounds
                 h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
@@ -197,17 +163,6 @@ entropy_kernel(const float* __restrict__ latents, const float* __restrict__ nois
                 }
                 lvl = a;
             }
-            }   // per-element path
-        }
-        if (hist) {
-            // warp-aggregated counting: a trained table holds a handful of distinct integers, so the 32 lanes of a warp
-            // fall into few bins -- one shared-memory atomic per distinct bin and warp (__match_any_sync) instead of 32
-            // adds serialising on the same few addresses
-            const unsigned counted = __ballot_sync(0xffffffffu, hkey >= 0);
-            if (hkey >= 0) {
-                const unsigned peers = __match_any_sync(counted, hkey);
-                if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[hkey], (unsigned)__popc(peers));
-            }
         }
         my_bits += bval;
         if (lb.num_lods > 0) {
@@ -215,13 +170,6 @@ entropy_kernel(const float* __restrict__ latents, const float* __restrict__ nois
             const float s = warp_sum((live && lvl == l0) ? bval : 0.0f);
             if (lane == 0) atomicAdd(&s_lvl[l0], s);
             if (live && lvl != l0) atomicAdd(&s_lvl[lvl], bval);
-        }
-    }
-    if (hist) {
-        __syncthreads();
-        for (int e = tid; e < HL * C * kEntBins; e += kEntBlock) {
-            const unsigned c = s_hist[e];
-            if (c) atomicAdd(hist + e, c);
         }
     }
     // block reduction: total bits (double) and parameter gradients per channel
@@ -269,73 +217,10 @@ entropy_kernel(const float* __restrict__ latents, const float* __restrict__ nois
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    unsigned nrows = gridDim.x;
-    if (hist) {
-        // the histogram's contribution: one evaluation per non-empty bin, weighted by its count -> partial row gridDim.x
-        __syncthreads();
-        if (tid < SHACIRA_MAX_LEVELS) s_lvl[tid] = 0.0f;
-        for (int e = tid; e < 3 * 4 * kMaxEntC; e += kEntBlock) s_acc[e] = 0.0f;
-        if (tid == 0) s_total = 0.0;
-        __syncthreads();
-        // thread = bin (kEntBins == kEntBlock), rows = (level, channel): every thread evaluates at most one integer per
-        // row; the row's sums are reduced over the warps (no 256-way contention on the shared accumulators)
-        static_assert(kEntBins == kEntBlock, "one bin per thread");
-        for (int row = 0; row < HL * C; ++row) {
-            const unsigned cnt = hist[row * kEntBins + tid];
-            if (!__syncthreads_or(cnt != 0u)) continue;   // empty row (uniform)
-            const int hc = row % C, hl = row / C;
-            float vals[13];
-#pragma unroll
-            for (int k = 0; k < 13; ++k) vals[k] = 0.0f;
-            if (cnt) {
-                hist[row * kEntBins + tid] = 0u;   // ready for the next launch
-                const float x = (float)(tid - kEntBins / 2), wgt = (float)cnt;
-                float e_sp[4] = {0, 0, 0, 0}, e_b[4] = {0, 0, 0, 0}, e_ta[4] = {0, 0, 0, 0};
-                CdfTrace up, lo;
-                const float Fu = cdf_forward(x + 0.5f, m, s_sp, s_b, s_ta, C, hc, up);
-                const float Fl = cdf_forward(x - 0.5f, m, s_sp, s_b, s_ta, C, hc, lo);
-                const float pr = Fu - Fl;
-                const float raw = -logf(pr + 1e-10f) * inv_ln2;
-                const float bv = fminf(fmaxf(raw, 0.0f), 50.0f);
-                const float g_raw = (raw >= 0.0f && raw <= 50.0f) ? 1.0f : 0.0f;
-                const float g_p = -g_raw * inv_ln2 / (pr + 1e-10f) * wgt;
-                cdf_backward(g_p, m, s_sp, s_ta, C, hc, up, e_sp, e_b, e_ta);
-                cdf_backward(-g_p, m, s_sp, s_ta, C, hc, lo, e_sp, e_b, e_ta);
-                vals[0] = bv * wgt;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    vals[1 + k * 3 + 0] = e_sp[k];
-                    vals[1 + k * 3 + 1] = e_b[k];
-                    vals[1 + k * 3 + 2] = e_ta[k];
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 13; ++k) vals[k] = warp_sum(vals[k]);
-            if (lane == 0) {
-                atomicAdd(&s_total, (double)vals[0]);
-                if (L > 0) atomicAdd(&s_lvl[hl], vals[0]);
-#pragma unroll
-                for (int k = 0; k < 12; ++k) atomicAdd(&s_acc[k * kMaxEntC + hc], vals[1 + k]);
-            }
-        }
-        __syncthreads();
-        float* extra = partials + (size_t)gridDim.x * P;
-        if (tid == 0) extra[0] = (float)s_total;
-        if (tid < L) extra[1 + tid] = s_lvl[tid];
-        if (tid < 4 * C) {
-            const int k = tid / C, c2 = tid % C;
-            extra[1 + L + (k * 3 + 0) * C + c2] = s_acc[(k * 3 + 0) * kMaxEntC + c2] * s_dsp[tid];
-            extra[1 + L + (k * 3 + 1) * C + c2] = s_acc[(k * 3 + 1) * kMaxEntC + c2];
-            extra[1 + L + (k * 3 + 2) * C + c2] = (k < 3) ? s_acc[(k * 3 + 2) * kMaxEntC + c2] * s_dta[tid] : 0.0f;
-        }
-        __threadfence_block();
-        __syncthreads();
-        nrows = gridDim.x + 1;
-    }
     // one warp per output value, lanes stride over the blocks (independent loads), fixed summation order
     for (int v = tid >> 5; v < P; v += kEntBlock / 32) {
         double sum = 0.0;
-        for (unsigned b = lane; b < nrows; b += 32) sum += (double)partials[(size_t)b * P + v];
+        for (unsigned b = lane; b < gridDim.x; b += 32) sum += (double)partials[(size_t)b * P + v];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if (lane == 0) {
