@@ -94,12 +94,32 @@ def main():
     def mlpk(s, st):
         _lib._check(lib.shacira_mlp_mse_step(p(s["feats"]), p(gt), n, 16, 16, 3, *[p(w) for w in mw], p(mgx), None, p(mout), st))
 
+    gmaxbuf = torch.zeros(16, device=dev)
+    mout2 = torch.zeros(2 + 16 * 16 + 16 + 256 + 16 + 48 + 3 + 16, device=dev)
+    gl_acc = torch.zeros((T, 1), device=dev)
+
+    def three_sorted(s, st):   # what the fit step ran before the fused kernel: rows in tile order, bound from the MLP
+        _lib._check(lib.shacira_latent_forward_planned(s["plan_sorted"].handle, p(lat), fi, rs, L, bench.BITWIDTH, 1, 1, 1,
+                                                       p(A), p(shift), 0, p(s["feats"]), st))
+        _lib._check(lib.shacira_mlp_mse_step_bounded(p(s["feats"]), p(gt), n, 16, 16, 3, *[p(w) for w in mw], p(mgx), None,
+                                                     p(mout2), p(mout2[-16:]), st))
+        _lib._check(lib.shacira_latent_backward_planned_bounded(s["plan_sorted"].handle, p(mgx), p(lat), fi, rs, L,
+                                                                bench.BITWIDTH, 1, 1, 1, p(A), 0, T, 0, p(gl_acc), p(gA),
+                                                                p(gS), p(mout2[-16:]), st))
+
+    def fused(s, st):
+        _lib._check(lib.shacira_fit_tile_step(s["plan_sorted"].handle, p(lat), fi, rs, L, bench.BITWIDTH, 1, p(A), p(shift),
+                                              p(gt), *[p(w) for w in mw], T, p(gl_acc), p(gA), p(gS), p(mout2), st))
+
     out = {}
     only_ent = bool(os.environ.get("ONLY_ENT"))
     for name, fn in ((("entropy_fwd_bwd", ent),) if only_ent else (("entropy_fwd_bwd", ent), ("mlp_mse_step", mlpk), ("fwd_tiled", fwd), ("bwd_tiled_dec", bwd), ("bwd_tiled_nodec", lambda s, st: bwd(s, st, False)), ("bwd_tiled_dec_bounded", bwd_bounded), ("fwd_tiled_sorted_io", fwd_sorted),
                      ("bwd_tiled_dec_bounded_sorted_io", bwd_sorted_bounded),
                      ("fwd_pointparallel", fwd_pp), ("bwd_pointparallel", bwd_pp),
-                     ("step_tiled", lambda s, st: (fwd(s, st), bwd(s, st))))):
+                     ("step_tiled", lambda s, st: (fwd(s, st), bwd(s, st))),
+                     ("fit_three_kernels_sorted_io", three_sorted), ("fit_tile_fused", fused))):
+        if os.environ.get("ONLY") and name not in os.environ["ONLY"].split(","):
+            continue
         stream = torch.cuda.Stream()
         with torch.cuda.stream(stream):
             st = ctypes.c_void_p(stream.cuda_stream)

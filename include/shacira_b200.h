@@ -255,6 +255,23 @@ int shacira_mlp_mse_step_bounded(const float* features, const float* target, int
                                  const float* b2, const float* W3, const float* b3, float* grad_features, float* pred,
                                  void* out, float* grad_feature_absmax, shacira_stream_t stream);
 
+/* ---- grid forward + decoder MLP + MSE + grid backward in ONE tile-resident kernel (row f-1 as written) ----------
+ * Replaces, for the static-coordinate image fit, the sequence shacira_latent_forward_planned ->
+ * shacira_mlp_mse_step_bounded -> shacira_latent_backward_planned_bounded (reference: latent_grid.py:340-382 ->
+ * nefs/image.py:109-120,152 -> image_trainer.py:298-300 and their autograd backward): the [n, 16] feature rows and
+ * their gradient never leave the SM. `plan`: 2D, sorted-I/O mode (shacira_plan_set_sorted_io); `target_sorted`
+ * [n, 3] in the plan's sorted order; latent_dim = feature_dim = 1, ONE affine decoder (A [1], shift [1] or NULL),
+ * 16 levels that all fit a tile's shared-memory node box (else SHACIRA_ERR_UNSUPPORTED: use the three calls).
+ * Weights in the torch.nn.Linear layout (W1 [16,16], W2 [16,16], W3 [3,16]). Outputs: grad_latents [table_rows]
+ * (ACCUMULATED into), grad_A [16] / grad_shift [16] (accumulated; only the sum over the 16 rows is defined),
+ * mlp_out as shacira_mlp_mse_step writes it (double SSE | dW1 | db1 | dW2 | db2 | dW3 | db3; cleared by the call). */
+int shacira_fit_tile_step(const shacira_plan_t* plan, const float* latents, const int32_t* first_idx,
+                          const int32_t* resolutions, int32_t num_lods, int32_t codebook_bitwidth, int32_t round_flag,
+                          const float* A, const float* shift, const float* target_sorted, const float* W1,
+                          const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
+                          int64_t table_rows, float* grad_latents, float* grad_A, float* grad_shift, void* mlp_out,
+                          shacira_stream_t stream);
+
 /* ---- fused Adam over the latent table ------------------------ */
 /* torch.optim.Adam semantics (L2 weight decay added to the gradient, bias correction, eps outside the sqrt) for
  * ONE float32 tensor in place; `step` is a device float counter (starts at 0) that the call advances, so the

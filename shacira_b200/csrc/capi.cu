@@ -98,15 +98,6 @@ inline int coarse_max_slabs() {
     }
     return v;
 }
-// cudaFuncSetAttribute is per DEVICE: remember which devices a kernel has been configured on (bit per ordinal),
-// so a process that drives several GPUs configures each of them.
-inline bool needs_config(unsigned long long& done_mask) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
-    if ((done_mask >> dev) & 1ull) return false;
-    done_mask |= 1ull << dev;
-    return true;
-}
 inline int join_side(cudaStream_t s) {
     SideStream* ss = nullptr;
     if (int rc = side_stream(&ss)) return rc;
@@ -505,8 +496,10 @@ static int entropy_bits_impl(const float* latents, const float* noise, int64_t t
     static const int per_sm = [] { const char* e = getenv("SHACIRA_ENT_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
     const int64_t cap = (int64_t)sms * per_sm;  // per-block prologue/epilogue (~500 instructions) vs parallelism: tuned on B200
     if (blocks > cap) blocks = cap;
-    // scratch for the block partials + arrival ticket: the caller's (zero-initialised once, reusable: the kernel
-    // leaves the ticket at 0), else a stream-ordered pool allocation (3 more graph nodes per call)
+    // scratch: [0, 256) arrival ticket, then the block partials. The ticket sits at a FIXED offset: one scratch serves
+    // launches of any table size (a ticket behind the partials would be overwritten by a larger launch's rows). The
+    // caller's scratch is zero-initialised once and reusable (the kernel leaves the ticket at 0); without one, a
+    // stream-ordered pool allocation (3 more graph nodes per call)
     const int P = 1 + num_lods + 12 * latent_dim;
     const size_t part_bytes = ((sizeof(float) * (size_t)blocks * P) + 255) & ~(size_t)255;
     char* buf = (char*)scratch;
@@ -514,11 +507,11 @@ static int entropy_bits_impl(const float* latents, const float* noise, int64_t t
     if (own) {
         buf = nullptr;
         CUDA_OK(cudaMallocAsync((void**)&buf, part_bytes + 256, s));
-        CUDA_OK(cudaMemsetAsync(buf + part_bytes, 0, sizeof(unsigned), s));
+        CUDA_OK(cudaMemsetAsync(buf, 0, sizeof(unsigned), s));
     }
-    unsigned* ticket = (unsigned*)(buf + part_bytes);
+    unsigned* ticket = (unsigned*)buf;
     entropy_kernel<<<(int)blocks, kEntBlock, 0, s>>>(latents, noise, total, latent_dim, params, num_layers, lb, bits,
-                                                     grad_latents, grad_params, (float*)buf, ticket,
+                                                     grad_latents, grad_params, (float*)(buf + 256), ticket,
                                                      (unsigned long long)rng_seed, (unsigned long long*)rng_step);
     launch_counter().fetch_add(1);
     const cudaError_t le = cudaGetLastError();

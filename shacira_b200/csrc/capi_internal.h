@@ -63,6 +63,16 @@ inline int sm_count() {
     return v;
 }
 
+// cudaFuncSetAttribute is per DEVICE: remember which devices a kernel has been configured on (bit per ordinal),
+// so a process that drives several GPUs configures each of them.
+inline bool needs_config(unsigned long long& done_mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    if ((done_mask >> dev) & 1ull) return false;
+    done_mask |= 1ull << dev;
+    return true;
+}
+
 // A side stream per calling thread AND device for kernels that run beside the caller's stream (event fork / join:
 // composes with stream capture). Created once per (thread, device) and kept until the thread exits.
 struct SideStream {

@@ -4,6 +4,7 @@
 
 #include "capi_internal.h"
 #include "tiled_kernels.cuh"
+#include "fit_kernels.cuh"
 
 using namespace shacira;
 
@@ -512,6 +513,50 @@ int shacira_latent_backward_planned(const shacira_plan_t* plan, const float* gra
                                                    codebook_bitwidth, latent_dim, feature_dim, round_flag, A, per_level,
                                                    table_rows, zero_first, grad_latents, grad_A, grad_shift, nullptr,
                                                    stream);
+}
+
+int shacira_fit_tile_step(const shacira_plan_t* plan, const float* latents, const int32_t* first_idx,
+                          const int32_t* resolutions, int32_t num_lods, int32_t codebook_bitwidth, int32_t round_flag,
+                          const float* A, const float* shift, const float* target_sorted, const float* W1,
+                          const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
+                          int64_t table_rows, float* grad_latents, float* grad_A, float* grad_shift, void* mlp_out,
+                          shacira_stream_t stream) {
+    if (!plan) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (plan->dim != 2 || !plan->sorted_io)
+        return fail(SHACIRA_ERR_UNSUPPORTED, "fit_tile_step: needs a 2D plan in sorted-I/O mode");
+    if (num_lods != 16) return fail(SHACIRA_ERR_UNSUPPORTED, "fit_tile_step: 16 levels (got %d)", num_lods);
+    LevelParams lp;
+    int rc = build_levels(2, first_idx, resolutions, num_lods, codebook_bitwidth, lp);
+    if (rc) return rc;
+    if (!latents || !A || !target_sorted || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !grad_latents || !mlp_out)
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "fit_tile_step: NULL argument");
+    if ((rc = check_table(lp, table_rows))) return rc;
+    shacira_plan* p = const_cast<shacira_plan*>(plan);
+    // every level must live in the tile's node box: the upper bound of the box over all levels against the budget
+    long long all = 0;
+    for (int l = 0; l < lp.num_lods; ++l) { const long long w = lp.res[l] / p->g + 3; all += w * w; }
+    const int rep = kRepBudget & ~3;
+    const int cap_max = (smem_budget() - rep * 4) / 8;   // float slot + int accumulator per node
+    if (all > cap_max) return fail(SHACIRA_ERR_UNSUPPORTED, "fit_tile_step: %lld nodes per tile exceed the shared-memory box", all);
+    const int cap = node_capacity(p, lp, cap_max);
+    const int cap_acc = cap + rep;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = ensure_node_table(p, lp, s))) return rc;
+    const size_t smem = sizeof(FitSmem) + sizeof(float) * ((size_t)cap + cap_acc);
+    static unsigned long long configured = 0ull;
+    if (needs_config(configured))
+        CUDA_OK(cudaFuncSetAttribute(fit_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    if (smem > 100 * 1024) return fail(SHACIRA_ERR_UNSUPPORTED, "fit_tile_step: %zu bytes of shared memory", smem);
+    CUDA_OK(cudaMemsetAsync(mlp_out, 0, 8 + sizeof(float) * kFitParams, s));
+    static const int per_sm = [] { const char* e = getenv("SHACIRA_FIT_CTAS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : SHACIRA_FIT_MIN_CTAS; }();
+    int blocks = sm_count() * per_sm;
+    if (blocks > p->ntiles) blocks = p->ntiles;
+    const float scale = (float)(2.0 / ((double)p->n * 3.0));
+    fit_tile_kernel<<<blocks, kTileThreads, smem, s>>>(view_of(p), latents, lp, A, shift, round_flag, target_sorted, W1, b1,
+                                                       W2, b2, W3, b3, scale, grad_latents, grad_A, grad_shift,
+                                                       (double*)mlp_out, (float*)((char*)mlp_out + 8), cap, cap_acc);
+    LAUNCHED();
+    return SHACIRA_OK;
 }
 
 }  // extern "C"

@@ -92,6 +92,10 @@ class ImageFitStep:
         self.feats = torch.empty((self.n, self.L * self.F), **f32)
         self.gfeat = torch.empty_like(self.feats)
         self.use_bound = self.IN == 16 and os.environ.get("SHACIRA_MLP_IMPL", "tc") == "tc"   # the tensor-core kernel
+        # one tile-resident kernel for grid forward + MLP / MSE + grid backward where its shapes apply (SHACIRA_FIT_FUSED=0:
+        # the three-kernel path, kept for every other shape and as the parity reference of the fused kernel)
+        self.fused = (os.environ.get("SHACIRA_FIT_FUSED", "1") != "0" and self.use_bound and self.H == 16 and
+                      self.OUT == 3 and self.C == 1 and self.F == 1 and self.L == 16 and amap[0].shape[0] == 1)
         n_par = self.H * self.IN + self.H + self.H * self.H + self.H + self.OUT * self.H + self.OUT
         # double SSE | packed MLP gradients | max |feature gradient| per column (reduced by the MLP kernel; kept behind
         # the gradients so that the call clears everything with one memset)
@@ -241,22 +245,37 @@ class ImageFitStep:
                                              1 if self.diff_sampling else 0, self.noise_seed + 0x5A17,
                                              P(self.sga_rng_step), P(self.w_hat), P(self.dw), st))
                 q_lat, rflag, gmul = self.w_hat, 0, self.dw
-            chk(lib.shacira_latent_forward_planned(self.plan.handle, P(q_lat), self.fi, self.rs, self.L, self.bw, self.C,
-                                                   self.F, rflag, P(self.A), P(shift), 0, P(self.feats), st))
-            # the MLP kernel reduces max |feature gradient| per column on the way; the tiled backward takes its
-            # fixed-point scales from that bound and skips its own pass over the gradient rows
-            bound = P(self.gfeat_max) if self.use_bound else None
-            chk(lib.shacira_mlp_mse_step_bounded(P(self.feats), P(self.target), self.n, self.IN, self.H, self.OUT,
-                                                 P(lin[0].weight.data), P(lin[0].bias.data), P(lin[1].weight.data),
-                                                 P(lin[1].bias.data), P(lin[2].weight.data), P(lin[2].bias.data),
-                                                 P(self.gfeat), None, P(self.mlp_out), bound, st))
-            if not self.has_shift:
-                self.g_dec[self.L * self.C * self.F:].zero_()   # no segment consumes (and clears) the shift rows
             CF = self.C * self.F
-            chk(lib.shacira_latent_backward_planned_bounded(self.plan.handle, P(self.gfeat), P(q_lat), self.fi, self.rs,
-                                                            self.L, self.bw, self.C, self.F, rflag, P(self.A), 0, self.T, 0,
-                                                            P(self.g_grid), P(self.g_dec), P(self.g_dec[self.L * CF:]),
-                                                            bound, st))
+            if not self.has_shift:
+                self.g_dec[self.L * CF:].zero_()   # no segment consumes (and clears) the shift rows
+            fused_done = False
+            if self.fused:
+                # grid forward + MLP / MSE + grid backward as ONE tile-resident kernel (csrc/fit_kernels.cuh): the feature
+                # rows and their gradient never leave the SM
+                rc = lib.shacira_fit_tile_step(self.plan.handle, P(q_lat), self.fi, self.rs, self.L, self.bw, rflag,
+                                               P(self.A), P(shift), P(self.target), P(lin[0].weight.data),
+                                               P(lin[0].bias.data), P(lin[1].weight.data), P(lin[1].bias.data),
+                                               P(lin[2].weight.data), P(lin[2].bias.data), self.T, P(self.g_grid),
+                                               P(self.g_dec), P(self.g_dec[self.L * CF:]), P(self.mlp_out), st)
+                if rc == _lib.ERR_UNSUPPORTED:
+                    self.fused = False     # e.g. a level whose node box does not fit a tile: the three-kernel path
+                else:
+                    chk(rc)
+                    fused_done = True
+            if not fused_done:
+                chk(lib.shacira_latent_forward_planned(self.plan.handle, P(q_lat), self.fi, self.rs, self.L, self.bw, self.C,
+                                                       self.F, rflag, P(self.A), P(shift), 0, P(self.feats), st))
+                # the MLP kernel reduces max |feature gradient| per column on the way; the tiled backward takes its
+                # fixed-point scales from that bound and skips its own pass over the gradient rows
+                bound = P(self.gfeat_max) if self.use_bound else None
+                chk(lib.shacira_mlp_mse_step_bounded(P(self.feats), P(self.target), self.n, self.IN, self.H, self.OUT,
+                                                     P(lin[0].weight.data), P(lin[0].bias.data), P(lin[1].weight.data),
+                                                     P(lin[1].bias.data), P(lin[2].weight.data), P(lin[2].bias.data),
+                                                     P(self.gfeat), None, P(self.mlp_out), bound, st))
+                chk(lib.shacira_latent_backward_planned_bounded(self.plan.handle, P(self.gfeat), P(q_lat), self.fi, self.rs,
+                                                                self.L, self.bw, self.C, self.F, rflag, P(self.A), 0, self.T, 0,
+                                                                P(self.g_grid), P(self.g_dec), P(self.g_dec[self.L * CF:]),
+                                                                bound, st))
             cur.wait_stream(self.side)
             chk(lib.shacira_adam_step_sum_mul(P(lat), P(self.g_grid), P(gmul), P(self.g_ent), P(self.lam), 1.0 / self.T,
                                               P(self.m_table), P(self.v_table), self.T * self.C, self.grid_lr,
