@@ -438,6 +438,39 @@ int shacira_host_session_step_async(shacira_host_session_t* session, const float
                                     float* grad_latents, float* grad_A, float* grad_shift, int32_t* slot);
 int shacira_host_session_wait(shacira_host_session_t* session, int32_t slot);
 
+/* ---- exchange step of the ray-batch data-parallel path over NVLink / NVSwitch peer memory ------------
+ * north_star: "NeRF ray batches are data-parallel, with the hash-table/latent gradient allreduced ... over NVLink".
+ * The reference is single-GPU (no counterpart file); the NCCL form is shacira_b200.dp.GradArena.allreduce.
+ * One process per GPU. Every rank allocates its gradient arena with shacira_peer_alloc (cudaMalloc: bytes rounded up to
+ * 256 + a 256-byte flag block at shacira_peer_flags_offset(bytes), all zero), exports it (64-byte CUDA IPC handle,
+ * exchanged by the host: torch.distributed.all_gather_object in shacira_b200/peer.py) and maps every other rank's
+ * arena with shacira_peer_open. Inside ONE process that drives several GPUs the pointers are used directly after
+ * shacira_peer_enable_access. */
+int64_t shacira_peer_flags_offset(int64_t bytes);
+int shacira_peer_alloc(int64_t bytes, void** ptr);
+int shacira_peer_free(void* ptr);
+int shacira_peer_export(void* ptr, void* handle64);
+int shacira_peer_open(const void* handle64, void** ptr);
+int shacira_peer_close(void* ptr);
+int shacira_peer_enable_access(int32_t device, int32_t peer_device);
+/* SUM all-reduce of `numel` floats (multiple of 4) in place over `world` in {2, 4, 8} arenas: bufs[p] = rank p's arena as
+ * mapped into this process (bufs[rank] = the local one). ONE kernel per rank: cross-GPU barrier, rank r reduces slice r
+ * from all arenas in rank order and stores the sum into all arenas, cross-GPU barrier. Every rank must make the same
+ * sequence of calls; the result is bit-identical on all ranks. Stream-ordered and CUDA-graph capturable (the barrier
+ * epoch lives on the device). */
+int shacira_peer_allreduce(void* const* bufs, int64_t flags_offset, int32_t rank, int32_t world, int64_t numel,
+                           shacira_stream_t stream);
+/* The same pass with the latent table's Adam step inside (reduce-scatter + sharded optimizer state + all-gather): the
+ * first `table_numel` floats of the arena are the table's gradient; the owner of a slice applies torch.optim.Adam's
+ * update to params[rank] there (exp_avg / exp_avg_sq: this rank's slice-sized state, passed as pointers already offset
+ * so that element i of the table is exp_avg[i]; `step` = device float, steps taken so far, advanced by the caller),
+ * stores the updated parameters into every rank's table params[p] and clears the gradient slots. The rest of the arena
+ * (decoder / density-model gradients) is all-reduced as above. */
+int shacira_peer_allreduce_adam(void* const* bufs, int64_t flags_offset, int32_t rank, int32_t world, int64_t numel,
+                                void* const* params, int64_t table_numel, float* exp_avg, float* exp_avg_sq,
+                                const float* step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                shacira_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,15 @@ SIGNATURES = {
     "shacira_mlp_mse_step": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "shacira_mlp_mse_step_bounded": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "shacira_fit_tile_step": (ctypes.c_int, [_vp, _vp, _c_int32_p, _c_int32_p, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "shacira_peer_flags_offset": (_i64, [_i64]),
+    "shacira_peer_alloc": (ctypes.c_int, [_i64, ctypes.POINTER(_vp)]),
+    "shacira_peer_free": (ctypes.c_int, [_vp]),
+    "shacira_peer_export": (ctypes.c_int, [_vp, _vp]),
+    "shacira_peer_open": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    "shacira_peer_close": (ctypes.c_int, [_vp]),
+    "shacira_peer_enable_access": (ctypes.c_int, [_i32, _i32]),
+    "shacira_peer_allreduce": (ctypes.c_int, [ctypes.POINTER(_vp), _i64, _i32, _i32, _i64, _vp]),
+    "shacira_peer_allreduce_adam": (ctypes.c_int, [ctypes.POINTER(_vp), _i64, _i32, _i32, _i64, ctypes.POINTER(_vp), _i64, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp]),
     "shacira_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _i32, _vp]),
     "shacira_adam_step_sum": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_float, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _i32, _i32, _vp]),
     "shacira_adam_step_sum_mul": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_float, _vp, _vp, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _i32, _i32, _vp]),

@@ -20,7 +20,7 @@
 //     tile's fixed-point node accumulators (shared-memory integer atomics, lane-replicated on coarse levels) with the
 //     cell / weights it kept from the forward.
 // The fixed-point scale of a level needs max |gradient| over the tile, which is only known when the tile's last pass
-// has run the MLP: the scale follows a RUNNING maximum (one bit of headroom) and, when a later pass outgrows it, the
+// has run the MLP: the scale follows a RUNNING maximum (`headroom` bits of slack) and, when a later pass outgrows it, the
 // accumulators of that level are shifted right once (exact up to one rounding per shift). After the last pass every
 // touched node is flushed with one float RED, decoder gradients (scale / shift of the affine latent decoder) are
 // applied per node there, as in latent_bwd_tiled_kernel's scatter-g mode.
@@ -41,8 +41,8 @@ constexpr int kExpUnset = 127, kExpNan = -128;
 #ifndef SHACIRA_FIT_MIN_CTAS
 #define SHACIRA_FIT_MIN_CTAS 4
 #endif
-#ifndef SHACIRA_FIT_HEADROOM
-#define SHACIRA_FIT_HEADROOM 1
+#ifndef SHACIRA_FIT_PREFETCH
+#define SHACIRA_FIT_PREFETCH 0   // measured: no gain, 8 registers
 #endif
 
 struct FitSmem {
@@ -53,10 +53,8 @@ struct FitSmem {
     float hi[16];
     float b1[16], b2[16], b3[4];
     float g[kFitParams + 1];                   // block reduction of the MLP gradients
-    unsigned pmax[16];                         // running max |feature gradient| per level of this tile (bit patterns)
-    int exp2[16];                              // exponent of the level's fixed-point scale (kExpUnset / kExpNan)
-    int shift[16];                             // pending right shift of the level's accumulators
-    float scale[16], inv[16];
+    unsigned pmax[2][16];                      // running max |feature gradient| per level of this tile (bit patterns)
+    float inv[16];                             // 2^-exponent of the level's fixed-point scale (flush)
     double loss;
     float gA, gS;
 };
@@ -83,7 +81,7 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
                 const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ W3,
                 const float* __restrict__ b3, float grad_scale, float* __restrict__ grad_latents,
                 float* __restrict__ grad_A, float* __restrict__ grad_shift, double* __restrict__ loss_sum,
-                float* __restrict__ grad_params, int cap, int cap_acc) {
+                float* __restrict__ grad_params, int cap, int cap_acc, int headroom) {
     constexpr int H = 16, OUT = 3, L = 16;
     constexpr int oW1 = 0, ob1 = oW1 + 256, oW2 = ob1 + H, ob2 = oW2 + 256, oW3 = ob2 + H, ob3 = oW3 + OUT * H;
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -140,7 +138,8 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
             int4* z4 = reinterpret_cast<int4*>(s_acc);
             for (int e = tid; e < n4; e += kTileThreads) z4[e] = make_int4(0, 0, 0, 0);
         }
-        if (tid < 16) { S.pmax[tid] = 0u; S.exp2[tid] = kExpUnset; S.scale[tid] = 0.0f; }
+        if (tid < 32) S.pmax[tid >> 4][tid & 15] = 0u;
+        int my_exp = kExpUnset, pb = 0;   // lane l < 16 (of every warp): exponent of level l's fixed-point scale
         int kbits = 0;
         while ((1 << kbits) < (end - beg)) ++kbits;
         __syncthreads();
@@ -165,6 +164,9 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
         request(beg);
         for (int p0 = beg; p0 < end; p0 += kFitPts) {
             const int base = p0 + warp * 16;
+#if !SHACIRA_FIT_PREFETCH
+            if (p0 > beg) request(p0);
+#endif
             bool live[2];
             double tu[2][2];
             float T[4];
@@ -176,7 +178,9 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r) T[r] = TN[r];
+#if SHACIRA_FIT_PREFETCH
             if (p0 + kFitPts < end) request(p0 + kFitPts);
+#endif
             // ---- grid forward: the A fragment of the first layer, entry by entry -------------------------------------
             float X[1][2][4];
             int slot[2][4];
@@ -301,6 +305,10 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
             tc_wgrad<2, kTcStride, 1>(bufB, bufA, g, t, accW1);   // dW1[i][m] = sum_p d1[p][i] x[p][m]
 
             // ---- running per-level maximum of |gx| over the tile (this warp's 16 points) -----------------------------------
+            // Two copies of the maxima, used by alternating passes: a warp that is already in the next pass adds to the
+            // other copy, so after this pass's barrier every warp reads the SAME values and takes the same decision
+            // without a second barrier (lane l < 16 of every warp tracks level l's exponent in a register).
+            unsigned* pm = S.pmax[pb];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float m = nan_max(fabsf(D[0][j >> 1][j & 1]), fabsf(D[0][j >> 1][2 + (j & 1)]));
@@ -308,47 +316,38 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
                 mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, 4));
                 mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, 8));
                 mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, 16));
-                if (g == 0 && mb > S.pmax[lev[j]]) atomicMax(&S.pmax[lev[j]], mb);
+                if (g == 0 && mb > pm[lev[j]]) atomicMax(&pm[lev[j]], mb);
             }
             __syncthreads();
-            bool grow = false;
-            if (tid < L) {
-                const unsigned mb = S.pmax[tid];
+            int sh = 0;
+            {
+                const unsigned mb = pm[lane & 15];
                 const float m = __uint_as_float(mb);
-                const int old = S.exp2[tid];
-                int e = old, sh = 0;
+                if (warp == 0 && lane < L && mb != 0u) atomicMax(&S.pmax[pb ^ 1][lane], mb);   // the running maximum carries over
+                const int old = my_exp;
                 if (m != m || mb >= 0x7f800000u) {
-                    e = kExpNan;    // Inf / NaN upstream: the level's nodes of this tile are poisoned at flush time
+                    my_exp = kExpNan;   // Inf / NaN upstream: the level's nodes of this tile are poisoned at flush time
                 } else if (mb != 0u && old != kExpNan) {
                     const int ex = (int)((mb >> 23) & 0xffu) - 126;   // m < 2^ex
                     const int need = max(-126, min(min(30 - kbits, 21) - ex, 126));
                     if (old == kExpUnset) {
-                        e = max(-126, need - SHACIRA_FIT_HEADROOM);   // accumulators still zero: nothing to shift
+                        my_exp = max(-126, need - headroom);   // accumulators still zero: nothing to shift
                     } else if (need < old) {
-                        e = max(-126, need - SHACIRA_FIT_HEADROOM);
-                        sh = old - e;
+                        my_exp = max(-126, need - headroom);
+                        sh = old - my_exp;
                     }
                 }
-                if (e != old) {
-                    S.exp2[tid] = e;
-                    const bool fin = e != kExpNan && e != kExpUnset;
-                    S.scale[tid] = fin ? __int_as_float((127 + e) << 23) : 0.0f;
-                }
-                S.shift[tid] = sh;
-                grow = sh > 0;
             }
-            if (__syncthreads_or(grow)) {
+            pb ^= 1;
+            if (__any_sync(0xffffffffu, sh > 0)) {   // uniform over the CTA: every warp evaluated the same numbers
                 // a level outgrew its scale: shift its accumulators (round to nearest), then go on at the new scale
-                for (int e = tid; e < tg.acc_total; e += kTileThreads) {
-                    int a = 0, b = L;   // last level with acc_off <= e
-                    while (b - a > 1) {
-                        const int mid = (a + b) >> 1;
-                        if (tg.acc_off[mid] <= e) a = mid; else b = mid;
-                    }
-                    const int sh = S.shift[a];
-                    if (sh > 0) {
+                for (int l = 0; l < L; ++l) {
+                    const int shl = __shfl_sync(0xffffffffu, sh, l);
+                    if (shl <= 0) continue;
+                    const int a0 = tg.acc_off[l], a1 = (l + 1 < L) ? tg.acc_off[l + 1] : tg.acc_total;
+                    for (int e = a0 + tid; e < a1; e += kTileThreads) {
                         const int v = s_acc[e];
-                        s_acc[e] = sh >= 31 ? 0 : ((v + (1 << (sh - 1))) >> sh);
+                        s_acc[e] = shl >= 31 ? 0 : ((v + (1 << (shl - 1))) >> shl);
                     }
                 }
                 __syncthreads();
@@ -357,7 +356,8 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int l = lev[j];
-                const float sc = S.scale[l];
+                const int ej = __shfl_sync(0xffffffffu, my_exp, l);
+                const float sc = (ej == kExpNan || ej == kExpUnset) ? 0.0f : __int_as_float((127 + ej) << 23);
                 const int amul = tg.acc_mul[l], w0 = tg.w[l][0];
                 const int abase = tg.acc_off[l] + (amul == 32 ? lane : 0) - tg.off[l] * amul;
 #pragma unroll
@@ -384,7 +384,7 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
             fpre[u] = (e < tg.total) ? __ldg(tab + e) : make_int2(0, 0);
         }
         if (tid < L) {
-            const int e = S.exp2[tid];
+            const int e = my_exp;
             S.inv[tid] = (e == kExpNan) ? __int_as_float(0x7fc00000) : ((e == kExpUnset) ? 0.0f : __int_as_float((127 - e) << 23));
         }
         __syncthreads();

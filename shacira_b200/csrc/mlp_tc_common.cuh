@@ -34,11 +34,19 @@ __device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ahi)[4], co
     mma_tf32(c, ahi, bh0, bh1);
 }
 // the same with the two small terms in an accumulator of their own: two independent HMMA chains per output tile
+// (SHACIRA_TC_SPLIT_CHAINS=0: one chain, 4 registers per tile less)
+#ifndef SHACIRA_TC_SPLIT_CHAINS
+#define SHACIRA_TC_SPLIT_CHAINS 0   // measured on B200: no gain in either kernel
+#endif
 __device__ __forceinline__ void mma3s(float (&c)[4], float (&sm)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4],
                                       uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+#if SHACIRA_TC_SPLIT_CHAINS
     mma_tf32(sm, alo, bh0, bh1);
     mma_tf32(c, ahi, bh0, bh1);
     mma_tf32(sm, ahi, bl0, bl1);
+#else
+    mma3(c, ahi, alo, bh0, bh1, bl0, bl1);
+#endif
 }
 // accumulator-layout tile (c0 c1 | c2 c3 = rows g | g+8, columns 2t, 2t+1) -> A fragment under the K permutation
 __device__ __forceinline__ void tile_to_a(const float (&c)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {

@@ -551,10 +551,11 @@ int shacira_fit_tile_step(const shacira_plan_t* plan, const float* latents, cons
     static const int per_sm = [] { const char* e = getenv("SHACIRA_FIT_CTAS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : SHACIRA_FIT_MIN_CTAS; }();
     int blocks = sm_count() * per_sm;
     if (blocks > p->ntiles) blocks = p->ntiles;
+    static const int headroom = [] { const char* e = getenv("SHACIRA_FIT_HEADROOM"); int v = e ? atoi(e) : 1; return v < 0 ? 0 : (v > 8 ? 8 : v); }();
     const float scale = (float)(2.0 / ((double)p->n * 3.0));
     fit_tile_kernel<<<blocks, kTileThreads, smem, s>>>(view_of(p), latents, lp, A, shift, round_flag, target_sorted, W1, b1,
                                                        W2, b2, W3, b3, scale, grad_latents, grad_A, grad_shift,
-                                                       (double*)mlp_out, (float*)((char*)mlp_out + 8), cap, cap_acc);
+                                                       (double*)mlp_out, (float*)((char*)mlp_out + 8), cap, cap_acc, headroom);
     LAUNCHED();
     return SHACIRA_OK;
 }
