@@ -438,6 +438,19 @@ int shacira_host_session_step_async(shacira_host_session_t* session, const float
                                     float* grad_latents, float* grad_A, float* grad_shift, int32_t* slot);
 int shacira_host_session_wait(shacira_host_session_t* session, int32_t slot);
 
+/* The optimizer side of the image-fit step as ONE launch: shacira_multi_adam_step's segments (one CTA each), the latent
+ * table's shacira_adam_step_sum_mul (gradient cleared after use) and -- when w_hat != NULL -- the NEXT step's SGA sample
+ * of the updated latents (shacira_sga_quantize's math with the draw index *rng_step, advanced by the call; dw may be NULL).
+ * Both step counters advance by one. Reference: optimizer.step() over the groups of base_trainer.py:206-266 followed by
+ * basic_latent_decoder.py:183-191 at the start of the next step. */
+int shacira_fit_optimizer_step(const shacira_adam_seg_t* segs, int32_t num_segs, float* table, float* grad,
+                               const float* grad_mul, const float* grad2, const float* scale2, float scale2_mul,
+                               float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float weight_decay, float beta1,
+                               float beta2, float eps, float* step_small, float* step_table, const float* scale,
+                               const float* div, float* A_out, int32_t latent_dim, int32_t feature_dim,
+                               const float* temperature, int32_t diff_sampling, uint64_t seed, uint64_t* rng_step,
+                               float* w_hat, float* dw, uint32_t* ticket, shacira_stream_t stream);
+
 /* ---- exchange step of the ray-batch data-parallel path over NVLink / NVSwitch peer memory ------------
  * north_star: "NeRF ray batches are data-parallel, with the hash-table/latent gradient allreduced ... over NVLink".
  * The reference is single-GPU (no counterpart file); the NCCL form is shacira_b200.dp.GradArena.allreduce.

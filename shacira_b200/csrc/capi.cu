@@ -10,6 +10,7 @@
 #include "mlp_kernels.cuh"
 #include "render_kernels.cuh"
 #include "sga_kernels.cuh"
+#include "optimizer_kernels.cuh"
 
 using namespace shacira;
 
@@ -603,6 +604,48 @@ int shacira_sga_quantize(const float* latents, const float* uniforms, int64_t co
         sga_advance_kernel<<<1, 1, 0, s>>>((unsigned long long*)rng_step);
         LAUNCHED();
     }
+    return SHACIRA_OK;
+}
+
+int shacira_fit_optimizer_step(const shacira_adam_seg_t* segs, int32_t num_segs, float* table, float* grad,
+                               const float* grad_mul, const float* grad2, const float* scale2, float scale2_mul,
+                               float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float weight_decay, float beta1,
+                               float beta2, float eps, float* step_small, float* step_table, const float* scale,
+                               const float* div, float* A_out, int32_t latent_dim, int32_t feature_dim,
+                               const float* temperature, int32_t diff_sampling, uint64_t seed, uint64_t* rng_step,
+                               float* w_hat, float* dw, uint32_t* ticket, shacira_stream_t stream) {
+    if (!step_small || !step_table || !ticket || num_segs < 0 || (num_segs > 0 && !segs))
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "fit_optimizer_step: NULL argument");
+    if (num_segs > SHACIRA_MAX_ADAM_SEGS)
+        return fail(SHACIRA_ERR_UNSUPPORTED, "fit_optimizer_step: %d segments (max %d)", num_segs, SHACIRA_MAX_ADAM_SEGS);
+    if (!table || !grad || !exp_avg || !exp_avg_sq || n <= 0)
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "fit_optimizer_step: table / grad / state is NULL");
+    if (w_hat && !temperature) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "fit_optimizer_step: SGA needs the temperature");
+    if (A_out && (!scale || !div || latent_dim < 1 || feature_dim < 1))
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "fit_optimizer_step: A_out needs scale, div, latent_dim, feature_dim");
+    AdamSegs S;
+    memset(&S, 0, sizeof(S));
+    S.num = num_segs;
+    bool owner = false;
+    for (int i = 0; i < num_segs; ++i) {
+        const shacira_adam_seg_t& g = segs[i];
+        if (!g.param || !g.grad || !g.exp_avg || !g.exp_avg_sq || g.n < 0 || g.grad_rows < 1 ||
+            (g.grad_div && g.div_group < 1))
+            return fail(SHACIRA_ERR_INVALID_ARGUMENT, "fit_optimizer_step: bad segment %d", i);
+        S.seg[i] = g;
+        owner |= (g.param == scale);
+    }
+    if (A_out && !owner) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "fit_optimizer_step: A_out needs `scale` among the segments");
+    TableAdam Tb;
+    memset(&Tb, 0, sizeof(Tb));
+    Tb.p = table; Tb.g = grad; Tb.gmul = grad_mul; Tb.g2 = grad2; Tb.scale2 = scale2; Tb.mul2 = scale2_mul;
+    Tb.m = exp_avg; Tb.v = exp_avg_sq; Tb.n = n; Tb.lr = lr; Tb.weight_decay = weight_decay;
+    Tb.temperature = temperature; Tb.diff_sampling = diff_sampling; Tb.seed = seed;
+    Tb.rng_step = (unsigned long long*)rng_step; Tb.w_hat = w_hat; Tb.dw = dw;
+    const int64_t blocks = num_segs + (n + 1023) / 1024;
+    fit_optimizer_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(S, Tb, beta1, beta2, eps, step_small, step_table,
+                                                                         scale, div, A_out, latent_dim, feature_dim, ticket);
+    LAUNCHED();
     return SHACIRA_OK;
 }
 

@@ -30,60 +30,57 @@ __device__ __forceinline__ float sga_uniform(uint32_t e, uint32_t base) {
     return (float)(h >> 8) * 5.9604644775390625e-08f;   // 24-bit uniform in [0, 1)
 }
 
+// One element: w_hat = floor(w) p0 + ceil(w) p1 with (p0, p1) the relaxed one-hot sample, and d w_hat / d w
+// (basic_latent_decoder.py:183-191). u0, u1: the two U(0, 1) draws of the element.
+__device__ __forceinline__ void sga_sample(float x, float u0, float u1, float tau, int diff_sampling, float& w_hat, float& d) {
+    const float inv_tau = 1.0f / tau;
+    const float bound = (float)(1.0 - 1e-6);             // basic_latent_decoder.py:13 epsilon
+    const float ueps = 1.1920928955078125e-07f;           // torch.finfo(float32).eps (clamp_probs)
+    const float wf = floorf(x), wc = wf + 1.0f;
+    const float df_raw = x - wf, dc_raw = wc - x;
+    const float df = fminf(fmaxf(df_raw, -bound), bound), dc = fminf(fmaxf(dc_raw, -bound), bound);
+    const float tf = tanhf(df), tc = tanhf(dc);
+    float lf = -tf / tau, lc = -tc / tau;
+    {   // Categorical(logits=...): logits - logsumexp(logits)
+        const float m = fmaxf(lf, lc);
+        const float lse = m + logf(expf(lf - m) + expf(lc - m));
+        lf -= lse;
+        lc -= lse;
+    }
+    u0 = fminf(fmaxf(u0, ueps), 1.0f - ueps);
+    u1 = fminf(fmaxf(u1, ueps), 1.0f - ueps);
+    const float g0 = -logf(-logf(u0)), g1 = -logf(-logf(u1));
+    const float s0 = (lf + g0) / tau, s1 = (lc + g1) / tau;
+    const float m2 = fmaxf(s0, s1);
+    const float lse2 = m2 + logf(expf(s0 - m2) + expf(s1 - m2));
+    const float p0 = expf(s0 - lse2), p1 = expf(s1 - lse2);
+    w_hat = __fadd_rn(__fmul_rn(wf, p0), __fmul_rn(wc, p1));
+    if (diff_sampling) {
+        const float in_f = (df_raw >= -bound && df_raw <= bound) ? (1.0f - tf * tf) : 0.0f;
+        const float in_c = (dc_raw >= -bound && dc_raw <= bound) ? (1.0f - tc * tc) : 0.0f;
+        d = p0 * p1 * (in_f + in_c) * inv_tau * inv_tau;
+    } else {
+        d = p0 + p1;
+    }
+}
+__device__ __forceinline__ uint32_t sga_rng_base(unsigned long long st, unsigned long long rng_seed) {
+    return (uint32_t)st * 0x9E3779B9u + (uint32_t)(st >> 32) * 0x7F4A7C15u + (uint32_t)rng_seed * 0x85EBCA6Bu +
+           (uint32_t)(rng_seed >> 32) * 0xC2B2AE35u + 0x68E31DA4u;
+}
+
 __global__ void __launch_bounds__(kSgaBlock)
 sga_quantize_kernel(const float* __restrict__ w, const float* __restrict__ u, int64_t n,
                     const float* __restrict__ temperature, int diff_sampling, unsigned long long rng_seed,
                     const unsigned long long* __restrict__ rng_step, float* __restrict__ w_hat, float* __restrict__ dw) {
     const float tau = __ldg(temperature);
-    const float inv_tau = 1.0f / tau;
-    uint32_t base = 0u;
-    if (!u) {
-        const unsigned long long st = rng_step ? *rng_step : 0ull;
-        base = (uint32_t)st * 0x9E3779B9u + (uint32_t)(st >> 32) * 0x7F4A7C15u + (uint32_t)rng_seed * 0x85EBCA6Bu +
-               (uint32_t)(rng_seed >> 32) * 0xC2B2AE35u + 0x68E31DA4u;
-    }
-    const float bound = (float)(1.0 - 1e-6);             // basic_latent_decoder.py:13 epsilon
-    const float ueps = 1.1920928955078125e-07f;           // torch.finfo(float32).eps (clamp_probs)
+    const uint32_t base = u ? 0u : sga_rng_base(rng_step ? *rng_step : 0ull, rng_seed);
     for (int64_t i = (int64_t)blockIdx.x * kSgaBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kSgaBlock) {
-        const float x = w[i];
-        const float wf = floorf(x), wc = wf + 1.0f;
-        const float df_raw = x - wf, dc_raw = wc - x;
-        const float df = fminf(fmaxf(df_raw, -bound), bound), dc = fminf(fmaxf(dc_raw, -bound), bound);
-        const float tf = tanhf(df), tc = tanhf(dc);
-        float lf = -tf / tau, lc = -tc / tau;
-        {   // Categorical(logits=...): logits - logsumexp(logits)
-            const float m = fmaxf(lf, lc);
-            const float lse = m + logf(expf(lf - m) + expf(lc - m));
-            lf -= lse;
-            lc -= lse;
-        }
-        float u0, u1;
-        if (u) {
-            u0 = u[2 * i];
-            u1 = u[2 * i + 1];
-        } else {
-            u0 = sga_uniform((uint32_t)(2 * i), base);
-            u1 = sga_uniform((uint32_t)(2 * i + 1), base);
-        }
-        u0 = fminf(fmaxf(u0, ueps), 1.0f - ueps);
-        u1 = fminf(fmaxf(u1, ueps), 1.0f - ueps);
-        const float g0 = -logf(-logf(u0)), g1 = -logf(-logf(u1));
-        const float s0 = (lf + g0) / tau, s1 = (lc + g1) / tau;
-        const float m2 = fmaxf(s0, s1);
-        const float lse2 = m2 + logf(expf(s0 - m2) + expf(s1 - m2));
-        const float p0 = expf(s0 - lse2), p1 = expf(s1 - lse2);
-        w_hat[i] = __fadd_rn(__fmul_rn(wf, p0), __fmul_rn(wc, p1));
-        if (dw) {
-            float d;
-            if (diff_sampling) {
-                const float in_f = (df_raw >= -bound && df_raw <= bound) ? (1.0f - tf * tf) : 0.0f;
-                const float in_c = (dc_raw >= -bound && dc_raw <= bound) ? (1.0f - tc * tc) : 0.0f;
-                d = p0 * p1 * (in_f + in_c) * inv_tau * inv_tau;
-            } else {
-                d = p0 + p1;
-            }
-            dw[i] = d;
-        }
+        const float u0 = u ? u[2 * i] : sga_uniform((uint32_t)(2 * i), base);
+        const float u1 = u ? u[2 * i + 1] : sga_uniform((uint32_t)(2 * i + 1), base);
+        float wh, d;
+        sga_sample(w[i], u0, u1, tau, diff_sampling, wh, d);
+        w_hat[i] = wh;
+        if (dw) dw[i] = d;
     }
 }
 

@@ -94,6 +94,8 @@ class ImageFitStep:
         self.use_bound = self.IN == 16 and os.environ.get("SHACIRA_MLP_IMPL", "tc") == "tc"   # the tensor-core kernel
         # one tile-resident kernel for grid forward + MLP / MSE + grid backward where its shapes apply (SHACIRA_FIT_FUSED=0:
         # the three-kernel path, kept for every other shape and as the parity reference of the fused kernel)
+        self.opt_fused = os.environ.get("SHACIRA_FIT_OPT_FUSED", "1") != "0"   # one optimizer launch (incl. next SGA sample)
+        self._what_valid = False
         self.fused = (os.environ.get("SHACIRA_FIT_FUSED", "1") != "0" and self.use_bound and self.H == 16 and
                       self.OUT == 3 and self.C == 1 and self.F == 1 and self.L == 16 and amap[0].shape[0] == 1)
         n_par = self.H * self.IN + self.H + self.H * self.H + self.H + self.OUT * self.H + self.OUT
@@ -132,6 +134,7 @@ class ImageFitStep:
         # the bit-rate kernel depends on nothing but the table: it runs on a forked stream beside the grid / MLP
         # kernels (it is latency bound: 17 us alone) and joins before the optimizer kernels
         self.side = torch.cuda.Stream(device=dev)
+        self._forked = torch.cuda.Event()
         segs = []
 
         def seg(param, grad, n, lr, wd, rows=1, stride=0, scale=None, mul=1.0, div=None, group=1, zero=False):
@@ -192,16 +195,22 @@ class ImageFitStep:
     def set_lambda(self, value):
         self.lam.fill_(float(value))
 
-    def set_temperature(self, value):
-        """SGA temperature of this epoch (image_trainer.py:131-133; base_trainer.py:155-157 builds the schedule)."""
+    def set_temperature(self, value, refresh=False):
+        """SGA temperature of this epoch (image_trainer.py:131-133; base_trainer.py:155-157 builds the schedule). The
+        sample of the NEXT step has already been drawn by the previous optimizer launch with the temperature of that
+        moment: refresh=True discards it, so the new value applies from the very next step (an epoch-boundary caller);
+        without it the new value applies one step later (a per-step schedule under CUDA-graph replay)."""
         self.temperature.fill_(float(value))
         self.grid.latent_dec.temperature = float(value)
+        if refresh:
+            self._what_valid = False
 
     def set_sga(self, flag):
         """Switch between SGA and straight-through rounding (the trainer turns SGA off once epoch / max_epochs >
         decay_period). A captured CUDA graph holds the mode it was captured with: re-capture after switching."""
         self.sga = bool(flag)
         self.grid.latent_dec.use_sga = bool(flag)
+        self._what_valid = False
 
     def draw_noise(self, generator=None):
         """U(-0.5, 0.5) per latent (latent_grid.py:128); with a CPU generator the reference's stream."""
@@ -227,23 +236,17 @@ class ImageFitStep:
         with torch.cuda.device(self.dev):
             st = _lib._stream()
             cur = torch.cuda.current_stream(self.dev)
-            self.side.wait_stream(cur)
-            with torch.cuda.stream(self.side):
-                if self.device_noise:
-                    chk(lib.shacira_entropy_bits_rng(P(lat), self.noise_seed, P(self.rng_step), self.T, self.C,
-                                                     P(self.prob), self.num_prob_layers, self.fi, self.L, P(self.bits),
-                                                     P(self.g_ent), P(self.g_prob), P(self.ent_scratch),
-                                                     self.ent_scratch.numel(), _lib._stream()))
-                else:
-                    chk(lib.shacira_entropy_bits(P(lat), P(self.noise), self.T, self.C, P(self.prob),
-                                                 self.num_prob_layers, self.fi, self.L, P(self.bits), P(self.g_ent),
-                                                 P(self.g_prob), P(self.ent_scratch), self.ent_scratch.numel(),
-                                                 _lib._stream()))
+            self._forked.record(cur)   # the table as the previous optimizer launch left it
             q_lat, rflag, gmul = lat, 1, None
+            # SGA sample of this step: normally already there -- the previous step's optimizer launch sampled the latents it
+            # had just updated (shacira_fit_optimizer_step); drawn here on the first step, after set_sga / a refreshing
+            # set_temperature, and whenever the draws are injected (parity runs)
+            prefetch = self.sga and self.opt_fused and self.sga_uniforms is None
             if self.sga:
-                chk(lib.shacira_sga_quantize(P(lat), P(self.sga_uniforms), self.T * self.C, P(self.temperature),
-                                             1 if self.diff_sampling else 0, self.noise_seed + 0x5A17,
-                                             P(self.sga_rng_step), P(self.w_hat), P(self.dw), st))
+                if not (prefetch and self._what_valid):
+                    chk(lib.shacira_sga_quantize(P(lat), P(self.sga_uniforms), self.T * self.C, P(self.temperature),
+                                                 1 if self.diff_sampling else 0, self.noise_seed + 0x5A17,
+                                                 P(self.sga_rng_step), P(self.w_hat), P(self.dw), st))
                 q_lat, rflag, gmul = self.w_hat, 0, self.dw
             CF = self.C * self.F
             if not self.has_shift:
@@ -276,15 +279,44 @@ class ImageFitStep:
                                                                 self.L, self.bw, self.C, self.F, rflag, P(self.A), 0, self.T, 0,
                                                                 P(self.g_grid), P(self.g_dec), P(self.g_dec[self.L * CF:]),
                                                                 bound, st))
+            # The bit-rate kernel only depends on the table: it is launched AFTER the tile kernel, on a forked stream. The tile
+            # kernel's persistent CTAs own every register of the SM during their first wave of tiles; the bit-rate CTAs move
+            # into the slots its second, partial wave leaves free (1024 tiles over 592 CTA slots) instead of delaying it.
+            self.side.wait_event(self._forked)
+            with torch.cuda.stream(self.side):
+                if self.device_noise:
+                    chk(lib.shacira_entropy_bits_rng(P(lat), self.noise_seed, P(self.rng_step), self.T, self.C,
+                                                     P(self.prob), self.num_prob_layers, self.fi, self.L, P(self.bits),
+                                                     P(self.g_ent), P(self.g_prob), P(self.ent_scratch),
+                                                     self.ent_scratch.numel(), _lib._stream()))
+                else:
+                    chk(lib.shacira_entropy_bits(P(lat), P(self.noise), self.T, self.C, P(self.prob),
+                                                 self.num_prob_layers, self.fi, self.L, P(self.bits), P(self.g_ent),
+                                                 P(self.g_prob), P(self.ent_scratch), self.ent_scratch.numel(),
+                                                 _lib._stream()))
             cur.wait_stream(self.side)
-            chk(lib.shacira_adam_step_sum_mul(P(lat), P(self.g_grid), P(gmul), P(self.g_ent), P(self.lam), 1.0 / self.T,
-                                              P(self.m_table), P(self.v_table), self.T * self.C, self.grid_lr,
-                                              self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                              P(self.step_table), 0, 1, st))
-            chk(lib.shacira_multi_adam_step(ctypes.cast(self.segs, ctypes.c_void_p), self.nseg, self.betas[0],
-                                            self.betas[1], self.eps, P(self.step_small), P(self.step_table),
-                                            P(self.layer.scale.data), P(dec.div.data), P(self.A), self.C, self.F,
-                                            P(self.adam_ticket), st))
+            if self.opt_fused:
+                # ONE optimizer launch: small tensors + table Adam + the next step's SGA sample (csrc/optimizer_kernels.cuh)
+                chk(lib.shacira_fit_optimizer_step(ctypes.cast(self.segs, ctypes.c_void_p), self.nseg, P(lat), P(self.g_grid),
+                                                   P(gmul), P(self.g_ent), P(self.lam), 1.0 / self.T, P(self.m_table),
+                                                   P(self.v_table), self.T * self.C, self.grid_lr, self.weight_decay,
+                                                   self.betas[0], self.betas[1], self.eps, P(self.step_small),
+                                                   P(self.step_table), P(self.layer.scale.data), P(dec.div.data), P(self.A),
+                                                   self.C, self.F, P(self.temperature), 1 if self.diff_sampling else 0,
+                                                   self.noise_seed + 0x5A17, P(self.sga_rng_step),
+                                                   P(self.w_hat) if prefetch else None, P(self.dw) if prefetch else None,
+                                                   P(self.adam_ticket), st))
+                self._what_valid = prefetch
+            else:
+                chk(lib.shacira_adam_step_sum_mul(P(lat), P(self.g_grid), P(gmul), P(self.g_ent), P(self.lam), 1.0 / self.T,
+                                                  P(self.m_table), P(self.v_table), self.T * self.C, self.grid_lr,
+                                                  self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                                  P(self.step_table), 0, 1, st))
+                chk(lib.shacira_multi_adam_step(ctypes.cast(self.segs, ctypes.c_void_p), self.nseg, self.betas[0],
+                                                self.betas[1], self.eps, P(self.step_small), P(self.step_table),
+                                                P(self.layer.scale.data), P(dec.div.data), P(self.A), self.C, self.F,
+                                                P(self.adam_ticket), st))
+                self._what_valid = False
 
     # ---- results of the last step (device tensors; reading them synchronises) -------------------
     def rgb_loss(self):

@@ -202,3 +202,43 @@ def test_fit_step_fused_matches_unfused_after_steps(lib, monkeypatch):
         assert float((p.data - q.data).abs().max()) <= 2e-3 * float(q.data.abs().max())
     fa.close()
     fb.close()
+
+
+def test_one_launch_optimizer_matches_separate_kernels(lib, monkeypatch):
+    """shacira_fit_optimizer_step (small tensors + table Adam + the NEXT step's SGA sample in one launch) against the
+    separate SGA / table-Adam / small-tensor-Adam launches: the draws are counter based (same index -> same sample), so
+    six steps (four with SGA, two with STE rounding) end in the same parameters."""
+    import copy
+    from shacira_b200.image_fit import ImageFitStep
+    dev = torch.device("cuda", 0)
+    grid, mlp, coords, target = _setup(dev, 14)
+    grid2, mlp2 = copy.deepcopy(grid), copy.deepcopy(mlp)
+    fa = ImageFitStep(grid, mlp, coords, target, device_noise=True, noise_seed=3)
+    monkeypatch.setenv("SHACIRA_FIT_OPT_FUSED", "0")
+    fb = ImageFitStep(grid2, mlp2, coords, target, device_noise=True, noise_seed=3)
+    monkeypatch.delenv("SHACIRA_FIT_OPT_FUSED")
+    assert fa.opt_fused and not fb.opt_fused
+    for it in range(6):
+        for f in (fa, fb):
+            if it == 0:
+                f.set_sga(True)
+                f.set_temperature(0.7)
+            if it == 4:
+                f.set_sga(False)
+            f.set_lambda(1e-3)
+        n0 = lib.launch_count()
+        fa.step()
+        na = lib.launch_count() - n0
+        fb.step()
+        nb = lib.launch_count() - n0 - na
+        if 0 < it < 4:
+            assert na == 3 and nb == 6, (na, nb)      # bit-rate + fused tile kernel + optimizer, against + SGA, its counter, two Adams
+        assert abs(float(fa.rgb_loss()) - float(fb.rgb_loss())) <= 1e-5 * float(fb.rgb_loss())
+        assert abs(float(fa.total_bits()) - float(fb.total_bits())) <= 1e-6 * float(fb.total_bits())
+    assert float((grid.codebook.data - grid2.codebook.data).abs().max()) <= 1e-5 * float(grid2.codebook.data.abs().max())
+    for p, q in zip(mlp.parameters(), mlp2.parameters()):
+        assert float((p.data - q.data).abs().max()) <= 1e-5 * float(q.data.abs().max())
+    # (the one-launch form has drawn one sample ahead -- discarded when SGA was switched off)
+    assert int(fa.sga_rng_step) == int(fb.sga_rng_step) + 1
+    fa.close()
+    fb.close()
