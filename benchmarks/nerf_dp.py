@@ -20,7 +20,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from shacira_b200 import _lib, dp  # noqa: E402
+from shacira_b200 import _lib, dp, peer  # noqa: E402
 from shacira_b200.grids import geometric_resolutions  # noqa: E402
 
 RAYS, SAMPLES_PER_RAY = 4096, 128
@@ -61,7 +61,24 @@ def run(dev, rank, world, steps=30, warmup=5, planned=True, overlap_binning=True
     prob = torch.randn((4, 3, C), device=dev) * 0.3
     r0, r1 = dp.shard_rows(T, rank, world)
     ent_stream = torch.cuda.Stream(device=dev)
-    arena = dp.GradArena([glat, gA, gS, gprob, gbits])     # one flat gradient buffer: the exchange step is ONE all-reduce
+    # one flat gradient buffer: the exchange step is ONE launch -- the peer-memory kernel over NVLink (csrc/peer_kernels.cuh,
+    # every rank maps every arena through CUDA IPC) or, with SHACIRA_DP_EXCHANGE=nccl / where IPC is unavailable, ncclAllReduce
+    arena, exchange_kind = None, "nccl all-reduce"
+    # auto: the peer-memory kernel, else nccl. Measured at 8 GPUs (profiles/r02q_peer_exchange.md): peer kernel 91 us,
+    # multicast kernel 89 us, ncclAllReduce 124 us for the 24.4 MB arena; the multicast form needs torch's private
+    # symmetric-memory allocator for its mapping and is only taken when asked for.
+    want = os.environ.get("SHACIRA_DP_EXCHANGE", "auto")
+    grads = [glat, gA, gS, gprob, gbits]
+    if world in (2, 4, 8) and want == "multimem":
+        arena = peer.McArena.try_create(grads)
+        if arena is not None:
+            exchange_kind = "NVSwitch multicast kernel (one launch per rank: barrier, multimem.ld_reduce own slice, multimem.st to all, barrier)"
+    if arena is None and world in (2, 4, 8) and want in ("auto", "peer", "multimem"):
+        arena = peer.PeerArena.try_create(grads)
+        if arena is not None:
+            exchange_kind = "peer-memory kernel over NVLink (one launch per rank: barrier, reduce own slice from all arenas, store to all arenas, barrier)"
+    if arena is None:
+        arena = dp.GradArena([glat, gA, gS, gprob, gbits])
     lib = _lib.load()
     fi, _ = _lib._i32_array(first)
     rs, _ = _lib._i32_array(res)
@@ -144,11 +161,17 @@ def run(dev, rank, world, steps=30, warmup=5, planned=True, overlap_binning=True
     if planned:
         for p in plans:
             p.close()
+    nbytes = arena.flat.numel() * 4
+    if isinstance(arena, (peer.PeerArena, peer.McArena)):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        arena.close()
     bps = algorithmic_bytes_per_sample()
     return {"workload": "BASELINE cfg4 NeRF-shape ray-batch DP step (re-bin + grid fwd + bwd + grad all-reduce)",
             "n_gpus": world, "scaling": "weak", "rays_per_rank": RAYS, "samples_per_rank": S,
             "ms_per_step": ms, "samples_per_s": S * world / ms * 1e3, "rays_per_s": RAYS * world / ms * 1e3,
-            "allreduce_bytes": arena.flat.numel() * 4,
+            "allreduce_bytes": nbytes, "exchange": exchange_kind,
             "bit_rate_rows_per_rank": (r1 - r0) if entropy else 0, "collectives_per_step": ncoll,
             "ms_per_step_without_exchange": ms_compute, "exposed_collective_us": max(0.0, (ms - ms_compute) * 1e3),
             "bytes_per_sample": bps, "alg_GBs_per_gpu": bps * S / ms / 1e6,

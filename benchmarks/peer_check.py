@@ -64,6 +64,30 @@ def main():
     assert worst <= 1e-6, worst
     out["peer_allreduce_us"] = timed(arena.allreduce, dev, world)
     out["nccl_allreduce_us"] = timed(ref.allreduce, dev, world)
+    # the NVSwitch multicast form (NVLS), where the fabric has it
+    mparams = [mk(T, 1), mk(16, 1, 4), mk(16, 4), mk(4, 3, 1), mk(1)]
+    mc = peer.McArena.try_create(mparams)
+    out["multicast"] = mc is not None
+    if mc is not None:
+        torch.manual_seed(70 + rank)
+        for it in range(2):
+            vals = [torch.randn_like(p) for p in mparams]
+            for p, q, v in zip(mparams, ref.params, vals):
+                p.grad.copy_(v)
+                q.grad.copy_(v)
+            mc.allreduce()
+            ref.allreduce()
+            torch.cuda.synchronize()
+            w = max(float((p.grad - q.grad).abs().max() / q.grad.abs().max()) for p, q in zip(mparams, ref.params))
+            assert w <= 1e-6, w
+            chk = mc.flat.view(torch.int32).to(torch.int64).sum().reshape(1)
+            allc = [torch.zeros_like(chk) for _ in range(world)]
+            dist.all_gather(allc, chk)
+            assert all(int(c) == int(allc[0]) for c in allc), "ranks disagree (multicast)"
+        out["multimem_allreduce_us"] = timed(mc.allreduce, dev, world)
+        torch.cuda.synchronize()
+        dist.barrier()
+        mc.close()
     # graph capture of the peer exchange
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()

@@ -484,6 +484,14 @@ int shacira_peer_allreduce_adam(void* const* bufs, int64_t flags_offset, int32_t
                                 const float* step, float lr, float beta1, float beta2, float eps, float weight_decay,
                                 shacira_stream_t stream);
 
+/* The all-reduce through the NVSwitch multicast object (NVLS): `multicast_ptr` = multicast address of the arena (every
+ * rank's copy bound to one CUDA multicast object; shacira_b200/peer.py maps it with torch's symmetric-memory allocator),
+ * flag_bufs[p] + flags_offset = rank p's 256-byte flag block in plain peer memory (a shacira_peer_alloc buffer). The sum
+ * is formed inside the switch (multimem.ld_reduce) and stored to all copies (multimem.st): one arena's worth of bytes per
+ * GPU and direction instead of 2 (N-1)/N. Same call discipline as shacira_peer_allreduce. */
+int shacira_peer_allreduce_multimem(void* multicast_ptr, void* const* flag_bufs, int64_t flags_offset, int32_t rank,
+                                    int32_t world, int64_t numel, shacira_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,4 +132,28 @@ int shacira_peer_allreduce_adam(void* const* bufs, int64_t flags_offset, int32_t
     return launch_peer<true>(v, numel / 4, ad, (cudaStream_t)stream);
 }
 
+int shacira_peer_allreduce_multimem(void* multicast_ptr, void* const* flag_bufs, int64_t flags_offset, int32_t rank,
+                                    int32_t world, int64_t numel, shacira_stream_t stream) {
+    PeerView v;
+    if (int rc = fill_view(v, flag_bufs, flags_offset, rank, world)) return rc;
+    if (!multicast_ptr) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "peer_allreduce_multimem: multicast pointer is NULL");
+    if (numel <= 0 || (numel & 3) || ((uintptr_t)multicast_ptr & 15))
+        return fail(SHACIRA_ERR_INVALID_ARGUMENT, "peer_allreduce_multimem: numel must be a positive multiple of 4, the pointer 16-byte aligned");
+    const int64_t numel4 = numel / 4;
+    const int64_t per = (numel4 + world - 1) / world;
+    int64_t blocks = (per + kPeerThreads * 4 - 1) / (kPeerThreads * 4);
+    static const int per_sm = [] { const char* e = getenv("SHACIRA_PEER_BLOCKS_PER_SM"); int k = e ? atoi(e) : 0; return k > 0 ? k : 2; }();
+    const int64_t cap = (int64_t)sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (world) {
+        case 2: peer_allreduce_mc_kernel<2><<<(int)blocks, kPeerThreads, 0, s>>>(v, (float*)multicast_ptr, numel4); break;
+        case 4: peer_allreduce_mc_kernel<4><<<(int)blocks, kPeerThreads, 0, s>>>(v, (float*)multicast_ptr, numel4); break;
+        default: peer_allreduce_mc_kernel<8><<<(int)blocks, kPeerThreads, 0, s>>>(v, (float*)multicast_ptr, numel4); break;
+    }
+    LAUNCHED();
+    return SHACIRA_OK;
+}
+
 }  // extern "C"

@@ -129,4 +129,63 @@ peer_allreduce_kernel(const __grid_constant__ PeerView pv, int64_t numel4, const
     }
 }
 
+// ---- the same exchange through the NVSwitch multicast object (NVLS) ---------------------------------------------------------
+// `mc` is the multicast address of the arena (every rank's copy bound to one multicast object; the host side maps it --
+// shacira_b200/peer.py uses torch's symmetric-memory allocator for that plumbing). multimem.ld_reduce returns the SUM of
+// the N copies, added inside the switch; multimem.st stores to all N copies. Per GPU and direction one arena's worth of
+// bytes crosses NVLink instead of 2 (N-1)/N arenas; the barriers are the ones above (flags in plain peer memory).
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st(float* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int N>
+__global__ void __launch_bounds__(kPeerThreads)
+peer_allreduce_mc_kernel(const __grid_constant__ PeerView pv, float* __restrict__ mc, int64_t numel4) {
+    unsigned* mine = pv.flags[pv.rank];
+    const unsigned epoch = ld_acquire_sys(mine + 16) + 1u;
+    if (blockIdx.x == 0 && threadIdx.x < N) {
+        __threadfence_system();
+        st_release_sys(pv.flags[threadIdx.x] + pv.rank, epoch);
+    }
+    if (threadIdx.x < N) {
+        while ((int)(ld_acquire_sys(mine + threadIdx.x) - epoch) < 0) {}
+    }
+    __syncthreads();
+    const int64_t per = (numel4 + N - 1) / N;
+    const int64_t begin = per * pv.rank, end = min(numel4, begin + per);
+    constexpr int U = 4;   // pieces in flight per thread
+    const int64_t stride = (int64_t)gridDim.x * kPeerThreads;
+    for (int64_t i0 = begin + (int64_t)blockIdx.x * kPeerThreads + threadIdx.x; i0 < end; i0 += stride * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i0 + u * stride < end) v[u] = multimem_ld_reduce_add(mc + 4 * (i0 + u * stride));
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i0 + u * stride < end) multimem_st(mc + 4 * (i0 + u * stride), v[u]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) s_last = (atomicAdd(mine + 17, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x < N) {
+        __threadfence_system();
+        st_release_sys(pv.flags[threadIdx.x] + 8 + pv.rank, epoch);
+        while ((int)(ld_acquire_sys(mine + 8 + threadIdx.x) - epoch) < 0) {}
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mine[17] = 0u;
+        st_release_sys(mine + 16, epoch);
+    }
+}
+
 }  // namespace shacira

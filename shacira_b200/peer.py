@@ -91,6 +91,32 @@ class PeerBuffer:
                 self.ptr = 0
 
 
+def _agreed_create(cls, params, group):
+    """cls(params, connect=False) then .connect(group) on every rank; None on EVERY rank if any step failed anywhere."""
+    params = list(params)
+    dev = params[0].device
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    arena = None
+    try:
+        arena = cls(params, group=group, connect=False)
+    except Exception:
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0:
+        if arena is not None:
+            arena.close()
+        return None
+    try:
+        arena.connect(group)
+    except Exception:
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0:
+        arena.close()
+        return None
+    return arena
+
+
 class PeerArena:
     """One flat float32 gradient buffer for a set of parameters (every `.grad` is a view into it, as dp.GradArena), in
     peer-mapped memory. `allreduce()` = shacira_peer_allreduce on the current stream."""
@@ -108,7 +134,17 @@ class PeerArena:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
         self.offsets = offs
         if connect:
-            self.buf.connect(group)
+            self.connect(group)
+
+    def connect(self, group=None):
+        self.buf.connect(group)
+        return self
+
+    @classmethod
+    def try_create(cls, params, group=None):
+        """PeerArena on every rank, or None on every rank (the ranks agree: CUDA IPC can be unavailable, e.g. across
+        containers or without peer access) -- the caller then keeps the NCCL form (dp.GradArena). Collective."""
+        return _agreed_create(cls, params, group)
 
     def zero_(self):
         self.flat.zero_()
@@ -138,6 +174,59 @@ class PeerArena:
             p.grad = None
         self.flat = None
         self.buf.close()
+
+
+class McArena:
+    """The gradient arena bound to an NVSwitch multicast object (NVLS): `allreduce()` = shacira_peer_allreduce_multimem,
+    the sum is formed inside the switch. The multicast mapping (cuMulticastCreate / bind over the ranks) is plumbing:
+    torch's symmetric-memory allocator does it; the cross-GPU barrier flags live in a small PeerBuffer of our own."""
+
+    def __init__(self, params, group=None, connect=True):
+        import torch.distributed._symmetric_memory as symm
+        self.params = list(params)
+        dev = self.params[0].device
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 3) & ~3
+        self.numel = total
+        self.flat = symm.empty(total, dtype=torch.float32, device=dev)
+        self.flat.zero_()
+        for p, off in zip(self.params, offs):
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+        self.flags = PeerBuffer(4, dev)
+        self.hdl = None
+        if connect:
+            self.connect(group)
+
+    def connect(self, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.hdl = symm.rendezvous(self.flat, group if group is not None else dist.group.WORLD)
+        if not int(getattr(self.hdl, "multicast_ptr", 0) or 0):
+            raise RuntimeError("no multicast support on this fabric")
+        self.flags.connect(group)
+        return self
+
+    @classmethod
+    def try_create(cls, params, group=None):
+        return _agreed_create(cls, params, group)
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def allreduce(self):
+        f = self.flags
+        with torch.cuda.device(f.device):
+            _lib._check(f.lib.shacira_peer_allreduce_multimem(ctypes.c_void_p(int(self.hdl.multicast_ptr)), f.ptr_array(),
+                                                              f.flags_offset, f.rank, f.world, self.numel, _lib._stream()))
+        return 1
+
+    def close(self):
+        for p in self.params:
+            p.grad = None
+        self.flags.close()
+        self.hdl = None
+        self.flat = None
 
 
 class PeerTable:
