@@ -479,9 +479,11 @@ def main():
                          "psnr_after_400_steps": one["psnr"], "bpp_after_400_steps": one["bpp"],
                          "note": "step times extrapolated to the reference's 60 000-step fits; the per-epoch size() / "
                                  "PSNR / best-state bookkeeping of ImageTrainer is not part of the step",
-                         "step": "shacira_b200.image_fit.ImageFitStep: (SGA kernel) + grid fwd/bwd + tensor-core decoder "
-                                 "MLP/MSE + bit-rate loss + Adam of every parameter group, native launches in one CUDA "
-                                 "graph per phase; independent images, no collective"}
+                         "step": "shacira_b200.image_fit.ImageFitStep: 3 launches per step in one CUDA graph per phase -- the "
+                                 "tile-resident fused kernel (grid forward + tensor-core decoder MLP / MSE + grid "
+                                 "backward, shacira_fit_tile_step), the bit-rate kernel beside it, and ONE optimizer "
+                                 "launch (Adam of every parameter group + the next step's SGA sample, "
+                                 "shacira_fit_optimizer_step); independent images, no collective"}
         except Exception as e:  # the headline metric must not depend on the extra measurement
             kodak_fit = {"unavailable": repr(e)[:200]}
 

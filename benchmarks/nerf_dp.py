@@ -162,6 +162,8 @@ def run(dev, rank, world, steps=30, warmup=5, planned=True, overlap_binning=True
         for p in plans:
             p.close()
     nbytes = arena.flat.numel() * 4
+    if isinstance(arena, (peer.PeerArena, peer.McArena)) and arena.timed_out():
+        exchange_kind += " -- A BARRIER TIMED OUT: numbers of this run are invalid"
     if isinstance(arena, (peer.PeerArena, peer.McArena)):
         torch.cuda.synchronize()
         if world > 1:

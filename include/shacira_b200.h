@@ -473,6 +473,10 @@ int shacira_peer_enable_access(int32_t device, int32_t peer_device);
  * epoch lives on the device). */
 int shacira_peer_allreduce(void* const* bufs, int64_t flags_offset, int32_t rank, int32_t world, int64_t numel,
                            shacira_stream_t stream);
+/* The cross-GPU barriers give up after ~4 s of polling (a peer that died must not hang this GPU) and raise an error word
+ * in the local flag block: *timed_out = 1 if any exchange on `buf` (the LOCAL arena / flag buffer) has timed out since it
+ * was allocated. Synchronises the device. */
+int shacira_peer_status(const void* buf, int64_t flags_offset, int32_t* timed_out);
 /* The same pass with the latent table's Adam step inside (reduce-scatter + sharded optimizer state + all-gather): the
  * first `table_numel` floats of the arena are the table's gradient; the owner of a slice applies torch.optim.Adam's
  * update to params[rank] there (exp_avg / exp_avg_sq: this rank's slice-sized state, passed as pointers already offset

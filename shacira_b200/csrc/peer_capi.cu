@@ -97,6 +97,14 @@ int shacira_peer_enable_access(int32_t device, int32_t peer_device) {
     return SHACIRA_OK;
 }
 
+int shacira_peer_status(const void* buf, int64_t flags_offset, int32_t* timed_out) {
+    if (!buf || !timed_out) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "peer_status: NULL");
+    unsigned w = 0;
+    CUDA_OK(cudaMemcpy(&w, (const char*)buf + flags_offset + 18 * sizeof(unsigned), sizeof(w), cudaMemcpyDeviceToHost));
+    *timed_out = w ? 1 : 0;
+    return SHACIRA_OK;
+}
+
 int shacira_peer_allreduce(void* const* bufs, int64_t flags_offset, int32_t rank, int32_t world, int64_t numel,
                            shacira_stream_t stream) {
     PeerView v;

@@ -26,7 +26,7 @@ constexpr int kPeerThreads = 512;
 
 struct PeerView {
     float* buf[kPeerMax];          // every rank's arena (index = rank), as mapped into THIS process
-    unsigned* flags[kPeerMax];     // every rank's flag block: [0, 8) barrier A, [8, 16) barrier B, [16] epoch, [17] ticket
+    unsigned* flags[kPeerMax];     // every rank's flag block: [0, 8) barrier A, [8, 16) barrier B, [16] epoch, [17] ticket, [18] error word (barrier timeout)
     int rank, world;
 };
 
@@ -45,6 +45,16 @@ __device__ __forceinline__ float4 ld_peer(const float* p) {   // coherent at sys
 }
 __device__ __forceinline__ void st_peer(float* p, float4 v) {
     asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Spin until *p has reached `epoch` (wrap-safe). Bounded: ~4 s of polling, then the kernel gives up, raises the error word
+// of the local flag block (slot 18) and goes on -- a peer that died must not hang this GPU forever (the host reads the
+// word with shacira_peer_status; the data of such a call is garbage).
+__device__ __forceinline__ void peer_wait(const unsigned* p, unsigned epoch, unsigned* err) {
+    for (unsigned spins = 0; (int)(ld_acquire_sys(p) - epoch) < 0; ++spins) {
+        if (spins > 64u) __nanosleep(200);
+        if (spins > 20000000u) { atomicExch(err, 1u); return; }
+    }
 }
 
 struct PeerAdam {       // optional fused optimizer on the owner's slice (all pointers in the owner's memory, nullptr = off)
@@ -67,7 +77,7 @@ peer_allreduce_kernel(const __grid_constant__ PeerView pv, int64_t numel4, const
         st_release_sys(pv.flags[threadIdx.x] + pv.rank, epoch);       // "rank pv.rank has arrived" into peer threadIdx.x
     }
     if (threadIdx.x < N) {
-        while ((int)(ld_acquire_sys(mine + threadIdx.x) - epoch) < 0) {}   // local spin: peers write into my flags
+        peer_wait(mine + threadIdx.x, epoch, mine + 18);   // local spin: peers write into my flags
     }
     __syncthreads();
     // ---- slice pv.rank: reduce from all arenas, broadcast into all arenas -----------------------------------------------
@@ -120,7 +130,7 @@ peer_allreduce_kernel(const __grid_constant__ PeerView pv, int64_t numel4, const
     if (threadIdx.x < N) {
         __threadfence_system();
         st_release_sys(pv.flags[threadIdx.x] + 8 + pv.rank, epoch);
-        while ((int)(ld_acquire_sys(mine + 8 + threadIdx.x) - epoch) < 0) {}
+        peer_wait(mine + 8 + threadIdx.x, epoch, mine + 18);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -154,7 +164,7 @@ peer_allreduce_mc_kernel(const __grid_constant__ PeerView pv, float* __restrict_
         st_release_sys(pv.flags[threadIdx.x] + pv.rank, epoch);
     }
     if (threadIdx.x < N) {
-        while ((int)(ld_acquire_sys(mine + threadIdx.x) - epoch) < 0) {}
+        peer_wait(mine + threadIdx.x, epoch, mine + 18);
     }
     __syncthreads();
     const int64_t per = (numel4 + N - 1) / N;
@@ -179,7 +189,7 @@ peer_allreduce_mc_kernel(const __grid_constant__ PeerView pv, float* __restrict_
     if (threadIdx.x < N) {
         __threadfence_system();
         st_release_sys(pv.flags[threadIdx.x] + 8 + pv.rank, epoch);
-        while ((int)(ld_acquire_sys(mine + 8 + threadIdx.x) - epoch) < 0) {}
+        peer_wait(mine + 8 + threadIdx.x, epoch, mine + 18);
     }
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -79,6 +79,13 @@ class PeerBuffer:
     def ptr_array(self):
         return (ctypes.c_void_p * self.world)(*self.ptrs)
 
+    def timed_out(self):
+        """True if a cross-GPU barrier of an exchange on this buffer gave up (a peer never arrived). Synchronises."""
+        v = ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            _lib._check(self.lib.shacira_peer_status(ctypes.c_void_p(self.ptr), self.flags_offset, ctypes.byref(v)))
+        return bool(v.value)
+
     def close(self):
         with torch.cuda.device(self.device):
             for q in self._opened:
@@ -157,6 +164,9 @@ class PeerArena:
                                                      _lib._stream()))
         return 1
 
+    def timed_out(self):
+        return self.buf.timed_out()
+
     def allreduce_adam(self, table, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         """The same pass with the Adam step of `table` (a PeerTable whose gradient is the FIRST tensor of this arena)
         on the owner's slice; the updated table is broadcast, its gradient slots come back zeroed."""
@@ -220,6 +230,9 @@ class McArena:
             _lib._check(f.lib.shacira_peer_allreduce_multimem(ctypes.c_void_p(int(self.hdl.multicast_ptr)), f.ptr_array(),
                                                               f.flags_offset, f.rank, f.world, self.numel, _lib._stream()))
         return 1
+
+    def timed_out(self):
+        return self.flags.timed_out()
 
     def close(self):
         for p in self.params:
