@@ -441,15 +441,23 @@ int shacira_host_session_wait(shacira_host_session_t* session, int32_t slot);
 /* The optimizer side of the image-fit step as ONE launch: shacira_multi_adam_step's segments (one CTA each), the latent
  * table's shacira_adam_step_sum_mul (gradient cleared after use) and -- when w_hat != NULL -- the NEXT step's SGA sample
  * of the updated latents (shacira_sga_quantize's math with the draw index *rng_step, advanced by the call; dw may be NULL).
- * Both step counters advance by one. Reference: optimizer.step() over the groups of base_trainer.py:206-266 followed by
- * basic_latent_decoder.py:183-191 at the start of the next step. */
+ * Both step counters advance by one. With ent_params != NULL (latent_dim 1; grad2 must be NULL) the table pass also
+ * evaluates the bit-rate loss of the latents BEFORE their update (shacira_entropy_bits' math and noise stream: ent_noise
+ * [n] injected, or NULL = drawn in the kernel from (ent_seed, *ent_rng_step), advanced by the call): bits[0] = total bits,
+ * the latents' bit-rate gradient goes straight into the table's Adam (scaled by *scale2 x scale2_mul), the density model's
+ * gradients grad_ent_params[4][3] are reduced by the last CTA, which then runs the segments whose gradient lives there.
+ * ent_scratch: at least 52 bytes per 1024 table entries. Reference: optimizer.step() over the groups of
+ * base_trainer.py:206-266, latent_grid.py:122-136, and basic_latent_decoder.py:183-191 at the start of the next step. */
 int shacira_fit_optimizer_step(const shacira_adam_seg_t* segs, int32_t num_segs, float* table, float* grad,
                                const float* grad_mul, const float* grad2, const float* scale2, float scale2_mul,
                                float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float weight_decay, float beta1,
                                float beta2, float eps, float* step_small, float* step_table, const float* scale,
                                const float* div, float* A_out, int32_t latent_dim, int32_t feature_dim,
                                const float* temperature, int32_t diff_sampling, uint64_t seed, uint64_t* rng_step,
-                               float* w_hat, float* dw, uint32_t* ticket, shacira_stream_t stream);
+                               float* w_hat, float* dw, const float* ent_params, int32_t ent_layers,
+                               const float* ent_noise, uint64_t ent_seed, uint64_t* ent_rng_step, double* bits,
+                               float* grad_ent_params, void* ent_scratch, int64_t ent_scratch_bytes, uint32_t* ticket,
+                               shacira_stream_t stream);
 
 /* ---- exchange step of the ray-batch data-parallel path over NVLink / NVSwitch peer memory ------------
  * north_star: "NeRF ray batches are data-parallel, with the hash-table/latent gradient allreduced ... over NVLink".

@@ -613,7 +613,10 @@ int shacira_fit_optimizer_step(const shacira_adam_seg_t* segs, int32_t num_segs,
                                float beta2, float eps, float* step_small, float* step_table, const float* scale,
                                const float* div, float* A_out, int32_t latent_dim, int32_t feature_dim,
                                const float* temperature, int32_t diff_sampling, uint64_t seed, uint64_t* rng_step,
-                               float* w_hat, float* dw, uint32_t* ticket, shacira_stream_t stream) {
+                               float* w_hat, float* dw, const float* ent_params, int32_t ent_layers,
+                               const float* ent_noise, uint64_t ent_seed, uint64_t* ent_rng_step, double* bits,
+                               float* grad_ent_params, void* ent_scratch, int64_t ent_scratch_bytes, uint32_t* ticket,
+                               shacira_stream_t stream) {
     if (!step_small || !step_table || !ticket || num_segs < 0 || (num_segs > 0 && !segs))
         return fail(SHACIRA_ERR_INVALID_ARGUMENT, "fit_optimizer_step: NULL argument");
     if (num_segs > SHACIRA_MAX_ADAM_SEGS)
@@ -642,6 +645,17 @@ int shacira_fit_optimizer_step(const shacira_adam_seg_t* segs, int32_t num_segs,
     Tb.m = exp_avg; Tb.v = exp_avg_sq; Tb.n = n; Tb.lr = lr; Tb.weight_decay = weight_decay;
     Tb.temperature = temperature; Tb.diff_sampling = diff_sampling; Tb.seed = seed;
     Tb.rng_step = (unsigned long long*)rng_step; Tb.w_hat = w_hat; Tb.dw = dw;
+    if (ent_params) {
+        if (latent_dim != 1) return fail(SHACIRA_ERR_UNSUPPORTED, "fit_optimizer_step: the folded bit-rate loss needs latent_dim = 1");
+        if (!bits || !grad_ent_params || !ent_scratch || ent_layers < 1)
+            return fail(SHACIRA_ERR_INVALID_ARGUMENT, "fit_optimizer_step: bit-rate outputs / scratch are NULL");
+        if (ent_scratch_bytes < (int64_t)sizeof(float) * kOptEnt * ((n + 1023) / 1024))
+            return fail(SHACIRA_ERR_INVALID_ARGUMENT, "fit_optimizer_step: bit-rate scratch too small");
+        if (grad2) return fail(SHACIRA_ERR_INVALID_ARGUMENT, "fit_optimizer_step: grad2 and the folded bit-rate loss exclude each other");
+        Tb.ent_params = ent_params; Tb.ent_layers = ent_layers; Tb.ent_noise = ent_noise; Tb.ent_seed = ent_seed;
+        Tb.ent_rng_step = (unsigned long long*)ent_rng_step; Tb.ent_partials = (float*)ent_scratch; Tb.bits = bits;
+        Tb.g_prob = grad_ent_params;
+    }
     const int64_t blocks = num_segs + (n + 1023) / 1024;
     fit_optimizer_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(S, Tb, beta1, beta2, eps, step_small, step_table,
                                                                          scale, div, A_out, latent_dim, feature_dim, ticket);

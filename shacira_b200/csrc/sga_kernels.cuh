@@ -40,20 +40,18 @@ __device__ __forceinline__ void sga_sample(float x, float u0, float u1, float ta
     const float df_raw = x - wf, dc_raw = wc - x;
     const float df = fminf(fmaxf(df_raw, -bound), bound), dc = fminf(fmaxf(dc_raw, -bound), bound);
     const float tf = tanhf(df), tc = tanhf(dc);
-    float lf = -tf / tau, lc = -tc / tau;
-    {   // Categorical(logits=...): logits - logsumexp(logits)
-        const float m = fmaxf(lf, lc);
-        const float lse = m + logf(expf(lf - m) + expf(lc - m));
-        lf -= lse;
-        lc -= lse;
-    }
+    // The reference normalises the two logits (Categorical: logits - logsumexp), adds the Gumbels, divides by tau and
+    // takes a softmax. Both normalisations cancel in the only quantity the softmax of TWO entries depends on, the
+    // difference of its arguments:  s0 - s1 = ((tc - tf) / tau + g0 - g1) / tau,  with
+    // g0 - g1 = log(log(u1) / log(u0)).  p0 = sigmoid(s0 - s1), p1 = sigmoid(s1 - s0): 2 tanh + 3 log + 2 exp instead of
+    // 2 tanh + 6 log + 4 exp, equal to the reference's chain to float rounding (golden vectors: tests/test_sga_gpu.py).
     u0 = fminf(fmaxf(u0, ueps), 1.0f - ueps);
     u1 = fminf(fmaxf(u1, ueps), 1.0f - ueps);
-    const float g0 = -logf(-logf(u0)), g1 = -logf(-logf(u1));
-    const float s0 = (lf + g0) / tau, s1 = (lc + g1) / tau;
-    const float m2 = fmaxf(s0, s1);
-    const float lse2 = m2 + logf(expf(s0 - m2) + expf(s1 - m2));
-    const float p0 = expf(s0 - lse2), p1 = expf(s1 - lse2);
+    const float dg = logf(logf(u1) / logf(u0));          // g0 - g1 (both logs are negative: the ratio is positive)
+    const float ds = ((tc - tf) / tau + dg) / tau;         // s0 - s1
+    const float e = expf(-fabsf(ds));                      // stable two-way softmax
+    const float big = 1.0f / (1.0f + e), small = e * big;
+    const float p0 = ds >= 0.0f ? big : small, p1 = ds >= 0.0f ? small : big;
     w_hat = __fadd_rn(__fmul_rn(wf, p0), __fmul_rn(wc, p1));
     if (diff_sampling) {
         const float in_f = (df_raw >= -bound && df_raw <= bound) ? (1.0f - tf * tf) : 0.0f;

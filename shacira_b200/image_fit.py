@@ -96,6 +96,9 @@ class ImageFitStep:
         # the three-kernel path, kept for every other shape and as the parity reference of the fused kernel)
         self.opt_fused = os.environ.get("SHACIRA_FIT_OPT_FUSED", "1") != "0"   # one optimizer launch (incl. next SGA sample)
         self._what_valid = False
+        # the bit-rate loss evaluated inside the optimizer launch's table pass (latent_dim 1): no bit-rate launch, no
+        # forked stream, the latents' bit-rate gradient never goes through memory
+        self.ent_in_opt = self.opt_fused and self.C == 1 and os.environ.get("SHACIRA_FIT_ENT_FUSED", "1") != "0"
         self.fused = (os.environ.get("SHACIRA_FIT_FUSED", "1") != "0" and self.use_bound and self.H == 16 and
                       self.OUT == 3 and self.C == 1 and self.F == 1 and self.L == 16 and amap[0].shape[0] == 1)
         n_par = self.H * self.IN + self.H + self.H * self.H + self.H + self.OUT * self.H + self.OUT
@@ -279,33 +282,38 @@ class ImageFitStep:
                                                                 self.L, self.bw, self.C, self.F, rflag, P(self.A), 0, self.T, 0,
                                                                 P(self.g_grid), P(self.g_dec), P(self.g_dec[self.L * CF:]),
                                                                 bound, st))
-            # The bit-rate kernel only depends on the table: it is launched AFTER the tile kernel, on a forked stream. The tile
-            # kernel's persistent CTAs own every register of the SM during their first wave of tiles; the bit-rate CTAs move
-            # into the slots its second, partial wave leaves free (1024 tiles over 592 CTA slots) instead of delaying it.
-            self.side.wait_event(self._forked)
-            with torch.cuda.stream(self.side):
-                if self.device_noise:
-                    chk(lib.shacira_entropy_bits_rng(P(lat), self.noise_seed, P(self.rng_step), self.T, self.C,
-                                                     P(self.prob), self.num_prob_layers, self.fi, self.L, P(self.bits),
-                                                     P(self.g_ent), P(self.g_prob), P(self.ent_scratch),
-                                                     self.ent_scratch.numel(), _lib._stream()))
-                else:
-                    chk(lib.shacira_entropy_bits(P(lat), P(self.noise), self.T, self.C, P(self.prob),
-                                                 self.num_prob_layers, self.fi, self.L, P(self.bits), P(self.g_ent),
-                                                 P(self.g_prob), P(self.ent_scratch), self.ent_scratch.numel(),
-                                                 _lib._stream()))
-            cur.wait_stream(self.side)
+            # The bit-rate loss: normally evaluated inside the optimizer launch's table pass (ent_in_opt). Otherwise its own
+            # kernel on a forked stream, launched AFTER the tile kernel (it only depends on the table).
+            ent_folded = self.ent_in_opt and self.opt_fused
+            if not ent_folded:
+                self.side.wait_event(self._forked)
+                with torch.cuda.stream(self.side):
+                    if self.device_noise:
+                        chk(lib.shacira_entropy_bits_rng(P(lat), self.noise_seed, P(self.rng_step), self.T, self.C,
+                                                         P(self.prob), self.num_prob_layers, self.fi, self.L, P(self.bits),
+                                                         P(self.g_ent), P(self.g_prob), P(self.ent_scratch),
+                                                         self.ent_scratch.numel(), _lib._stream()))
+                    else:
+                        chk(lib.shacira_entropy_bits(P(lat), P(self.noise), self.T, self.C, P(self.prob),
+                                                     self.num_prob_layers, self.fi, self.L, P(self.bits), P(self.g_ent),
+                                                     P(self.g_prob), P(self.ent_scratch), self.ent_scratch.numel(),
+                                                     _lib._stream()))
+                cur.wait_stream(self.side)
             if self.opt_fused:
                 # ONE optimizer launch: small tensors + table Adam + the next step's SGA sample (csrc/optimizer_kernels.cuh)
                 chk(lib.shacira_fit_optimizer_step(ctypes.cast(self.segs, ctypes.c_void_p), self.nseg, P(lat), P(self.g_grid),
-                                                   P(gmul), P(self.g_ent), P(self.lam), 1.0 / self.T, P(self.m_table),
+                                                   P(gmul), None if ent_folded else P(self.g_ent), P(self.lam),
+                                                   1.0 / self.T, P(self.m_table),
                                                    P(self.v_table), self.T * self.C, self.grid_lr, self.weight_decay,
                                                    self.betas[0], self.betas[1], self.eps, P(self.step_small),
                                                    P(self.step_table), P(self.layer.scale.data), P(dec.div.data), P(self.A),
                                                    self.C, self.F, P(self.temperature), 1 if self.diff_sampling else 0,
                                                    self.noise_seed + 0x5A17, P(self.sga_rng_step),
                                                    P(self.w_hat) if prefetch else None, P(self.dw) if prefetch else None,
-                                                   P(self.adam_ticket), st))
+                                                   P(self.prob) if ent_folded else None, self.num_prob_layers,
+                                                   None if self.device_noise else P(self.noise), self.noise_seed,
+                                                   P(self.rng_step), P(self.bits), P(self.g_prob), P(self.ent_scratch),
+                                                   self.ent_scratch.numel(), P(self.adam_ticket), st))
                 self._what_valid = prefetch
             else:
                 chk(lib.shacira_adam_step_sum_mul(P(lat), P(self.g_grid), P(gmul), P(self.g_ent), P(self.lam), 1.0 / self.T,

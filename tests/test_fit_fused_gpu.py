@@ -205,8 +205,8 @@ def test_fit_step_fused_matches_unfused_after_steps(lib, monkeypatch):
 
 
 def test_one_launch_optimizer_matches_separate_kernels(lib, monkeypatch):
-    """shacira_fit_optimizer_step (small tensors + table Adam + the NEXT step's SGA sample in one launch) against the
-    separate SGA / table-Adam / small-tensor-Adam launches: the draws are counter based (same index -> same sample), so
+    """shacira_fit_optimizer_step (bit-rate loss + small tensors + table Adam + the NEXT step's SGA sample in one launch)
+    against the separate bit-rate / SGA / table-Adam / small-tensor-Adam launches: the draws are counter based (same index -> same sample), so
     six steps (four with SGA, two with STE rounding) end in the same parameters."""
     import copy
     from shacira_b200.image_fit import ImageFitStep
@@ -232,9 +232,10 @@ def test_one_launch_optimizer_matches_separate_kernels(lib, monkeypatch):
         fb.step()
         nb = lib.launch_count() - n0 - na
         if 0 < it < 4:
-            assert na == 3 and nb == 6, (na, nb)      # bit-rate + fused tile kernel + optimizer, against + SGA, its counter, two Adams
+            assert na == 2 and nb == 6, (na, nb)      # fused tile kernel + optimizer (bit-rate loss, all Adams, next SGA sample inside)
+                                                     # against bit-rate, SGA, its counter, tile kernel, two Adam launches
         assert abs(float(fa.rgb_loss()) - float(fb.rgb_loss())) <= 1e-5 * float(fb.rgb_loss())
-        assert abs(float(fa.total_bits()) - float(fb.total_bits())) <= 1e-6 * float(fb.total_bits())
+        assert abs(float(fa.total_bits()) - float(fb.total_bits())) <= 1e-5 * float(fb.total_bits())
     assert float((grid.codebook.data - grid2.codebook.data).abs().max()) <= 1e-5 * float(grid2.codebook.data.abs().max())
     for p, q in zip(mlp.parameters(), mlp2.parameters()):
         assert float((p.data - q.data).abs().max()) <= 1e-5 * float(q.data.abs().max())
