@@ -16,7 +16,8 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
     lo = __float_as_uint(v - __uint_as_float(hi)) + 0x1000u;
 }
 // Activations: lo is left unrounded (the tensor core truncates it to 10 mantissa bits: error 2^-21 |v|, the order of the
-// dropped lo*lo term) -- one instruction less per split, ~90 splits per 16 points.
+// dropped lo*lo term) -- one instruction less per split, ~90 splits per 16 points. (Measured and not adopted: hi left
+// unmasked for the hardware to truncate, two instructions per split -- no change in either kernel: they are latency bound.)
 __device__ __forceinline__ void split_tf32_act(float v, uint32_t& hi, uint32_t& lo) {
     hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
     lo = __float_as_uint(v - __uint_as_float(hi));
