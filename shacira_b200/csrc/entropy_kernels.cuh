@@ -234,6 +234,178 @@ entropy_kernel(const float* __restrict__ latents, const float* __restrict__ nois
     }
 }
 
+// ---- validation mode (x = round(w)) through a per-integer table -------------------------------------------------------
+// The NeRF trainer evaluates the bit-rate loss on round(w) every step (multiview_trainer.py:110) and
+// LatentGrid.size()-style reports do the same: the CDF chain then depends on (channel, integer) only. Every CTA builds the
+// table of the 256 integers around 0 in its prologue (one thread per integer: value and the 12 parameter-gradient terms,
+// cdf_forward / cdf_backward as in the per-element kernel, so the numbers are the same) and the table's elements then cost
+// 13 shared-memory loads + 13 adds each instead of ~300 dependent instructions with two transcendental chains. Integers
+// outside [-128, 127] and NaN take the per-element evaluation. Contiguous element ranges per CTA, so a thread walks the
+// levels monotonically (no per-element level search). Partial-row layout, ticket and final reduction as entropy_kernel.
+constexpr int kLutN = 256, kLutK = 13;   // integers per channel; bits | d softplus(h) x4 | d b x4 | d tanh(a) x4
+__global__ void __launch_bounds__(kEntBlock)   // (capped at 64 registers for 4 CTAs per SM it spills: 56 vs 34 us)
+entropy_val_lut_kernel(const float* __restrict__ latents, int64_t total, int C, const float* __restrict__ params,
+                       int num_layers, const __grid_constant__ LevelBounds lb, double* __restrict__ bits,
+                       float* __restrict__ grad_latents, float* __restrict__ grad_params, float* __restrict__ partials,
+                       unsigned* __restrict__ ticket, int64_t per_block) {
+    extern __shared__ float s_lut[];   // [C][kLutK][kLutN]
+    __shared__ float s_sp[4 * kMaxEntC], s_b[4 * kMaxEntC], s_ta[4 * kMaxEntC];
+    __shared__ float s_dsp[4 * kMaxEntC], s_dta[4 * kMaxEntC];
+    __shared__ float s_lvl[SHACIRA_MAX_LEVELS];
+    __shared__ float s_acc[3 * 4 * kMaxEntC];
+    __shared__ double s_total;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 4 * C) {
+        const int k = tid / C, ch = tid % C;
+        const float h = params[(k * 3 + 0) * C + ch];
+        const float a = params[(k * 3 + 2) * C + ch];
+        s_sp[tid] = (h > 20.0f) ? h : log1pf(expf(h));
+        s_dsp[tid] = 1.0f / (1.0f + expf(-h));
+        s_b[tid] = params[(k * 3 + 1) * C + ch];
+        const float t = (k < 3) ? tanhf(a) : 0.0f;
+        s_ta[tid] = t;
+        s_dta[tid] = 1.0f - t * t;
+    }
+    if (tid < SHACIRA_MAX_LEVELS) s_lvl[tid] = 0.0f;
+    for (int e = tid; e < 3 * 4 * kMaxEntC; e += kEntBlock) s_acc[e] = 0.0f;
+    if (tid == 0) s_total = 0.0;
+    __syncthreads();
+    const int m = min(num_layers, 4) - 1;
+    const float inv_ln2 = 1.0f / 0.6931471805599453f;
+    // one element's value and parameter-gradient terms at x (the per-element kernel's formulas)
+    auto eval = [&](float x, int ch, float (&out)[kLutK]) {
+        CdfTrace up, lo;
+        const float Fu = cdf_forward(x + 0.5f, m, s_sp, s_b, s_ta, C, ch, up);
+        const float Fl = cdf_forward(x - 0.5f, m, s_sp, s_b, s_ta, C, ch, lo);
+        const float p = Fu - Fl;
+        const float raw = -logf(p + 1e-10f) * inv_ln2;
+        const float g_raw = (raw >= 0.0f && raw <= 50.0f) ? 1.0f : 0.0f;
+        const float g_p = -g_raw * inv_ln2 / (p + 1e-10f);
+        float d_sp[4] = {0, 0, 0, 0}, d_b[4] = {0, 0, 0, 0}, d_ta[4] = {0, 0, 0, 0};
+        cdf_backward(g_p, m, s_sp, s_ta, C, ch, up, d_sp, d_b, d_ta);
+        cdf_backward(-g_p, m, s_sp, s_ta, C, ch, lo, d_sp, d_b, d_ta);
+        out[0] = fminf(fmaxf(raw, 0.0f), 50.0f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { out[1 + k] = d_sp[k]; out[5 + k] = d_b[k]; out[9 + k] = d_ta[k]; }
+    };
+    for (int ch = 0; ch < C; ++ch) {   // thread tid <-> integer tid - 128
+        float v[kLutK];
+        eval((float)(tid - kLutN / 2), ch, v);
+#pragma unroll
+        for (int k = 0; k < kLutK; ++k) s_lut[(ch * kLutK + k) * kLutN + tid] = v[k];
+    }
+    __syncthreads();
+
+    // terms that can be non-zero with m non-final layers in use: bits, the final layer's (softplus, b), layers j < m
+    unsigned used = 1u | (1u << 4) | (1u << 8);
+    for (int j = 0; j < m; ++j) used |= (1u << (1 + j)) | (1u << (5 + j)) | (1u << (9 + j));
+    const int64_t base = (int64_t)blockIdx.x * per_block, end = min(total, base + per_block);
+    const int ch = (int)((base + tid) % C);   // per_block and 256 are multiples of C: fixed per thread
+    const float* lut = s_lut + (size_t)ch * kLutK * kLutN;
+    float acc[kLutK];
+#pragma unroll
+    for (int k = 0; k < kLutK; ++k) acc[k] = 0.0f;
+    float lvl_bits = 0.0f;
+    int lvl = 0;
+    int64_t next_first = (lb.num_lods > 0) ? (int64_t)lb.first[1] : (int64_t)1 << 62;
+    // this warp's per-level bits so far go to shared memory: one add per warp for lane 0's level, stragglers (a warp spans
+    // at most two levels) add their own
+    auto flush_levels = [&]() {
+        const int l0 = __shfl_sync(0xffffffffu, lvl, 0);
+        const float sum = warp_sum(lvl == l0 ? lvl_bits : 0.0f);
+        if (lane == 0 && sum != 0.0f) atomicAdd(&s_lvl[l0], sum);
+        if (lvl != l0 && lvl_bits != 0.0f) atomicAdd(&s_lvl[lvl], lvl_bits);
+        lvl_bits = 0.0f;
+    };
+    constexpr int U = 4;   // elements per thread in flight (the loop is otherwise bound by one load latency per element)
+    // warp-uniform trip count (the level flush votes across the warp): the warp's first lane decides, lanes past `end` idle
+    for (int64_t ew = base + (tid & ~31); ew < end; ew += (int64_t)U * kEntBlock) {
+        const int64_t e0 = ew + lane;
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t e = e0 + (int64_t)u * kEntBlock;
+            w[u] = (e < end) ? __ldg(latents + e) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t e = e0 + (int64_t)u * kEntBlock;
+            const bool live = e < end;
+            const float xq = rintf(w[u]);
+            float v[kLutK];
+            if (xq >= -128.0f && xq <= 127.0f) {
+                const int q = (int)xq + kLutN / 2;
+#pragma unroll
+                for (int k = 0; k < kLutK; ++k) v[k] = (live && ((used >> k) & 1u)) ? lut[k * kLutN + q] : 0.0f;   // (uniform)
+            } else {
+                eval(xq, ch, v);   // far-out integers, Inf, NaN: the per-element evaluation
+            }
+            if (live && grad_latents) grad_latents[e] = 0.0f;   // round() has zero gradient
+            if (lb.num_lods > 0) {
+                const int64_t row = e / C;
+                if (__any_sync(0xffffffffu, live && row >= next_first)) {
+                    flush_levels();
+                    while (live && lvl + 1 < lb.num_lods && row >= (int64_t)lb.first[lvl + 1]) ++lvl;
+                    next_first = (lvl + 1 < lb.num_lods) ? (int64_t)lb.first[lvl + 1] : (int64_t)1 << 62;
+                }
+                lvl_bits += v[0];
+            }
+#pragma unroll
+            for (int k = 0; k < kLutK; ++k) acc[k] += v[k];
+        }
+    }
+    if (lb.num_lods > 0) flush_levels();
+    const float wsum = warp_sum(acc[0]);
+    if (lane == 0) atomicAdd(&s_total, (double)wsum);
+    if (grad_params) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v0 = acc[1 + k], v1 = acc[5 + k], v2 = acc[9 + k];
+            for (int o = 16; o >= C; o >>= 1) {   // lanes l and l^o share a channel when o is a multiple of C
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+            }
+            if (lane < C) {
+                const int c2 = (int)((base + (tid & ~31) + lane) % C);
+                atomicAdd(&s_acc[(k * 3 + 0) * kMaxEntC + c2], v0);
+                atomicAdd(&s_acc[(k * 3 + 1) * kMaxEntC + c2], v1);
+                atomicAdd(&s_acc[(k * 3 + 2) * kMaxEntC + c2], v2);
+            }
+        }
+    }
+    __syncthreads();
+    const int L = lb.num_lods;
+    const int P = 1 + L + 12 * C;
+    float* mine = partials + (size_t)blockIdx.x * P;
+    if (tid == 0) mine[0] = (float)s_total;
+    if (tid < L) mine[1 + tid] = s_lvl[tid];
+    if (tid < 4 * C) {
+        const int k = tid / C, c2 = tid % C;
+        mine[1 + L + (k * 3 + 0) * C + c2] = s_acc[(k * 3 + 0) * kMaxEntC + c2] * s_dsp[tid];
+        mine[1 + L + (k * 3 + 1) * C + c2] = s_acc[(k * 3 + 1) * kMaxEntC + c2];
+        mine[1 + L + (k * 3 + 2) * C + c2] = (k < 3) ? s_acc[(k * 3 + 2) * kMaxEntC + c2] * s_dta[tid] : 0.0f;
+    }
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int v = tid >> 5; v < P; v += kEntBlock / 32) {
+        double sum = 0.0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) sum += (double)partials[(size_t)b * P + v];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) {
+            if (v <= L) bits[v] = sum;
+            else if (grad_params) grad_params[v - 1 - L] = (float)sum;
+        }
+    }
+    if (tid == 0) *ticket = 0u;
+}
+
 // ---- fused Adam over one tensor ---------------------------------------------------
 // torch.optim.Adam's multi-tensor kernel walks a single tensor in 64 K-element chunks -- 6 CTAs for the
 // 375 k-row latent table of the image fit (39 us measured). One thread per 4 elements here (~3 us), same update:
