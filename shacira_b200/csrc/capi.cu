@@ -355,6 +355,11 @@ int shacira_l2_pin(const void* base, int64_t bytes, shacira_stream_t stream) {
         attr.accessPolicyWindow.num_bytes = 0;
     }
     CUDA_OK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
+    if (!(bytes > 0 && base)) {
+        // clearing: give the carve-out back as well (measured: a 24 MB carve-out left behind costs an unpinned 3D step 13 %)
+        CUDA_OK(cudaCtxResetPersistingL2Cache());
+        CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));
+    }
     return SHACIRA_OK;
 }
 
