@@ -16,10 +16,15 @@ KERNELS = [
     ("lane-pair backward, 3D NeRF shape", r"latent_bwd3d_lp_kernelILi1ELi4E"),
     ("tile-staged coarse levels of the 3D backward", r"latent_bwd_tiled_kernelILi3ELi1ELi4ELb0E"),
     ("decoder MLP + MSE on the tensor cores (mma.sync TF32)", r"mlp16_tc_step_kernelILi2ELi6ELi2E"),
+    ("fused fit kernel: grid forward + MLP / MSE + grid backward (mma.sync TF32, ATOMS fixed point)", r"fit_tile_kernel"),
+    ("one-launch optimizer: bit-rate loss + Adam of every group + next SGA sample", r"fit_optimizer_kernel"),
+    ("peer-memory all-reduce over NVLink, 8 ranks (ld/st .sys on peer pointers, release/acquire flags)", r"peer_allreduce_kernelILi8ELb0E"),
+    ("NVSwitch multicast all-reduce, 8 ranks (multimem.ld_reduce / multimem.st)", r"peer_allreduce_mc_kernelILi8E"),
     ("bit-rate kernel", r"entropy_kernel"),
+    ("bit-rate kernel, validation mode through the per-integer table", r"entropy_val_lut_kernel"),
     ("SGA quantiser", r"sga_quantize_kernel"),
 ]
-KEY = ["REDG", "RED", "ATOMS", "ATOMG", "CREDUX", "REDUX", "LDGSTS", "HMMA", "UTCHMMA", "LDTM", "UTMALDG", "MATCH", "SHFL",
+KEY = ["LDGMC", "MULTIMEM", "MEMBAR", "ERRBAR", "CCTL", "LD", "ST", "ATOM", "REDG", "RED", "ATOMS", "ATOMG", "CREDUX", "REDUX", "LDGSTS", "HMMA", "UTCHMMA", "LDTM", "UTMALDG", "MATCH", "SHFL",
        "LDS", "STS", "LDG", "STG", "F2I", "I2F", "I2FP", "F2F", "FRND", "DMUL", "DFMA", "MUFU", "BAR"]
 
 
