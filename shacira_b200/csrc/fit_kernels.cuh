@@ -151,8 +151,10 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
             const int base = p0 + warp * 16;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                const int j = base + g + 8 * hh;
-                cN[hh] = (j < end) ? __ldg(reinterpret_cast<const float2*>(pv.coords_sorted) + j) : make_float2(0.0f, 0.0f);
+                // rows past the tile's end take the tile's last point: every slot they form is valid, their loss gradient is
+                // zero (row < end below), so they add zeros -- no liveness branches in the lerp and the scatter
+                const int j = min(base + g + 8 * hh, end - 1);
+                cN[hh] = __ldg(reinterpret_cast<const float2*>(pv.coords_sorted) + j);
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -167,12 +169,10 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
 #if !SHACIRA_FIT_PREFETCH
             if (p0 > beg) request(p0);
 #endif
-            bool live[2];
             double tu[2][2];
             float T[4];
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                live[hh] = base + g + 8 * hh < end;
                 tu[hh][0] = unit_coord(cN[hh].x);
                 tu[hh][1] = unit_coord(cN[hh].y);
             }
@@ -202,7 +202,7 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
                     z = __fmaf_rn(v0, __fmul_rn(g0, g1), z);
                     z = __fmaf_rn(v2, __fmul_rn(f0[hh][j], g1), z);
                     z = __fmaf_rn(v3, __fmul_rn(f0[hh][j], f1[hh][j]), z);
-                    X[0][j >> 1][2 * hh + (j & 1)] = live[hh] ? __fmaf_rn(z, Aval, Sval) : 0.0f;
+                    X[0][j >> 1][2 * hh + (j & 1)] = __fmaf_rn(z, Aval, Sval);
                 }
             }
             // ---- MLP forward ------------------------------------------------------------------------------------------
@@ -362,7 +362,6 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
                 const int abase = tg.acc_off[l] + (amul == 32 ? lane : 0) - tg.off[l] * amul;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                    if (!live[hh]) continue;
                     const float gs = __fmul_rn(D[0][j >> 1][2 * hh + (j & 1)], sc);   // power-of-two scale: exact
                     const float a0 = f0[hh][j], a1 = f1[hh][j];
                     const float g0 = __fsub_rn(1.0f, a0), g1 = __fsub_rn(1.0f, a1);

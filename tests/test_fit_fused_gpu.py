@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
 BWD_TOL = 1e-4
 
 
-def _setup(dev, seed, h=512, w=768, max_res=512):
+def _setup(dev, seed, h=512, w=768, max_res=512, random_coords=False):
     import fit_image
     from shacira_b200.grids import LatentGrid
     torch.manual_seed(seed)
@@ -36,6 +36,8 @@ def _setup(dev, seed, h=512, w=768, max_res=512):
         grid.latent_dec.layers[0].shift.normal_(0, 0.05)
     ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
     coords = torch.stack([(ys.reshape(-1) + 0.5) / h * 2 - 1, (xs.reshape(-1) + 0.5) / w * 2 - 1], 1).float()
+    if random_coords:   # uneven tiles: their last pass is partial
+        coords = torch.rand(h * w, 2) * 2 - 1
     target = torch.rand(h * w, 3)
     return grid.to(dev), mlp.to(dev), coords.to(dev), target.to(dev)
 
@@ -72,11 +74,12 @@ def _run(fs, fused, lat, rflag):
             float(fs.g_dec[:L].double().sum()), float(fs.g_dec[L:].double().sum()))
 
 
-@pytest.mark.parametrize("mode", ["ste", "unrounded"])
+@pytest.mark.parametrize("mode", ["ste", "unrounded", "ste-random-coords"])
 def test_fused_tile_step_matches_three_kernels_and_fp64(lib, mode):
     from shacira_b200.image_fit import ImageFitStep
     dev = torch.device("cuda", 0)
-    grid, mlp, coords, target = _setup(dev, 11)
+    grid, mlp, coords, target = _setup(dev, 11, random_coords=mode.endswith("random-coords"))
+    mode = mode.split("-")[0]
     fs = ImageFitStep(grid, mlp, coords, target)
     assert fs.fused
     lat = grid.codebook.data if mode == "ste" else (grid.codebook.data + 0.37).contiguous()
