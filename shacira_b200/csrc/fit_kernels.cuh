@@ -41,9 +41,6 @@ constexpr int kExpUnset = 127, kExpNan = -128;
 #ifndef SHACIRA_FIT_MIN_CTAS
 #define SHACIRA_FIT_MIN_CTAS 4
 #endif
-#ifndef SHACIRA_FIT_PREFETCH
-#define SHACIRA_FIT_PREFETCH 0   // measured: no gain, 8 registers
-#endif
 
 struct FitSmem {
     uint4 wf[20][32];                          // weight fragments (tc_build_fragments)
@@ -166,9 +163,6 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
         request(beg);
         for (int p0 = beg; p0 < end; p0 += kFitPts) {
             const int base = p0 + warp * 16;
-#if !SHACIRA_FIT_PREFETCH
-            if (p0 > beg) request(p0);
-#endif
             double tu[2][2];
             float T[4];
 #pragma unroll
@@ -178,9 +172,6 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r) T[r] = TN[r];
-#if SHACIRA_FIT_PREFETCH
-            if (p0 + kFitPts < end) request(p0 + kFitPts);
-#endif
             // ---- grid forward: the A fragment of the first layer, entry by entry -------------------------------------
             float X[1][2][4];
             int slot[2][4];
@@ -303,6 +294,10 @@ fit_tile_kernel(const PlanView pv, const float* __restrict__ latents, const __gr
             tc_layer<2, 2, 1>(S.wf, B_GX, lane, h2, D);           // gx = d1 W1: D[0][nt][2 hh + e] <-> level 8 nt + 2 t + e
             __syncwarp();
             tc_wgrad<2, kTcStride, 1>(bufB, bufA, g, t, accW1);   // dW1[i][m] = sum_p d1[p][i] x[p][m]
+            // the next pass's coordinates and targets: requested here, where the MLP's registers are dead, and in flight
+            // behind the maxima, the barrier and the scatter (requested at the top of the pass they cost 8 registers
+            // across the whole MLP: spills, measured slower)
+            if (p0 + kFitPts < end) request(p0 + kFitPts);
 
             // ---- running per-level maximum of |gx| over the tile (this warp's 16 points) -----------------------------------
             // Two copies of the maxima, used by alternating passes: a warp that is already in the next pass adds to the
