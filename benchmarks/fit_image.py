@@ -271,9 +271,37 @@ def fit_native(seed, steps, dev, use_graph, noise_cpu):
     return fit_native_many([seed], steps, dev, use_graph, noise_cpu)[0]
 
 
-def fit(seed, impl, steps, dev, use_graph, noise_cpu, fused_mlp=False):
+def fit_native_sga(seed, steps, dev, decay_period=0.9):
+    """The recipe fit of fit(..., sga=True) through ImageFitStep: same CPU-drawn bit-rate noise and SGA draws (injected)."""
+    grid, mlp, coords, gt, fs = _native_setup(seed, dev, device_noise=False, sga=True)
+    gen = torch.Generator().manual_seed(10_000 + seed)
+    sga_gen = torch.Generator().manual_seed(20_000 + seed)
+    T = grid.codebook.shape[0]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for it in range(steps):
+        fs.set_lambda(1e-4 + 0.5 * (1e-3 - 1e-4) * (1 + math.cos(math.pi * it / steps)))
+        fs.draw_noise(gen)
+        if it + 1 in (1, 2, 5, 10):
+            fs.update_div()
+        on = it < int(decay_period * steps)
+        if on != fs.sga:
+            fs.set_sga(on)
+        fs.set_temperature(sga_temperature(it + 1, steps, 0.1, decay_period), refresh=True)
+        fs.sga_uniforms = torch.rand((T, 1, 2), generator=sga_gen).to(dev) if on else None
+        fs.step()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    return _native_metrics(seed, grid, mlp, coords, gt, fs, ms)
+
+
+def fit(seed, impl, steps, dev, use_graph, noise_cpu, fused_mlp=False, sga=False, decay_period=0.9):
+    """sga=True: the reference's recipe -- SGA sampling (temperature schedule of image_trainer.py:131-137) while
+    it / steps <= decay_period, straight-through rounding afterwards -- with the U(0,1) draws of every step taken from a
+    CPU generator and INJECTED into each arm, so that the arms differ by float ordering only. The "ref" arm then runs the
+    torch definition of the sample (latent_decoders.FORCE_TORCH_SGA) in front of the reference's own kernels."""
     if impl == "native":
-        return fit_native(seed, steps, dev, use_graph, noise_cpu)
+        return fit_native_sga(seed, steps, dev, decay_period) if sga else fit_native(seed, steps, dev, use_graph, noise_cpu)
     from shacira_b200 import grid_ops
     from shacira_b200.grids import LatentGrid
     torch.manual_seed(seed)
@@ -308,10 +336,19 @@ def fit(seed, impl, steps, dev, use_graph, noise_cpu, fused_mlp=False):
     noise_gen = torch.Generator().manual_seed(10_000 + seed)
     noise_buf = torch.zeros((T, 1), device=dev)
     out = {}
+    sga_gen = torch.Generator().manual_seed(20_000 + seed)
+    if sga:
+        assert not use_graph
+        from shacira_b200 import latent_decoders
+        grid.latent_dec.diff_sampling = True
 
     def train_step():
         opt.zero_grad(set_to_none=use_graph)   # captured step: gradients are re-created from the graph's pool, no fills
+        if sga:
+            latent_decoders.FORCE_TORCH_SGA = impl == "ref"
         feats = grid.interpolate(coords, 0)
+        if sga:
+            latent_decoders.FORCE_TORCH_SGA = False
         if fused_mlp:   # MLP + MSE + all their gradients in one kernel
             rgb_loss, pred = grid_ops.mlp_mse_loss(feats, gt, mlp)
         else:
@@ -342,6 +379,11 @@ def fit(seed, impl, steps, dev, use_graph, noise_cpu, fused_mlp=False):
             with torch.no_grad():
                 w = grid.codebook
                 grid.latent_dec.div.data.copy_(torch.max(torch.abs(w.min(dim=0)[0]), torch.abs(w.max(dim=0)[0])))
+        if sga:
+            on = it < int(decay_period * steps)
+            grid.latent_dec.use_sga = on
+            grid.latent_dec.temperature = sga_temperature(it + 1, steps, 0.1, decay_period)
+            grid.latent_dec.sga_uniforms = torch.rand((T, 1, 2), generator=sga_gen).to(dev) if on else None
 
     graph = None
     if use_graph:

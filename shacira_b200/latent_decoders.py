@@ -66,13 +66,16 @@ def _activation(name):
     return table[name]()
 
 
+FORCE_TORCH_SGA = False   # parity runs: the torch definition below also for CUDA tensors (benchmarks/fit_image.py)
+
+
 def sga_quantize(weight, temperature, diff_sampling, uniforms=None):
     """Stochastic Gumbel annealing between floor and ceil (basic_latent_decoder.py:183-191), active for the first
     `decay_period` of training (every shipped yaml: use_sga True, decay_period 0.9). CUDA tensors take the fused
     table-side kernel (shacira_sga_quantize: value + derivative in one pass, noise drawn in the kernel or injected
     through `uniforms` [T, C, 2]); its output feeds the fused grid kernels with rounding disabled. The torch
     expression below is the definition (host tensors, multi decoder)."""
-    if weight.is_cuda and weight.dtype == torch.float32:
+    if weight.is_cuda and weight.dtype == torch.float32 and not FORCE_TORCH_SGA:
         from . import grid_ops
         return grid_ops.sga_quantize(weight, temperature, diff_sampling, uniforms=uniforms)
     wf = torch.floor(weight) if diff_sampling else StraightThroughFloor.apply(weight)
@@ -80,9 +83,20 @@ def sga_quantize(weight, temperature, diff_sampling, uniforms=None):
     lo, hi = -1 + epsilon, 1 - epsilon
     logit_f = -torch.tanh(torch.clamp(weight - wf, min=lo, max=hi)).unsqueeze(-1) / temperature
     logit_c = -torch.tanh(torch.clamp(wc - weight, min=lo, max=hi)).unsqueeze(-1) / temperature
-    dist = torch.distributions.relaxed_categorical.RelaxedOneHotCategorical(
-        temperature, logits=torch.cat((logit_f, logit_c), dim=-1))
-    sample = dist.rsample() if diff_sampling else dist.sample()
+    logits = torch.cat((logit_f, logit_c), dim=-1)
+    if uniforms is None:
+        dist = torch.distributions.relaxed_categorical.RelaxedOneHotCategorical(temperature, logits=logits)
+        sample = dist.rsample() if diff_sampling else dist.sample()
+    else:
+        # RelaxedOneHotCategorical.rsample on given draws (torch/distributions/relaxed_categorical.py: normalised logits,
+        # clamp_probs, Gumbels, (logits + g) / temperature, log-softmax, exp)
+        logits = logits - logits.logsumexp(dim=-1, keepdim=True)
+        eps = torch.finfo(uniforms.dtype).eps
+        u = uniforms.reshape(logits.shape).clamp(min=eps, max=1 - eps)
+        scores = (logits - (-(u.log())).log()) / temperature
+        sample = (scores - scores.logsumexp(dim=-1, keepdim=True)).exp()
+        if not diff_sampling:
+            sample = sample.detach()
     return wf * sample[..., 0] + wc * sample[..., 1]
 
 

@@ -31,6 +31,26 @@ def test_image_fit_psnr_and_bpp_match_reference_kernels(lib):
     assert abs(ours["bpp"] - ref["bpp"]) <= BPP_TOL * ref["bpp"]
 
 
+def test_recipe_fit_sga_then_ste_matches_reference_path(lib):
+    """The reference's RECIPE (kodak.yaml:43-52: SGA sampling with the temperature schedule for the first 90 % of the
+    steps, straight-through rounding afterwards) through the natively fused step against the reference path -- the torch
+    definition of the SGA sample (basic_latent_decoder.py:183-191 on RelaxedOneHotCategorical's rsample) in front of the
+    reference's own kernels, autograd, torch.optim.Adam -- with the SAME injected U(0,1) draws and bit-rate noise."""
+    from oracle import build_ref
+    build_ref.build()
+    if build_ref.load() is None:
+        pytest.skip("oracle/_ref/wisp_ref_ops.so not present")
+    import fit_image
+    dev = torch.device("cuda", 0)
+    steps = 300
+    ours = fit_image.fit(0, "native", steps, dev, use_graph=False, noise_cpu=True, sga=True)
+    ref = fit_image.fit(0, "ref", steps, dev, use_graph=False, noise_cpu=True, sga=True)
+    print("native", ours, "ref", ref)
+    assert ours["psnr"] > 20.0
+    assert abs(ours["psnr"] - ref["psnr"]) <= PSNR_TOL_DB
+    assert abs(ours["bpp"] - ref["bpp"]) <= BPP_TOL * ref["bpp"]
+
+
 def test_whole_step_cuda_graph_matches_eager(lib):
     """The fused ops are CUDA-graph capturable: a captured training step reaches the same quality."""
     import fit_image
