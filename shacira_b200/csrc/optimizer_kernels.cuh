@@ -4,11 +4,14 @@
 // start of the next step, the SGA sample of the latents (basic_latent_decoder.py:183-191). Here:
 //   CTAs [0, S.num)      Adam over the ~20 small tensors (decoder MLP, latent decoder, density model) with their chain
 //                        rules, exactly multi_adam_kernel's per-CTA work;
-//   the remaining CTAs   Adam over the latent table (gradient = grid gradient x d w_hat / d w + (lambda / rows) x bit-rate
-//                        gradient, adam_step_sum_kernel's math) and, with SGA on, the NEXT step's sample of the freshly
-//                        updated latents (w_hat, d w_hat / d w) while they are still in registers -- the table is read and
-//                        written once per step instead of three times (SGA kernel, Adam kernel) and two launches go away;
-//   the last CTA         (arrival ticket) advances the step counters and the SGA draw counter.
+//   the remaining CTAs   one pass over the latent table: optionally the bit-rate loss of the latents before their update
+//                        (latent_grid.py:122-136: entropy_kernel's math and noise stream, latent_dim 1), Adam (gradient =
+//                        grid gradient x d w_hat / d w + (lambda / rows) x bit-rate gradient, adam_step_sum_kernel's math)
+//                        and, with SGA on, the NEXT step's sample of the freshly updated latents (w_hat, d w_hat / d w)
+//                        while they are still in registers -- the table is read and written once per step instead of four
+//                        times (bit-rate kernel, SGA kernel, Adam kernel) and three launches go away;
+//   the last CTA         (arrival ticket) reduces the bit-rate partial sums, runs the density model's Adam segments that
+//                        wait for them, advances the step counters and the draw counters.
 #pragma once
 #include "entropy_kernels.cuh"
 #include "sga_kernels.cuh"

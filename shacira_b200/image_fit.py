@@ -10,15 +10,18 @@ Mirrors `ImageTrainer.step` (wisp/trainers/image_trainer.py:269-359) for the sta
     loss.backward(); optimizer.step()           :321-359, parameter groups base_trainer.py:206-266
 
 In PyTorch terms that step is ~50 kernels (autograd glue, gradient scaling passes over the table, one multi-tensor
-Adam per group). Here it is 9 graph nodes (6 kernels, 3 memsets) and no autograd: the gradients each kernel produces
-are consumed in place --
-the bit-rate gradient joins the grid gradient inside the table's Adam kernel (`shacira_adam_step_sum`, lambda is a
-device scalar), and ONE single-CTA kernel runs Adam over all ~20 small tensors with their chain rules
-(`shacira_multi_adam_step`). The MLP kernel hands the per-column bound of the feature gradients to the tiled
-backward (no second pass over the gradient rows), grid and MLP exchange rows in the plan's tile order (sorted-I/O
-plan, targets permuted once), and with device_noise=True the bit-rate kernel draws its own training noise. The
-whole step is CUDA-graph capturable; `set_lambda` / `draw_noise` / `update_div` are the host-side schedule hooks of
-the trainer (image_trainer.py:131-137,284-296).
+Adam per group). Here it is TWO launches (+ one 2.4 KB memset) and no autograd:
+  * shacira_fit_tile_step -- grid forward + decoder MLP + MSE + grid backward in one tile-resident kernel
+    (csrc/fit_kernels.cuh): the [N, 16] feature rows and their gradient never leave the SM;
+  * shacira_fit_optimizer_step -- everything table-side in one launch (csrc/optimizer_kernels.cuh): the bit-rate loss of
+    the latents (value + gradients; the latents' bit-rate gradient goes straight into the table's Adam, lambda is a device
+    scalar), Adam over the table and over all ~20 small tensors with their chain rules, and the NEXT step's SGA sample of
+    the freshly updated latents.
+Shapes outside the fused kernels' (latent_dim / feature_dim != 1, levels that do not fit a tile, injected SGA draws) keep
+the separate launches: tiled forward -> tensor-core MLP -> tiled backward, bit-rate kernel on a forked stream, SGA kernel.
+Grid and MLP exchange rows in the plan's tile order (sorted-I/O plan, targets permuted once), and with device_noise=True
+the bit-rate noise is drawn in the kernel. The whole step is CUDA-graph capturable; `set_lambda` / `set_temperature` /
+`set_sga` / `draw_noise` / `update_div` are the host-side schedule hooks of the trainer (image_trainer.py:131-137,284-296).
 
 The module parameters stay the single source of truth: the kernels read and update the storage of
 `grid.codebook`, `grid.latent_dec.layers[0].{scale,shift}`, `grid.prob_model.f*.{h,b,a}` and the MLP in place, so

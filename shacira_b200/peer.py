@@ -253,11 +253,14 @@ class PeerTable:
         self.buf = PeerBuffer(init.numel(), dev)
         self.buf.flat[:init.numel()].copy_(init.reshape(-1))
         self.data = self.buf.flat[:init.numel()].view(self.shape)
+        self.m = self.v = self.step = None
         if connect:
             self.buf.connect(group)
-        self._init_state(arena_numel)
+            self.init_state(arena_numel)
 
-    def _init_state(self, arena_numel):
+    def init_state(self, arena_numel):
+        """Allocate this rank's slice of the Adam state. Called by the constructor after connect(); a single-process
+        caller (connect=False, then buf.connect_local) calls it once the world size is known."""
         # the exchange kernel splits the ARENA (table gradient + small gradients) into `world` slices of float4 pieces
         w, r = self.buf.world, self.buf.rank
         n4 = ((int(arena_numel) + 3) & ~3) // 4
