@@ -21,21 +21,24 @@ import torch
 
 from .. import _lib
 
-_host_cache = {}
+_host_cache = {}   # key -> (the tensor itself, its host copy)
 
 
 def _host_ints(t):
-    """Host copy of a small int tensor (first_idx), cached on (ptr, version) to avoid a sync per call."""
+    """Host copy of a small int tensor (first_idx: the reference passes it as a DEVICE tensor on every call), cached to
+    avoid a device synchronisation per call. The entry HOLDS the tensor: its storage cannot be freed and handed to
+    another tensor while the entry lives, so (pointer, version) identifies the contents -- a key without the reference
+    goes stale as soon as the caching allocator recycles the address for a different first_idx."""
     if not isinstance(t, torch.Tensor):
         return tuple(int(v) for v in t)
     key = (t.data_ptr(), t._version, t.numel(), str(t.device))
     got = _host_cache.get(key)
-    if got is None:
-        got = tuple(int(v) for v in t.detach().cpu().tolist())
-        if len(_host_cache) > 256:
+    if got is None or got[0].data_ptr() != t.data_ptr():
+        if len(_host_cache) >= 64:
             _host_cache.clear()
+        got = (t.detach(), tuple(int(v) for v in t.detach().cpu().tolist()))
         _host_cache[key] = got
-    return got
+    return got[1]
 
 
 _eye_cache = {}

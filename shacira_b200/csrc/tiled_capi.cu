@@ -112,9 +112,16 @@ int launch_fwd(shacira_plan* p, const float* lat, const LevelParams& lp, const f
     const int cap = node_capacity(p, lp, smem_budget() / (4 * C));
     const int rc_tab = ensure_node_table(p, lp, s);
     if (rc_tab) return rc_tab;
-    const size_t smem = smem_pad(sizeof(float) * ((size_t)cap * C + nA * C * F + nA * F));
+    size_t smem = sizeof(float) * ((size_t)cap * C + nA * C * F + nA * F);
+    // scattered rows (original point order) of 16..64 floats: collected per batch in shared memory and written as whole rows
+    static const int rows_knob = [] { const char* e = getenv("SHACIRA_FWD_ROWS_SMEM"); return e ? atoi(e) : 1; }();
+    const int RL = lp.num_lods * F;
+    const size_t rows_bytes = ((smem + 15) & ~(size_t)15) - smem + sizeof(float) * (size_t)kTileThreads * kPts * (RL + 4 + 1);
+    const int rows_via_smem = rows_knob && !p->sorted_io && RL % 4 == 0 && RL <= 64 && smem + rows_bytes <= 46 * 1024;
+    if (rows_via_smem) smem += rows_bytes;
+    smem = smem_pad(smem);
     latent_fwd_tiled_kernel<D, C, F><<<p->ntiles, kTileThreads, smem, s>>>(view_of(p), lat, lp, A, shift, per_level,
-                                                                            round_flag, feats, cap);
+                                                                            round_flag, feats, cap, rows_via_smem);
     LAUNCHED();
     return SHACIRA_OK;
 }

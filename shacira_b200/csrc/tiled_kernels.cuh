@@ -543,7 +543,7 @@ template <int D, int C, int F>
 __global__ void __launch_bounds__(kTileThreads, (C * F <= 4) ? SHACIRA_MIN_CTAS : 3)
 latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, const __grid_constant__ LevelParams lp,
                         const float* __restrict__ A, const float* __restrict__ shift, int per_level, int round_flag,
-                        float* __restrict__ feats, int cap) {
+                        float* __restrict__ feats, int cap, int rows_via_smem) {
     extern __shared__ float s_dyn[];
     __shared__ TileGeom<D> tg;
     const int L = lp.num_lods;
@@ -551,6 +551,12 @@ latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, co
     float* s_nodes = s_dyn;                  // [cap][C]
     float* s_A = s_dyn + (size_t)cap * C;    // [nA][C][F]
     float* s_shift = s_A + nA * C * F;       // [nA][F]
+    // rows_via_smem (rows go back to their ORIGINAL index, i.e. scattered): a batch's rows are collected in shared memory
+    // and written as whole contiguous rows by neighbouring threads, instead of one 16-byte piece per thread and level
+    // chunk -- every row then reaches L2 as full sectors in one request
+    const int RL = L * F, RS = RL + 4;       // row length / padded stride (floats): conflict-free 16-byte accesses
+    float* s_rows = s_dyn + (((size_t)cap * C + nA * C * F + nA * F + 3) & ~(size_t)3);   // [kTileThreads * kPts][RS]
+    int* s_orig = reinterpret_cast<int*>(s_rows + (size_t)kTileThreads * kPts * RS);      // [kTileThreads * kPts]
     const int tile = blockIdx.x;
     const int beg = pv.tile_off[tile], end = pv.tile_off[tile + 1];
     if (beg == end) return;
@@ -622,8 +628,23 @@ latent_fwd_tiled_kernel(const PlanView pv, const float* __restrict__ latents, co
                         o[q * F + jf] = acc;
                     }
                 }
-                store_row<kLv * F>(feats + (int64_t)orig[k] * L * F + l0 * F, o);
+                if (rows_via_smem) store_row<kLv * F>(s_rows + (size_t)(k * kTileThreads + threadIdx.x) * RS + l0 * F, o);
+                else store_row<kLv * F>(feats + (int64_t)orig[k] * L * F + l0 * F, o);
             }
+        }
+        if (rows_via_smem) {
+#pragma unroll
+            for (int k = 0; k < kPts; ++k) s_orig[k * kTileThreads + threadIdx.x] = orig[k];
+            __syncthreads();
+            const int pieces = RL >> 2;   // 16-byte pieces per row
+            for (int idx = threadIdx.x; idx < kTileThreads * kPts * pieces; idx += kTileThreads) {
+                const int r = idx / pieces, pc = idx - r * pieces;
+                const int og = s_orig[r];
+                if (og >= 0)
+                    *reinterpret_cast<float4*>(feats + (int64_t)og * RL + 4 * pc) =
+                        *reinterpret_cast<const float4*>(s_rows + (size_t)r * RS + 4 * pc);
+            }
+            __syncthreads();
         }
     }
 }

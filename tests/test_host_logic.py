@@ -240,3 +240,14 @@ def test_codec_container_round_trip_and_size_accounting(lib):
     bad[first_stream + 40] ^= 0x10
     with pytest.raises((ValueError, lib.ShaciraError)):
         codec.decode_model(bytes(bad))
+
+
+def test_first_idx_host_cache_survives_address_reuse():
+    """The shim caches the host copy of a device / tensor first_idx (the reference passes a tensor on every call). A new
+    tensor that the allocator places at a freed tensor's address must not be served the old contents."""
+    import torch
+    from shacira_b200._C.ops import _host_ints
+    for i in range(200):
+        t = torch.arange(16, dtype=torch.int32) * (i + 1)
+        assert _host_ints(t) == tuple(int(v) for v in t.tolist())
+        del t
