@@ -57,6 +57,14 @@ def _worker(rank, world, port, out):
     ok &= a.grad.data_ptr() == arena.flat.data_ptr() and arena.flat.numel() == 2015
     arena.zero_()
     ok &= not bool(a.grad.any()) and not bool(b2.grad.any())
+    # the peer-memory arenas need CUDA IPC: on a host without a GPU every rank must AGREE to fall back (None on all
+    # ranks, the gradients still attached to nothing), never one rank with an arena and one without
+    from shacira_b200 import peer
+    c1, c2 = torch.nn.Parameter(torch.zeros(64, 1)), torch.nn.Parameter(torch.zeros(3))
+    ok &= peer.PeerArena.try_create([c1, c2]) is None and peer.McArena.try_create([c1, c2]) is None
+    fallback = dp.GradArena([c1, c2])
+    c1.grad.fill_(float(rank + 1))
+    ok &= fallback.allreduce() == 1 and bool((c1.grad == 3.0).all())
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
