@@ -491,7 +491,7 @@ def main():
     # pinned host memory in, the step's loss out): the natively fused fit step keeps table, decoder, MLP and optimizer
     # state on the device, so per step only the batch's targets cross PCIe (4.7 MB) and 8 bytes of loss come back --
     # against 53 MB per step when a host-side consumer wants the feature rows (the `e2e` entry above).
-    e2e_fit = None
+    e2e_fit = fit_tile = None
     if not args.no_fit and not args.no_plan:
         try:
             import fit_image
@@ -501,19 +501,38 @@ def main():
             fs.set_lambda(5e-4)
             fs.set_temperature(0.5)
             fstream = torch.cuda.Stream(device=dev)
+            cstream = torch.cuda.Stream(device=dev)      # uploads: step i + 1's targets travel while step i runs
+            tbuf = [fs.target, torch.empty_like(fs.target)]
+            gfit, uploaded, consumed = [], [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
             with torch.cuda.stream(fstream):
                 for _ in range(3):
                     fs.step()
                 fstream.synchronize()
-                gfit = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gfit, stream=fstream):
-                    fs.step()
+                for b in range(2):                       # one captured step per target buffer
+                    fs.target = tbuf[b]
+                    g_ = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_, stream=fstream):
+                        fs.step()
+                    gfit.append(g_)
+                fs.target = tbuf[0]
+
+                loss_dev = fs.mlp_out[:2].view(torch.float64)                    # views made once: the loop is host bound
+                loss_slot = [loss_host[0:1], loss_host[1:2]]
+                cctx = torch.cuda.stream(cstream)
 
                 def fit_e2e(count):
+                    for b in range(2):
+                        consumed[b].record(fstream)
                     for i in range(count):
-                        fs.target.copy_(h_gt[i % 2], non_blocking=True)         # this step's targets, host -> device
-                        gfit.replay()
-                        loss_host[i % 2:i % 2 + 1].copy_(fs.mlp_out[:2].view(torch.float64), non_blocking=True)
+                        b = i & 1
+                        with cctx:
+                            cstream.wait_event(consumed[b])                     # the step that last read this buffer is done
+                            tbuf[b].copy_(h_gt[b], non_blocking=True)           # this step's targets, host -> device
+                            uploaded[b].record(cstream)
+                        fstream.wait_event(uploaded[b])
+                        gfit[b].replay()
+                        consumed[b].record(fstream)
+                        loss_slot[b].copy_(loss_dev, non_blocking=True)
                         if i % 8 == 7:
                             fstream.synchronize()                               # the host reads the losses in small batches
                     fstream.synchronize()
@@ -521,20 +540,60 @@ def main():
                 fit_e2e(16)
                 if world > 1:
                     dist.barrier()
-                t0 = time.perf_counter()
-                fit_steps = 200
-                fit_e2e(fit_steps)
-                fit_s = time.perf_counter() - t0
+                # three timed batches, the median one reported: this leg is bound by the HOST side of the loop (six CUDA calls
+                # per step from Python) and its wall clock is jittery (0.16 ... 0.45 ms per step seen for one batch)
+                fit_steps, batches = 100, []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    fit_e2e(fit_steps)
+                    batches.append(time.perf_counter() - t0)
+                fit_s = sorted(batches)[1]
             tfit = torch.tensor([fit_s], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(tfit, op=dist.ReduceOp.MAX)
             fit_s = float(tfit.item())
+            # the fused tile kernel of that step alone (grid forward + decoder MLP / MSE + grid backward
+            # in one launch, feature rows never in HBM): device time over a graph of 20 launches
+            try:
+                Pp, lin = _lib._ptr, fs.lin
+                sh = fs.layer.shift.data if fs.has_shift else None
+
+                def tile_step(st_):
+                    _lib._check(lib.shacira_fit_tile_step(
+                        fs.plan.handle, Pp(fs.grid.codebook.data), fs.fi, fs.rs, fs.L, fs.bw, 1, Pp(fs.A), Pp(sh),
+                        Pp(fs.target), Pp(lin[0].weight.data), Pp(lin[0].bias.data), Pp(lin[1].weight.data),
+                        Pp(lin[1].bias.data), Pp(lin[2].weight.data), Pp(lin[2].bias.data), fs.T, Pp(fs.g_grid),
+                        Pp(fs.g_dec), Pp(fs.g_dec[fs.L:]), Pp(fs.mlp_out), st_))
+                with torch.cuda.stream(fstream):
+                    tile_step(ctypes.c_void_p(fstream.cuda_stream))
+                    fstream.synchronize()
+                    gt_ = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gt_, stream=fstream):
+                        for _ in range(20):
+                            tile_step(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                    gt_.replay()
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                    gt_.replay()
+                    ev1.record()
+                    fstream.synchronize()
+                    tile_ms = ev0.elapsed_time(ev1) / 20
+                bpp_alg = sum(algorithmic_bytes_per_point(DIM, L, LATENT_DIM, FEATURE_DIM))
+                fit_tile = {"ms": tile_ms, "what": "shacira_fit_tile_step: grid forward + decoder MLP / MSE + grid backward, one launch",
+                            "algorithmic_GBs": bpp_alg * n / tile_ms / 1e6, "bytes_per_point": bpp_alg,
+                            "dram_bytes_per_launch_ncu": 22004480,
+                            "note": "ncu: 22 MB of DRAM traffic per launch (profiles/r02r_ncu_fit_fused_summary.txt) against "
+                                    "~170 MB for the three launches it replaces (96 us); bound by instruction issue / "
+                                    "latency of the MLP and lerp chains at 16 warps per SM, not by memory"}
+            except Exception as e:
+                fit_tile = {"unavailable": repr(e)[:200]}
             fs.close()
             e2e_fit = {"value": n * world * fit_steps / fit_s / 1e6, "unit": "Mpoints/s", "ms_per_step": fit_s / fit_steps * 1e3,
                        "h2d_bytes_per_step": int(gt_f.numel() * 4), "d2h_bytes_per_step": 8, "steps": fit_steps,
+                       "batches_ms_per_step": [round(b / fit_steps * 1e3, 4) for b in batches],
                        "api": "shacira_b200.image_fit.ImageFitStep (SGA phase, CUDA graph): targets from pinned host "
-                              "memory every step, loss read back; grid fwd + bwd + decoder MLP / MSE + bit-rate loss + "
-                              "Adam per step"}
+                              "memory every step (two device buffers: the next step's upload runs beside this step), loss "
+                              "read back; grid fwd + bwd + decoder MLP / MSE + bit-rate loss + Adam per step"}
         except Exception as e:
             e2e_fit = {"unavailable": repr(e)[:200]}
 
@@ -585,7 +644,7 @@ def main():
                 "api": "shacira_host_session_* (C-ABI, pinned host buffers in and out, two steps in flight; static "
                        "coordinate set uploaded and binned once; table + decoder + gradient rows up, feature rows + "
                        "table / decoder gradients down every step)"},
-        "e2e_fit": e2e_fit, "gpu_launches": int(launches), "clocks": clocks,
+        "e2e_fit": e2e_fit, "fit_tile_kernel": fit_tile, "gpu_launches": int(launches), "clocks": clocks,
         "path": "point-parallel (no plan)" if args.no_plan else "tiled (spatial plan, built once per coordinate set)",
         "kodak_fit": kodak_fit, "nerf_dp": nerf, "plan_ms": plan_ms, "launch": "host loop" if args.no_graph else "one CUDA graph of K steps, replayed",
     }
