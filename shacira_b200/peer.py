@@ -71,7 +71,7 @@ class PeerBuffer:
         """Single process, several GPUs: `buffers` = the PeerBuffers of all ranks in rank order (peer access enabled)."""
         self.rank, self.world = int(rank), len(buffers)
         for b in buffers:
-            if b is not self:
+            if b is not self and b.device != self.device:
                 _lib._check(self.lib.shacira_peer_enable_access(self.device.index, b.device.index))
         self.ptrs = [b.ptr for b in buffers]
         return self
